@@ -1,0 +1,8 @@
+"""cocg -- B200 (sm_100a) kernels behind collaborative-circom's MPC proving hot path.
+
+The directory name carries a hyphen (it mirrors the reference's name), so import it with
+``importlib.import_module("collaborative-circom_b200")`` or through the ``cocg`` shim at the repo root.
+"""
+from ._lib import (BN254, BLS12_381, G1, G2, OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_TO_MONT, OP_FROM_MONT,  # noqa: F401
+                   EC_ADD, EC_MUL, EC_TO_AFFINE, EC_FROM_AFFINE, EC_NEG, EC_DBL, SYMBOLS, LIB_PATH, CocgError, load)
+from .context import Context, DeviceVec  # noqa: F401

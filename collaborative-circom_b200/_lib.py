@@ -1,0 +1,75 @@
+"""ctypes binding of libcocg.so (the C ABI declared in include/cocg.h).
+
+The library is the product; there is no CPU path.  Loading fails loudly when the shared object is missing
+and `Context()` fails loudly when no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcocg.so")
+
+BN254, BLS12_381 = 0, 1
+G1, G2 = 1, 2
+OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_TO_MONT, OP_FROM_MONT = range(6)
+EC_ADD, EC_MUL, EC_TO_AFFINE, EC_FROM_AFFINE, EC_NEG, EC_DBL = range(6)
+
+# every symbol include/cocg.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "cocg_create", "cocg_destroy", "cocg_last_error", "cocg_version", "cocg_set_stream", "cocg_sync",
+    "cocg_launch_count", "cocg_malloc", "cocg_free", "cocg_h2d", "cocg_d2h", "cocg_memset0", "cocg_vec_op",
+    "cocg_vec_scale_powers", "cocg_rep3_mul_local", "cocg_ntt", "cocg_bases_upload", "cocg_bases_free",
+    "cocg_msm", "cocg_msm_host", "cocg_csr_upload", "cocg_csr_free", "cocg_spmv", "cocg_ec_op",
+]
+
+_lib = None
+
+
+class CocgError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcocg.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CocgError(f"{LIB_PATH} is missing: build it with `make -C {_HERE}/csrc` (there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, ci, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+    pvp = ctypes.POINTER(ctypes.c_void_p)
+    sig = {
+        "cocg_create": (ci, [pvp, ci, ci]),
+        "cocg_destroy": (None, [vp]),
+        "cocg_last_error": (ctypes.c_char_p, [vp]),
+        "cocg_version": (ci, []),
+        "cocg_set_stream": (ci, [vp, vp]),
+        "cocg_sync": (ci, [vp]),
+        "cocg_launch_count": (u64, [vp]),
+        "cocg_malloc": (ci, [vp, sz, pvp]),
+        "cocg_free": (ci, [vp, vp]),
+        "cocg_h2d": (ci, [vp, vp, vp, sz]),
+        "cocg_d2h": (ci, [vp, vp, vp, sz]),
+        "cocg_memset0": (ci, [vp, vp, sz]),
+        "cocg_vec_op": (ci, [vp, ci, vp, vp, vp, sz]),
+        "cocg_vec_scale_powers": (ci, [vp, vp, sz, vp, vp]),
+        "cocg_rep3_mul_local": (ci, [vp, vp, vp, vp, vp, vp, vp, sz]),
+        "cocg_ntt": (ci, [vp, pvp, ci, ctypes.c_uint, vp, ci, vp]),
+        "cocg_bases_upload": (ci, [vp, ci, vp, sz, sz, ci, ctypes.POINTER(u64)]),
+        "cocg_bases_free": (ci, [vp, u64]),
+        "cocg_msm": (ci, [vp, u64, sz, sz, pvp, ci, ci, vp]),
+        "cocg_msm_host": (ci, [vp, u64, sz, sz, pvp, ci, ci, vp]),
+        "cocg_csr_upload": (ci, [vp, vp, vp, vp, sz, sz, ctypes.POINTER(u64)]),
+        "cocg_csr_free": (ci, [vp, u64]),
+        "cocg_spmv": (ci, [vp, u64, vp, sz, vp, vp]),
+        "cocg_ec_op": (ci, [vp, ci, ci, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L

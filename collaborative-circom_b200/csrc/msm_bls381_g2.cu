@@ -1,0 +1,7 @@
+// One (curve, group) instantiation of the MSM pipeline per translation unit, so that they compile in parallel.
+#include "msm_impl.cuh"
+namespace cocg {
+int msm_bls381_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac) {
+  return msm_impl<Bls381Fq2, Bls381FrP>(ctx, be, off, n, scalars, k, mont, out_jac);
+}
+}  // namespace cocg

@@ -1,0 +1,150 @@
+// Element-wise share-vector kernels and the power-table builder.
+//
+// Reference call sites replaced (paths under /root/reference):
+//   add_vec / sub_assign_vec / neg_vec_in_place      mpc-core/src/protocols/rep3.rs:581-593, 634-648, 672-679
+//   mul_vec local step                               mpc-core/src/protocols/rep3.rs:656-660 (shamir.rs:618-621, plain.rs:224)
+//   distribute_powers_and_mul_by_const               mpc-core/src/protocols/rep3.rs:681-688
+// The reference runs these as serial iterators on one core; here one thread owns one 32-byte element
+// (two 128-bit loads per operand, a warp covers 1 KiB contiguous per operand), grids are a multiple of the
+// 148 SMs and grid-stride over the vector.  add/sub/neg are HBM-bound (96 B/element); the multiplications
+// are bound by the integer-multiply pipe.
+#include <string.h>
+
+#include "ctx.cuh"
+
+namespace cocg {
+
+template <class P, int OP>
+__global__ void __launch_bounds__(256) vec_op_kernel(const void* __restrict__ a, const void* __restrict__ b,
+                                                      void* __restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fp<P> x = load_fp<P>(a, i);
+    Fp<P> r;
+    if (OP == COCG_OP_MUL) r = fp_mul(x, load_fp<P>(b, i));
+    else if (OP == COCG_OP_ADD) r = fp_add(x, load_fp<P>(b, i));
+    else if (OP == COCG_OP_SUB) r = fp_sub(x, load_fp<P>(b, i));
+    else if (OP == COCG_OP_NEG) r = fp_neg(x);
+    else if (OP == COCG_OP_TO_MONT) r = fp_to_mont(x);
+    else r = fp_from_mont(x);
+    store_fp<P>(out, i, r);
+  }
+}
+
+// out[i] = aa*ba + aa*bb + ab*ba (+ mask)  ==  aa*(ba+bb) + ab*ba (+ mask): two products instead of three,
+// same value mod r, hence bit-identical canonical output.
+template <class P, bool MASK>
+__global__ void __launch_bounds__(256) rep3_mul_local_kernel(const void* __restrict__ aa, const void* __restrict__ ab,
+                                                              const void* __restrict__ ba, const void* __restrict__ bb,
+                                                              const void* __restrict__ mask, void* __restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fp<P> xa = load_fp<P>(aa, i), xb = load_fp<P>(ab, i), ya = load_fp<P>(ba, i), yb = load_fp<P>(bb, i);
+    Fp<P> r = fp_add(fp_mul(xa, fp_add(ya, yb)), fp_mul(xb, ya));
+    if (MASK) r = fp_add(r, load_fp<P>(mask, i));
+    store_fp<P>(out, i, r);
+  }
+}
+
+// out[i] = first * base^i.  Thread t owns a run of RUN consecutive exponents: one square-and-multiply to
+// reach base^(t*RUN), then RUN-1 dependent products.
+constexpr int kPowRun = 32;
+template <class P>
+__global__ void __launch_bounds__(128) powers_kernel(void* __restrict__ out, size_t n, Fp<P> base, Fp<P> first) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * kPowRun;
+  if (lo >= n) return;
+  Fp<P> pw = fp_mul(first, fp_pow_u64(base, (uint64_t)lo));
+  size_t hi = lo + kPowRun < n ? lo + kPowRun : n;
+  for (size_t i = lo; i < hi; i++) {
+    store_fp<P>(out, i, pw);
+    pw = fp_mul(pw, base);
+  }
+}
+
+template <class P>
+static int powers_table_impl(cocg_ctx* ctx, uint32_t kind, size_t n, const uint32_t* base, const uint32_t* first, void** out) {
+  std::array<uint32_t, 18> key;
+  key[0] = kind;
+  key[1] = (uint32_t)n;
+  for (int i = 0; i < 8; i++) { key[2 + i] = base[i]; key[10 + i] = first[i]; }
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) { *out = it->second; return 0; }
+  void* d = nullptr;
+  COCG_CUDA(ctx, cudaMalloc(&d, (n ? n : 1) * sizeof(Fp<P>)));
+  Fp<P> b, f;
+  for (int i = 0; i < 8; i++) { b.l[i] = base[i]; f.l[i] = first[i]; }
+  size_t threads = (n + kPowRun - 1) / kPowRun;
+  if (n) {
+    powers_kernel<P><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(d, n, b, f);
+    COCG_LAUNCH_CHECK(ctx);
+  }
+  ctx->tables[key] = d;
+  *out = d;
+  return 0;
+}
+int powers_table(cocg_ctx* ctx, uint32_t kind, size_t n, const uint32_t* base, const uint32_t* first, void** out) {
+  return ctx->curve == COCG_BN254 ? powers_table_impl<Bn254FrP>(ctx, kind, n, base, first, out)
+                                  : powers_table_impl<Bls381FrP>(ctx, kind, n, base, first, out);
+}
+
+template <class P>
+static int vec_op_impl(cocg_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n) {
+  if (n == 0) return 0;
+  int grid = grid_for(n, 256, 8);
+  switch (op) {
+    case COCG_OP_MUL: vec_op_kernel<P, COCG_OP_MUL><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case COCG_OP_ADD: vec_op_kernel<P, COCG_OP_ADD><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case COCG_OP_SUB: vec_op_kernel<P, COCG_OP_SUB><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case COCG_OP_NEG: vec_op_kernel<P, COCG_OP_NEG><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case COCG_OP_TO_MONT: vec_op_kernel<P, COCG_OP_TO_MONT><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    case COCG_OP_FROM_MONT: vec_op_kernel<P, COCG_OP_FROM_MONT><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
+    default: return fail(ctx, "cocg_vec_op: unknown op");
+  }
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+template <class P>
+static int rep3_mul_local_impl(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
+                               const void* mask, void* out, size_t n) {
+  if (n == 0) return 0;
+  int grid = grid_for(n, 256, 8);
+  if (mask) rep3_mul_local_kernel<P, true><<<grid, 256, 0, ctx->stream>>>(aa, ab, ba, bb, mask, out, n);
+  else rep3_mul_local_kernel<P, false><<<grid, 256, 0, ctx->stream>>>(aa, ab, ba, bb, mask, out, n);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace cocg
+
+using namespace cocg;
+
+extern "C" int cocg_vec_op(cocg_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!a || !out || ((op == COCG_OP_MUL || op == COCG_OP_ADD || op == COCG_OP_SUB) && !b))
+    return n == 0 ? 0 : fail(ctx, "cocg_vec_op: null operand");
+  return COCG_FR_DISPATCH(ctx, vec_op_impl, ctx, op, a, b, out, n);
+}
+
+extern "C" int cocg_rep3_mul_local(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
+                                   const void* mask, void* out, size_t n) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n && (!aa || !ab || !ba || !bb || !out)) return fail(ctx, "cocg_rep3_mul_local: null operand");
+  return COCG_FR_DISPATCH(ctx, rep3_mul_local_impl, ctx, aa, ab, ba, bb, mask, out, n);
+}
+
+extern "C" int cocg_vec_scale_powers(cocg_ctx* ctx, void* x, size_t n, const void* g, const void* c) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  if (!x || !g || !c) return fail(ctx, "cocg_vec_scale_powers: null operand");
+  void* tab = nullptr;
+  uint32_t gl[8], cl[8];
+  memcpy(gl, g, 32);
+  memcpy(cl, c, 32);
+  COCG_TRY(powers_table(ctx, /*kind=*/1, n, gl, cl, &tab));
+  return cocg_vec_op(ctx, COCG_OP_MUL, x, tab, x, n);
+}

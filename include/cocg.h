@@ -1,0 +1,126 @@
+/* cocg -- C ABI of the B200 (sm_100a) kernels behind collaborative-circom's MPC proving path.
+ *
+ * The reference (pure Rust) has no FFI; its operator seam is the trait set in
+ * /root/reference/mpc-core/src/traits.rs consumed by CoGroth16<T,P> / CoPlonk<T,P>.  Every entry point below
+ * is what a Rust `impl {MSMProvider, FFTProvider, PrimeFieldMpcProtocol} for {Rep3Protocol, ShamirProtocol,
+ * PlainDriver}` would bind through `extern "C"` (see INTEGRATION.md for the binding), and names the trait
+ * method / impl (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *  - All functions return 0 on success, nonzero on failure; cocg_last_error() gives the message.  Nothing
+ *    throws or aborts across the boundary (the reference's compute ops are infallible, traits.rs:535-568).
+ *  - One cocg_ctx per driver / thread (the reference's drivers are `&mut self`, traits.rs:43); contexts are
+ *    independent and may be used concurrently from different threads.  Work is enqueued on the context's CUDA
+ *    stream; entry points taking HOST pointers synchronise before returning, entry points taking DEVICE
+ *    pointers are asynchronous until cocg_sync().
+ *  - Field elements: 32 bytes (Fr of either curve), little-endian limbs, MONTGOMERY form (R = 2^256) -- the
+ *    in-memory layout of arkworks' Fp<MontBackend<_,4>> a Rust caller holds.  Share vectors are plain arrays
+ *    of such elements, one array per share component (the reference's SoA Rep3PrimeFieldShareVec{a,b},
+ *    mpc-core/src/protocols/rep3/fieldshare.rs:232-236).
+ *  - Affine points: x | y (G2: x.c0 | x.c1 | y.c0 | y.c1), each coordinate 32 B (BN254) / 48 B (BLS12-381)
+ *    Montgomery limbs; all-zero = point at infinity (zkey layout, circom-types/src/traits.rs:107-155).
+ *  - Jacobian points (outputs): X | Y | Z in the same coordinate encoding; Z == 0 is infinity.  Equality is
+ *    group equality (X/Z^2, Y/Z^3) as for arkworks' Projective.
+ */
+#ifndef COCG_H
+#define COCG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define COCG_API __attribute__((visibility("default")))
+#else
+#define COCG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cocg_ctx cocg_ctx;
+
+enum { COCG_BN254 = 0, COCG_BLS12_381 = 1 };
+enum { COCG_G1 = 1, COCG_G2 = 2 };
+/* element-wise ops (cocg_vec_op) */
+enum { COCG_OP_MUL = 0, COCG_OP_ADD = 1, COCG_OP_SUB = 2, COCG_OP_NEG = 3, COCG_OP_TO_MONT = 4, COCG_OP_FROM_MONT = 5 };
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+COCG_API int cocg_create(cocg_ctx** out, int device, int curve);
+COCG_API void cocg_destroy(cocg_ctx* ctx);
+COCG_API const char* cocg_last_error(cocg_ctx* ctx); /* ctx may be NULL: error of the last failed cocg_create */
+COCG_API int cocg_version(void);
+/* Use an externally owned cudaStream_t (e.g. the torch current stream); NULL restores the context's own. */
+COCG_API int cocg_set_stream(cocg_ctx* ctx, void* cuda_stream);
+COCG_API int cocg_sync(cocg_ctx* ctx);
+/* Number of kernel launches issued by this context since creation (bench.py's `gpu_launches`). */
+COCG_API uint64_t cocg_launch_count(cocg_ctx* ctx);
+
+/* ---- device memory (so that share vectors can stay resident between MPC network rounds) ------------- */
+COCG_API int cocg_malloc(cocg_ctx* ctx, size_t bytes, void** dptr);
+COCG_API int cocg_free(cocg_ctx* ctx, void* dptr);
+COCG_API int cocg_h2d(cocg_ctx* ctx, void* dptr, const void* hptr, size_t bytes); /* synchronous */
+COCG_API int cocg_d2h(cocg_ctx* ctx, void* hptr, const void* dptr, size_t bytes); /* synchronous */
+COCG_API int cocg_memset0(cocg_ctx* ctx, void* dptr, size_t bytes);
+
+/* ---- a7: element-wise share-vector arithmetic (DEVICE pointers, n elements) --------------------------
+ * Replaces PrimeFieldMpcProtocol::{add_vec, sub_assign_vec, neg_vec_in_place, mul (plain/Shamir local)}
+ * traits.rs:67,146-149,161; rep3.rs:581-593,634-648,672-679; plain.rs:111-285.  `out` may alias `a`/`b`. */
+COCG_API int cocg_vec_op(cocg_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n);
+/* a5: x[i] <- x[i] * c * g^i.  Replaces distribute_powers_and_mul_by_const traits.rs:177, rep3.rs:681-688.
+ * g, c: HOST pointers to one Montgomery Fr each. */
+COCG_API int cocg_vec_scale_powers(cocg_ctx* ctx, void* x, size_t n, const void* g, const void* c);
+/* a6: REP3 mul_vec local step out[i] = aa*ba + aa*bb + ab*ba + mask[i] (mask may be NULL).
+ * Replaces rep3.rs:656-660; the send_next/recv_prev round (rep3.rs:661-662) stays with the caller. */
+COCG_API int cocg_rep3_mul_local(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
+                        const void* mask, void* out, size_t n);
+
+/* ---- a4 (+a5): in-order radix-2 NTT over Fr, in place (DEVICE pointers) -------------------------------
+ * Replaces FFTProvider::{fft_in_place, ifft_in_place} traits.rs:535-555; rep3.rs:880-921, shamir.rs:826-863,
+ * plain.rs:369-400.  vecs: k device pointers (HOST array), each 2^log_n elements (k = 2 for a REP3 share
+ * vector, 1 for Shamir / plain).  root: HOST pointer to the domain generator (Montgomery) -- the caller's
+ * `domain.group_gen`, i.e. the snarkjs root for Groth16 (groth16.rs:62-71).  inverse != 0 computes the
+ * inverse transform (uses root^-1, scales by n^-1).  coset_g: NULL, or HOST pointer to g; fuses
+ * distribute_powers_and_mul_by_const(c = 1): forward -> input is pre-scaled by g^i, inverse -> output is
+ * post-scaled by g^i (the ifft; distribute_powers pair of groth16.rs:175-186). */
+COCG_API int cocg_ntt(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, const void* root, int inverse,
+             const void* coset_g);
+
+/* ---- a1: variable-base MSM over resident public bases -------------------------------------------------
+ * Replaces MSMProvider::msm_public_points traits.rs:561-568; rep3.rs:934-947, shamir.rs:1027-1039,
+ * plain.rs:408-416 (-> ark-ec msm_unchecked).  Bases are uploaded once per zkey query (the reference
+ * borrows &ZKey for the whole prove, groth16.rs:113-117) and addressed by handle.
+ * pts: HOST pointer, n points, `stride` bytes apart (2*coordinate size for packed zkey bytes; 72/136/104/200
+ * for arkworks Affine structs -- the trailing infinity flag is ignored, infinity is x = y = 0);
+ * mont = 1 if coordinates are Montgomery limbs, 0 if canonical. */
+COCG_API int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size_t n, size_t stride, int mont, uint64_t* handle);
+COCG_API int cocg_bases_free(cocg_ctx* ctx, uint64_t handle);
+/* out[j] = sum_i scalars[j][i] * bases[off + i], i < n, for each of the k share components.
+ * scalars: HOST array of k DEVICE pointers; scalars_mont = 1 if Montgomery form.
+ * out_jacobian: HOST pointer, k Jacobian points. */
+COCG_API int cocg_msm(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, const void* const* scalars, int k,
+             int scalars_mont, void* out_jacobian);
+/* Same with HOST scalar pointers (staged through pinned memory); the drop-in call for a host-resident caller. */
+COCG_API int cocg_msm_host(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, const void* const* scalars, int k,
+                  int scalars_mont, void* out_jacobian);
+
+/* ---- a8: evaluate_constraint as CSR sparse mat-vec ----------------------------------------------------
+ * Replaces the loop groth16.rs:159-166 over evaluate_constraint traits.rs:180-185 (rep3.rs:690-708,
+ * plain.rs:243-251).  Matrix: rowptr[rows+1], col[nnz] (u32), coeff[nnz] (Montgomery Fr); uploaded once. */
+COCG_API int cocg_csr_upload(cocg_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const void* coeff, size_t rows,
+                    size_t nnz, uint64_t* handle);
+COCG_API int cocg_csr_free(cocg_ctx* ctx, uint64_t handle);
+/* out[r] = sum_k coeff[k] * z[col[k]]; z = public inputs followed by the witness share, given as two DEVICE
+ * arrays (z_pub: npub elements, may be NULL meaning zeros -- parties that do not add the public part,
+ * rep3.rs:600-608 -- and z_wit).  out: DEVICE pointer, rows elements. */
+COCG_API int cocg_spmv(cocg_ctx* ctx, uint64_t csr, const void* z_pub, size_t npub, const void* z_wit, void* out);
+
+/* ---- K7: O(1) group operations on HOST Jacobian points (proof assembly, groth16.rs:257-312) -----------
+ * op: 0 add(a,b)  1 scalar-mul(a, b = canonical 32-byte scalar)  2 to_affine(a) -> packed affine
+ *     3 from_affine(a)  4 neg(a)  5 double(a).  Replaces EcMpcProtocol::{add_points, scalar_mul_public_point,
+ *     ...} traits.rs:472-522 for single points. */
+COCG_API int cocg_ec_op(cocg_ctx* ctx, int group, int op, const void* a, const void* b, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COCG_H */

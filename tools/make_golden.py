@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/ from the reference checkout (run in the build container, where /root/reference exists).
+
+Two kinds of artefacts are produced:
+  * data fixtures copied verbatim from the reference's test_vectors/ (zkey, wtns, snarkjs proofs, verification keys) --
+    these are inputs/outputs of snarkjs, not reference source code;
+  * known-answer literals lifted out of the reference's own unit tests into JSON:
+      - circom-types/src/groth16/zkey.rs:335-585  (every point of the multiplier2 zkeys, both curves)
+      - mpc-core/tests/protocols/rep3.rs:242-350  (rep3_mul_vec_bn: x, y, x*y)
+The GPU box has no /root/reference; tests read only tests/golden/.
+"""
+import json
+import os
+import re
+import shutil
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def copy_fixtures():
+    for curve in ("bn254", "bls12_381"):
+        for circ in ("multiplier2", "poseidon"):
+            src = os.path.join(REF, "test_vectors", "Groth16", curve, circ)
+            dst = os.path.join(OUT, "groth16", curve, circ)
+            os.makedirs(dst, exist_ok=True)
+            for f in ("circuit.zkey", "witness.wtns", "circom.proof", "public.json", "verification_key.json"):
+                shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+                os.chmod(os.path.join(dst, f), 0o644)
+
+
+def _fn_body(text, name):
+    i = text.index("fn %s()" % name)
+    j = text.index("\n    }\n", i)
+    return text[i:j]
+
+
+_ITEM = re.compile(
+    r'to_g1_\w+!\(\s*"(\d+)"\s*,\s*"(\d+)"\s*\)'
+    r'|to_g2_\w+!\(\s*\{\s*"(\d+)"\s*,\s*"(\d+)"\s*\}\s*,\s*\{\s*"(\d+)"\s*,\s*"(\d+)"\s*\}\s*\)'
+    r'|(G1Affine::identity\(\))|(G2Affine::identity\(\))')
+
+
+def zkey_kats():
+    text = open(os.path.join(REF, "co-circom/circom-types/src/groth16/zkey.rs")).read()
+    out = {}
+    for name, key in (("can_deser_bls12_381_mult2_key", "bls12_381"), ("can_deser_bn254_mult2_key", "bn254")):
+        body = _fn_body(text, name)
+        kat = {}
+        for m in re.finditer(r"let (\w+) = (.*?);\n", body, flags=re.S):
+            var, val = m.group(1), m.group(2)
+            items = []
+            for it in _ITEM.finditer(val):
+                if it.group(1):
+                    items.append([it.group(1), it.group(2)])
+                elif it.group(3):
+                    items.append([[it.group(3), it.group(4)], [it.group(5), it.group(6)]])
+                else:
+                    items.append(None)
+            if items:
+                kat[var] = items if val.lstrip().startswith("vec!") else items[0]
+        out[key] = kat
+    return out
+
+
+def rep3_mul_kat():
+    text = open(os.path.join(REF, "mpc-core/tests/protocols/rep3.rs")).read()
+    body = _fn_body(text, "rep3_mul_vec_bn").replace("\n    }\n", "")
+    i = text.index("fn rep3_mul_vec_bn()")
+    body = text[i:text.index("let mut x_shares1", i)]
+    nums = re.findall(r'from_str\(\s*"(\d+)"', body)
+    assert len(nums) == 12
+    return {"x": nums[0:4], "y": nums[4:8], "xy": nums[8:12]}
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    copy_fixtures()
+    with open(os.path.join(OUT, "zkey_kats.json"), "w") as f:
+        json.dump(zkey_kats(), f, indent=1)
+    with open(os.path.join(OUT, "rep3_mul_vec_bn.json"), "w") as f:
+        json.dump(rep3_mul_kat(), f, indent=1)
+    print("wrote", OUT)
