@@ -22,6 +22,8 @@ SYMBOLS = [
     "cocg_launch_count", "cocg_malloc", "cocg_free", "cocg_h2d", "cocg_d2h", "cocg_memset0", "cocg_vec_op",
     "cocg_vec_scale_powers", "cocg_rep3_mul_local", "cocg_ntt", "cocg_bases_upload", "cocg_bases_free",
     "cocg_msm", "cocg_msm_host", "cocg_csr_upload", "cocg_csr_free", "cocg_spmv", "cocg_ec_op",
+    "cocg_d2d", "cocg_host_alloc", "cocg_host_free", "cocg_rep3_mul_local_prf", "cocg_prf_fill", "cocg_prf_field_host",
+    "cocg_bases_share", "cocg_csr_share",
 ]
 
 _lib = None
@@ -66,6 +68,14 @@ def load():
         "cocg_csr_free": (ci, [vp, u64]),
         "cocg_spmv": (ci, [vp, u64, vp, sz, vp, vp]),
         "cocg_ec_op": (ci, [vp, ci, ci, vp, vp, vp]),
+        "cocg_d2d": (ci, [vp, vp, vp, sz]),
+        "cocg_host_alloc": (ci, [vp, sz, pvp]),
+        "cocg_host_free": (ci, [vp, vp]),
+        "cocg_rep3_mul_local_prf": (ci, [vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp, sz]),
+        "cocg_prf_fill": (ci, [vp, vp, ctypes.c_uint32, vp, sz]),
+        "cocg_prf_field_host": (ci, [ci, vp, ctypes.c_uint32, u64, vp]),
+        "cocg_bases_share": (ci, [vp, vp, u64, ctypes.POINTER(u64)]),
+        "cocg_csr_share": (ci, [vp, vp, u64, ctypes.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -51,9 +51,9 @@ extern "C" void cocg_destroy(cocg_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto& kv : ctx->tables) cudaFree(kv.second);
   for (auto& b : ctx->bases)
-    if (b.d) cudaFree(b.d);
+    if (b.d && b.owned) cudaFree(b.d);
   for (auto& m : ctx->csrs)
-    if (m.rowptr) { cudaFree(m.rowptr); cudaFree(m.col); cudaFree(m.coeff); }
+    if (m.rowptr && m.owned) { cudaFree(m.rowptr); cudaFree(m.col); cudaFree(m.coeff); }
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -114,6 +114,27 @@ extern "C" int cocg_memset0(cocg_ctx* ctx, void* dptr, size_t bytes) {
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (bytes == 0) return 0;
   COCG_CUDA(ctx, cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+  return 0;
+}
+
+extern "C" int cocg_d2d(cocg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (bytes == 0) return 0;
+  COCG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+extern "C" int cocg_host_alloc(cocg_ctx* ctx, size_t bytes, void** hptr) {
+  if (!ctx) return 1;
+  if (!hptr) return fail(ctx, "cocg_host_alloc: null out pointer");
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  COCG_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 16));
+  return 0;
+}
+extern "C" int cocg_host_free(cocg_ctx* ctx, void* hptr) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  COCG_CUDA(ctx, cudaFreeHost(hptr));
   return 0;
 }
 
@@ -195,8 +216,33 @@ int ec_op_impl(cocg_ctx* ctx, int op, const void* a, const void* b, void* out) {
 }
 }  // namespace
 
+// op 6: the group generator as a Jacobian point (x, y, 1)
+static int ec_generator(cocg_ctx* ctx, int group, void* out) {
+  static const uint32_t bn_g1[2][8] = BN254_G1_GEN;
+  static const uint32_t bn_g2[4][8] = BN254_G2_GEN;
+  static const uint32_t bls_g1[2][12] = BLS381_G1_GEN;
+  static const uint32_t bls_g2[4][12] = BLS381_G2_GEN;
+  char* o = (char*)out;
+  if (ctx->curve == COCG_BN254) {
+    Bn254Fq one = Bn254Fq::one();
+    size_t nb = group == COCG_G1 ? sizeof(bn_g1) : sizeof(bn_g2);
+    memcpy(o, group == COCG_G1 ? (const void*)bn_g1 : (const void*)bn_g2, nb);
+    memset(o + nb, 0, nb / 2);
+    memcpy(o + nb, one.l, 32);
+  } else {
+    Bls381Fq one = Bls381Fq::one();
+    size_t nb = group == COCG_G1 ? sizeof(bls_g1) : sizeof(bls_g2);
+    memcpy(o, group == COCG_G1 ? (const void*)bls_g1 : (const void*)bls_g2, nb);
+    memset(o + nb, 0, nb / 2);
+    memcpy(o + nb, one.l, 48);
+  }
+  return 0;
+}
+
 extern "C" int cocg_ec_op(cocg_ctx* ctx, int group, int op, const void* a, const void* b, void* out) {
   if (!ctx) return 1;
+  if (group != COCG_G1 && group != COCG_G2) return fail(ctx, "cocg_ec_op: group must be 1 or 2");
+  if (op == 6) return out ? ec_generator(ctx, group, out) : fail(ctx, "cocg_ec_op: null argument");
   if (!a || !out || ((op == 0 || op == 1) && !b)) return fail(ctx, "cocg_ec_op: null argument");
   if (group != COCG_G1 && group != COCG_G2) return fail(ctx, "cocg_ec_op: group must be 1 or 2");
   if (ctx->curve == COCG_BN254) return group == COCG_G1 ? ec_op_impl<Bn254Fq>(ctx, op, a, b, out) : ec_op_impl<Bn254Fq2>(ctx, op, a, b, out);

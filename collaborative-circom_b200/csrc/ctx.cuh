@@ -21,12 +21,14 @@ struct BasesEntry {
   size_t n = 0;
   int group = 0;
   size_t point_bytes = 0;
+  bool owned = true;  // false: alias of another context's allocation (cocg_bases_share)
 };
 struct CsrEntry {
   uint32_t* rowptr = nullptr;
   uint32_t* col = nullptr;
   void* coeff = nullptr;
   size_t rows = 0, nnz = 0;
+  bool owned = true;
 };
 }  // namespace cocg
 

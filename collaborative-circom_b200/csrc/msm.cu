@@ -57,8 +57,22 @@ extern "C" int cocg_bases_free(cocg_ctx* ctx, uint64_t handle) {
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (handle == 0 || handle > ctx->bases.size() || !ctx->bases[handle - 1].d) return fail(ctx, "cocg_bases_free: bad handle");
   COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  COCG_CUDA(ctx, cudaFree(ctx->bases[handle - 1].d));
+  if (ctx->bases[handle - 1].owned) COCG_CUDA(ctx, cudaFree(ctx->bases[handle - 1].d));
   ctx->bases[handle - 1] = BasesEntry();
+  return 0;
+}
+
+extern "C" int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handle, uint64_t* handle) {
+  if (!ctx) return 1;
+  if (!owner || !handle) return fail(ctx, "cocg_bases_share: null argument");
+  if (owner->device != ctx->device || owner->curve != ctx->curve) return fail(ctx, "cocg_bases_share: contexts differ in device or curve");
+  if (owner_handle == 0 || owner_handle > owner->bases.size() || !owner->bases[owner_handle - 1].d) return fail(ctx, "cocg_bases_share: bad handle");
+  BasesEntry be = owner->bases[owner_handle - 1];
+  be.owned = false;
+  for (size_t i = 0; i < ctx->bases.size(); i++)
+    if (!ctx->bases[i].d) { ctx->bases[i] = be; *handle = i + 1; return 0; }
+  ctx->bases.push_back(be);
+  *handle = ctx->bases.size();
   return 0;
 }
 

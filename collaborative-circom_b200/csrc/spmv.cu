@@ -71,8 +71,22 @@ extern "C" int cocg_csr_free(cocg_ctx* ctx, uint64_t handle) {
   if (handle == 0 || handle > ctx->csrs.size() || !ctx->csrs[handle - 1].rowptr) return fail(ctx, "cocg_csr_free: bad handle");
   COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   CsrEntry& m = ctx->csrs[handle - 1];
-  cudaFree(m.rowptr); cudaFree(m.col); cudaFree(m.coeff);
+  if (m.owned) { cudaFree(m.rowptr); cudaFree(m.col); cudaFree(m.coeff); }
   m = CsrEntry();
+  return 0;
+}
+
+extern "C" int cocg_csr_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handle, uint64_t* handle) {
+  if (!ctx) return 1;
+  if (!owner || !handle) return fail(ctx, "cocg_csr_share: null argument");
+  if (owner->device != ctx->device || owner->curve != ctx->curve) return fail(ctx, "cocg_csr_share: contexts differ in device or curve");
+  if (owner_handle == 0 || owner_handle > owner->csrs.size() || !owner->csrs[owner_handle - 1].rowptr) return fail(ctx, "cocg_csr_share: bad handle");
+  CsrEntry m = owner->csrs[owner_handle - 1];
+  m.owned = false;
+  for (size_t i = 0; i < ctx->csrs.size(); i++)
+    if (!ctx->csrs[i].rowptr) { ctx->csrs[i] = m; *handle = i + 1; return 0; }
+  ctx->csrs.push_back(m);
+  *handle = ctx->csrs.size();
   return 0;
 }
 

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "ctx.cuh"
+#include "prf.cuh"
 
 namespace cocg {
 
@@ -44,6 +45,26 @@ __global__ void __launch_bounds__(256) rep3_mul_local_kernel(const void* __restr
     if (MASK) r = fp_add(r, load_fp<P>(mask, i));
     store_fp<P>(out, i, r);
   }
+}
+
+// Same with the zero-mask generated in the kernel: mask[i] = F(k_own, ctr, i) - F(k_prev, ctr, i), the counter-addressed
+// form of masking_field_element (rep3/rngs.rs:37-46; see prf.cuh).  No mask vector ever exists in HBM.
+template <class P>
+__global__ void __launch_bounds__(256) rep3_mul_local_prf_kernel(const void* __restrict__ aa, const void* __restrict__ ab,
+                                                                  const void* __restrict__ ba, const void* __restrict__ bb,
+                                                                  PrfKey k_own, PrfKey k_prev, uint32_t ctr, void* __restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fp<P> xa = load_fp<P>(aa, i), xb = load_fp<P>(ab, i), ya = load_fp<P>(ba, i), yb = load_fp<P>(bb, i);
+    Fp<P> r = fp_add(fp_mul(xa, fp_add(ya, yb)), fp_mul(xb, ya));
+    r = fp_add(r, fp_sub(prf_field<P>(k_own, ctr, i), prf_field<P>(k_prev, ctr, i)));
+    store_fp<P>(out, i, r);
+  }
+}
+template <class P>
+__global__ void __launch_bounds__(256) prf_fill_kernel(PrfKey key, uint32_t ctr, void* __restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) store_fp<P>(out, i, prf_field<P>(key, ctr, i));
 }
 
 // out[i] = first * base^i.  Thread t owns a run of RUN consecutive exponents: one square-and-multiply to
@@ -116,9 +137,53 @@ static int rep3_mul_local_impl(cocg_ctx* ctx, const void* aa, const void* ab, co
   return 0;
 }
 
+template <class P>
+static int rep3_mul_local_prf_impl(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
+                                   const void* seed_own, const void* seed_prev, uint32_t ctr, void* out, size_t n) {
+  if (n == 0) return 0;
+  PrfKey k1, k2;
+  memcpy(k1.k, seed_own, 32);
+  memcpy(k2.k, seed_prev, 32);
+  rep3_mul_local_prf_kernel<P><<<grid_for(n, 256, 8), 256, 0, ctx->stream>>>(aa, ab, ba, bb, k1, k2, ctr, out, n);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template <class P>
+static int prf_fill_impl(cocg_ctx* ctx, const void* seed, uint32_t ctr, void* out, size_t n) {
+  if (n == 0) return 0;
+  PrfKey k;
+  memcpy(k.k, seed, 32);
+  prf_fill_kernel<P><<<grid_for(n, 256, 8), 256, 0, ctx->stream>>>(k, ctr, out, n);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 }  // namespace cocg
 
 using namespace cocg;
+
+extern "C" int cocg_rep3_mul_local_prf(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
+                                       const void* seed_own, const void* seed_prev, uint32_t ctr, void* out, size_t n) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!seed_own || !seed_prev || (n && (!aa || !ab || !ba || !bb || !out))) return fail(ctx, "cocg_rep3_mul_local_prf: null operand");
+  return COCG_FR_DISPATCH(ctx, rep3_mul_local_prf_impl, ctx, aa, ab, ba, bb, seed_own, seed_prev, ctr, out, n);
+}
+extern "C" int cocg_prf_fill(cocg_ctx* ctx, const void* seed, uint32_t ctr, void* out, size_t n) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!seed || (n && !out)) return fail(ctx, "cocg_prf_fill: null operand");
+  return COCG_FR_DISPATCH(ctx, prf_fill_impl, ctx, seed, ctr, out, n);
+}
+extern "C" int cocg_prf_field_host(int curve, const void* seed, uint32_t ctr, uint64_t idx, void* out) {
+  if (!seed || !out) return 1;
+  PrfKey k;
+  memcpy(k.k, seed, 32);
+  if (curve == COCG_BN254) { auto v = prf_field<Bn254FrP>(k, ctr, idx); memcpy(out, v.l, 32); }
+  else if (curve == COCG_BLS12_381) { auto v = prf_field<Bls381FrP>(k, ctr, idx); memcpy(out, v.l, 32); }
+  else return 1;
+  return 0;
+}
 
 extern "C" int cocg_vec_op(cocg_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n) {
   if (!ctx) return 1;

@@ -1,0 +1,382 @@
+// C entry points of the host layer (libcohost.so): device-resident zkeys and proving sessions that run the reference's
+// prover structure (CoGroth16<T> over PlainDriver / three Rep3Protocol drivers on three threads with an in-process
+// Rep3TestNetwork, exactly how /root/reference/tests/tests/circom/e2e_tests/mod.rs:55-70 and
+// tests/benches/poseidon_hash2.rs:197-222 run it) on top of libcocg.so.  Declared in include/cohost.h.
+#include <algorithm>
+#include <thread>
+
+#include "../../include/cohost.h"
+#include "groth16.hpp"
+
+using namespace cohost;
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+template <class Fn>
+int guarded(Fn fn) {
+  try {
+    fn();
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(e.what());
+  }
+}
+Point load_point(const void* p, size_t limbs) {
+  Point r;
+  memcpy(r.l, p, limbs * 8);
+  return r;
+}
+}  // namespace
+
+struct cohost_zkey {
+  ZKey zk;
+  int device = 0;
+  size_t lq = 4;
+};
+
+struct cohost_rep3_session {
+  cohost_zkey* zkey = nullptr;
+  std::unique_ptr<Rep3TestNetwork> net;
+  std::unique_ptr<Rep3Protocol> drv[3];
+  std::unique_ptr<CoGroth16<Rep3Protocol>> prover[3];
+  CoGroth16<Rep3Protocol>::Handles hd[3];
+  DevVec pub[3];
+  // multi-GPU two-phase state
+  int world = 1, rank = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int partials_ready = 0;
+  bool combined_ready = false;
+  bool abort_wait = false;
+  MsmPartials partials[3];
+  // in-flight prove
+  std::thread th[3];
+  std::string errs[3];
+  Groth16Proof proofs[3];
+  bool running = false;
+  bool failed = false;
+};
+
+struct cohost_plain_session {
+  cohost_zkey* zkey = nullptr;
+  std::unique_ptr<PlainDriver> drv;
+  std::unique_ptr<CoGroth16<PlainDriver>> prover;
+  CoGroth16<PlainDriver>::Handles hd;
+};
+
+extern "C" const char* cohost_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) {
+  if (!d || !out) return fail("cohost_zkey_create: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    std::unique_ptr<cohost_zkey> z(new cohost_zkey());
+    ZKey& zk = z->zk;
+    zk.curve = d->curve;
+    z->device = d->device;
+    z->lq = d->curve == COCG_BN254 ? 4 : 6;
+    const size_t lq = z->lq;
+    if (cocg_create(&zk.owner, d->device, d->curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
+    zk.n_public = d->n_public;
+    zk.n_vars = d->n_vars;
+    zk.pow = d->pow;
+    zk.num_constraints = d->num_constraints;
+    if (zk.n_vars < zk.n_public + 1) throw Error("zkey: n_vars < n_public + 1");
+    const size_t m = zk.n_vars, l = zk.n_public;
+    const size_t g1b = 2 * lq * 8, g2b = 4 * lq * 8;
+    cocg_ctx* c = zk.owner;
+    check(c, cocg_bases_upload(c, COCG_G1, d->a_query, m, g1b, 1, &zk.a_query), "a_query");
+    check(c, cocg_bases_upload(c, COCG_G1, d->b_g1_query, m, g1b, 1, &zk.b_g1_query), "b_g1_query");
+    check(c, cocg_bases_upload(c, COCG_G2, d->b_g2_query, m, g2b, 1, &zk.b_g2_query), "b_g2_query");
+    check(c, cocg_bases_upload(c, COCG_G1, d->h_query, zk.domain_size(), g1b, 1, &zk.h_query), "h_query");
+    check(c, cocg_bases_upload(c, COCG_G1, d->l_query, zk.n_aux(), g1b, 1, &zk.l_query), "l_query");
+    check(c, cocg_csr_upload(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, &zk.csr_a), "csr_a");
+    check(c, cocg_csr_upload(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, &zk.csr_b), "csr_b");
+    for (size_t i = 0; i <= l; i++) {
+      zk.a_head.push_back(load_point((const char*)d->a_query + i * g1b, 2 * lq));
+      zk.b_g1_head.push_back(load_point((const char*)d->b_g1_query + i * g1b, 2 * lq));
+      zk.b_g2_head.push_back(load_point((const char*)d->b_g2_query + i * g2b, 4 * lq));
+    }
+    zk.alpha_g1 = load_point(d->alpha_g1, 2 * lq);
+    zk.beta_g1 = load_point(d->beta_g1, 2 * lq);
+    zk.delta_g1 = load_point(d->delta_g1, 2 * lq);
+    zk.beta_g2 = load_point(d->beta_g2, 4 * lq);
+    zk.delta_g2 = load_point(d->delta_g2, 4 * lq);
+    *out = z.release();
+  });
+}
+
+extern "C" void cohost_zkey_destroy(cohost_zkey* z) {
+  if (!z) return;
+  if (z->zk.owner) cocg_destroy(z->zk.owner);
+  delete z;
+}
+
+template <class H>
+static void share_handles(cocg_ctx* ctx, const ZKey& zk, H& hd) {
+  check(ctx, cocg_bases_share(ctx, zk.owner, zk.a_query, &hd.a_query), "share a_query");
+  check(ctx, cocg_bases_share(ctx, zk.owner, zk.b_g1_query, &hd.b_g1_query), "share b_g1_query");
+  check(ctx, cocg_bases_share(ctx, zk.owner, zk.b_g2_query, &hd.b_g2_query), "share b_g2_query");
+  check(ctx, cocg_bases_share(ctx, zk.owner, zk.h_query, &hd.h_query), "share h_query");
+  check(ctx, cocg_bases_share(ctx, zk.owner, zk.l_query, &hd.l_query), "share l_query");
+  check(ctx, cocg_csr_share(ctx, zk.owner, zk.csr_a, &hd.csr_a), "share csr_a");
+  check(ctx, cocg_csr_share(ctx, zk.owner, zk.csr_b, &hd.csr_b), "share csr_b");
+}
+
+// ------------------------------------------------------------------------------------------------ plain driver
+extern "C" int cohost_plain_session_create(cohost_zkey* z, cohost_plain_session** out) {
+  if (!z || !out) return fail("cohost_plain_session_create: null argument");
+  return guarded([&] {
+    std::unique_ptr<cohost_plain_session> s(new cohost_plain_session());
+    s->zkey = z;
+    s->drv.reset(new PlainDriver(z->zk.curve, z->device));
+    s->prover.reset(new CoGroth16<PlainDriver>(*s->drv));
+    share_handles(s->drv->ctx, z->zk, s->hd);
+    *out = s.release();
+  });
+}
+extern "C" void cohost_plain_session_destroy(cohost_plain_session* s) {
+  if (!s) return;
+  s->prover->driver.release(s->prover->last_h);
+  delete s;
+}
+extern "C" int cohost_plain_prove(cohost_plain_session* s, const void* public_inputs, const void* witness, const void* r, const void* s_rand,
+                                  void* proof_out, void* h_out) {
+  if (!s || !public_inputs || !proof_out) return fail("cohost_plain_prove: null argument");
+  return guarded([&] {
+    const ZKey& zk = s->zkey->zk;
+    PlainDriver& d = *s->drv;
+    const size_t lq = s->zkey->lq;
+    InjectedRandomness inj;
+    if (r && s_rand) {
+      FieldShare fr_, fs_;
+      memcpy(fr_.a.l, r, 32);
+      memcpy(fs_.a.l, s_rand, 32);
+      fr_.b = fs_.b = d.fr.zero();
+      inj.rand = {fr_, fs_};
+      d.injected = &inj;
+    }
+    std::vector<Fr> pub_host(zk.num_inputs());
+    memcpy(pub_host.data(), public_inputs, zk.num_inputs() * 32);
+    DevVec pub = d.upload(public_inputs, zk.num_inputs());
+    FieldShareVec wit = d.share_vec_from_host(witness, nullptr, zk.n_aux());
+    Groth16Proof p = s->prover->prove(zk, s->hd, pub, pub_host, wit);
+    d.injected = nullptr;
+    if (h_out) d.download(s->prover->last_h.a, h_out);
+    d.release(pub);
+    d.release(wit);
+    uint64_t* o = (uint64_t*)proof_out;
+    memcpy(o, p.pi_a.l, 2 * lq * 8);
+    memcpy(o + 2 * lq, p.pi_b.l, 4 * lq * 8);
+    memcpy(o + 6 * lq, p.pi_c.l, 2 * lq * 8);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ REP3, three parties
+extern "C" int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds /* 3 x 32 */, int rank, int world, cohost_rep3_session** out) {
+  if (!z || !out || !seeds) return fail("cohost_rep3_session_create: null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("cohost_rep3_session_create: bad rank/world");
+  return guarded([&] {
+    std::unique_ptr<cohost_rep3_session> s(new cohost_rep3_session());
+    s->zkey = z;
+    s->rank = rank;
+    s->world = world;
+    s->net.reset(new Rep3TestNetwork());
+    for (int i = 0; i < 3; i++) s->drv[i].reset(new Rep3Protocol(z->zk.curve, z->device, s->net->party(i), seeds + 32 * i));
+    for (int i = 0; i < 3; i++) {
+      s->drv[i]->finish_setup();
+      s->prover[i].reset(new CoGroth16<Rep3Protocol>(*s->drv[i]));
+      s->prover[i]->shard.rank = rank;
+      s->prover[i]->shard.world = world;
+      share_handles(s->drv[i]->ctx, z->zk, s->hd[i]);
+    }
+    cohost_rep3_session* sp = s.get();
+    if (world > 1) {
+      for (int i = 0; i < 3; i++)
+        s->prover[i]->combine = [sp](int party, MsmPartials& m) {
+          std::unique_lock<std::mutex> lk(sp->mu);
+          sp->partials[party] = m;
+          sp->partials_ready++;
+          sp->cv.notify_all();
+          sp->cv.wait(lk, [&] { return sp->combined_ready || sp->abort_wait; });
+          if (sp->abort_wait) throw Error("prove aborted while waiting for the multi-GPU combine");
+          m = sp->partials[party];
+        };
+    }
+    *out = s.release();
+  });
+}
+
+extern "C" void cohost_rep3_session_destroy(cohost_rep3_session* s) {
+  if (!s) return;
+  if (s->running) {
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      s->abort_wait = true;
+    }
+    s->cv.notify_all();
+    s->net->close_all();
+    for (auto& t : s->th)
+      if (t.joinable()) t.join();
+  }
+  for (int i = 0; i < 3; i++) {
+    if (s->prover[i]) s->drv[i]->release(s->prover[i]->last_h);
+    s->drv[i]->release(s->pub[i]);
+  }
+  delete s;
+}
+
+static size_t partial_limbs(size_t lq) { return 8 * 3 * lq + 2 * 6 * lq; }
+static void pack_partials(const MsmPartials& m, size_t lq, uint64_t* o) {
+  const PointShare* g1[4] = {&m.h_acc, &m.l_acc, &m.a_acc, &m.b1_acc};
+  for (int i = 0; i < 4; i++) {
+    memcpy(o, g1[i]->a.l, 3 * lq * 8); o += 3 * lq;
+    memcpy(o, g1[i]->b.l, 3 * lq * 8); o += 3 * lq;
+  }
+  memcpy(o, m.b2_acc.a.l, 6 * lq * 8); o += 6 * lq;
+  memcpy(o, m.b2_acc.b.l, 6 * lq * 8);
+}
+
+// Starts one proof on the three party threads.  wit_a[i] / wit_b[i]: HOST share components of party i (n_aux elements).
+// rnd may be NULL (PRF-derived randomness).
+extern "C" int cohost_rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                       const cohost_rep3_randomness* rnd) {
+  if (!s || !public_inputs || !wit_a || !wit_b) return fail("cohost_rep3_prove_begin: null argument");
+  if (s->running) return fail("cohost_rep3_prove_begin: a proof is already in flight");
+  if (s->failed) return fail("cohost_rep3_prove_begin: the session's network is closed after an earlier failure");
+  const ZKey& zk = s->zkey->zk;
+  const size_t lq = s->zkey->lq;
+  s->partials_ready = 0;
+  s->combined_ready = false;
+  s->abort_wait = false;
+  s->running = true;
+  // the caller's pointer arrays need not outlive this call: copy them before the party threads start
+  const void* wa[3] = {wit_a[0], wit_a[1], wit_a[2]};
+  const void* wb[3] = {wit_b[0], wit_b[1], wit_b[2]};
+  cohost_rep3_randomness rnd_copy;
+  if (rnd) rnd_copy = *rnd;
+  const bool have_rnd = rnd != nullptr;
+  for (int i = 0; i < 3; i++) {
+    s->errs[i].clear();
+    const void* wit_a_i = wa[i];
+    const void* wit_b_i = wb[i];
+    s->th[i] = std::thread([=] {
+      const cohost_rep3_randomness* rnd = have_rnd ? &rnd_copy : nullptr;
+      try {
+        Rep3Protocol& d = *s->drv[i];
+        InjectedRandomness inj;
+        if (rnd) {
+          FieldShare r, sv;
+          memcpy(r.a.l, (const char*)rnd->r + 64 * i, 32);
+          memcpy(r.b.l, (const char*)rnd->r + 64 * i + 32, 32);
+          memcpy(sv.a.l, (const char*)rnd->s + 64 * i, 32);
+          memcpy(sv.b.l, (const char*)rnd->s + 64 * i + 32, 32);
+          inj.rand = {r, sv};
+          Fr mrs;
+          memcpy(mrs.l, (const char*)rnd->mask_rs + 32 * i, 32);
+          inj.mul_masks = {mrs};
+          inj.mul_vec_masks = {rnd->masks1[i], rnd->masks2[i]};
+          inj.ec_masks = {load_point((const char*)rnd->mask_pt + 3 * lq * 8 * i, 3 * lq)};
+          d.injected = &inj;
+        }
+        std::vector<Fr> pub_host(zk.num_inputs());
+        memcpy(pub_host.data(), public_inputs, zk.num_inputs() * 32);
+        d.release(s->pub[i]);
+        s->pub[i] = d.upload(public_inputs, zk.num_inputs());
+        FieldShareVec wit = d.share_vec_from_host(wit_a_i, wit_b_i, zk.n_aux());
+        s->proofs[i] = s->prover[i]->prove(zk, s->hd[i], s->pub[i], pub_host, wit);
+        d.release(wit);
+        d.injected = nullptr;
+      } catch (const std::exception& e) {
+        s->errs[i] = e.what();
+        s->drv[i]->injected = nullptr;
+        s->net->close_all();  // unblock the peers (a dead party aborts the proof)
+        {
+          std::lock_guard<std::mutex> lk(s->mu);
+          s->abort_wait = true;
+        }
+        s->cv.notify_all();
+      }
+    });
+  }
+  return 0;
+}
+
+// Multi-GPU: blocks until the three parties have produced this rank's partial MSM sums; copies them out
+// (3 x cohost_rep3_partial_bytes).  The caller all-gathers these over ranks (one NCCL all-gather per proof).
+extern "C" size_t cohost_rep3_partial_bytes(cohost_rep3_session* s) { return s ? 3 * partial_limbs(s->zkey->lq) * 8 : 0; }
+extern "C" int cohost_rep3_prove_partials(cohost_rep3_session* s, void* out) {
+  if (!s || !out) return fail("cohost_rep3_prove_partials: null argument");
+  if (!s->running || s->world == 1) return fail("cohost_rep3_prove_partials: no sharded proof in flight");
+  std::unique_lock<std::mutex> lk(s->mu);
+  s->cv.wait(lk, [&] { return s->partials_ready == 3 || s->abort_wait; });
+  if (s->abort_wait) return fail("cohost_rep3_prove_partials: a party failed");
+  const size_t pl = partial_limbs(s->zkey->lq);
+  for (int i = 0; i < 3; i++) pack_partials(s->partials[i], s->zkey->lq, (uint64_t*)out + pl * i);
+  return 0;
+}
+// gathered: world x (3 x partial) buffers in rank order.  Folds them (group additions) and releases the party threads.
+extern "C" int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gathered) {
+  if (!s || !gathered) return fail("cohost_rep3_prove_combine: null argument");
+  return guarded([&] {
+    const size_t lq = s->zkey->lq, pl = partial_limbs(lq);
+    Rep3Protocol& d = *s->drv[0];
+    std::unique_lock<std::mutex> lk(s->mu);
+    for (int i = 0; i < 3; i++) {
+      MsmPartials& m = s->partials[i];
+      PointShare* g1[4] = {&m.h_acc, &m.l_acc, &m.a_acc, &m.b1_acc};
+      for (int q = 0; q < 5; q++) {
+        const int g = q < 4 ? 1 : 2;
+        PointShare* ps = q < 4 ? g1[q] : &m.b2_acc;
+        const size_t off = q < 4 ? (size_t)q * 6 * lq : 24 * lq, nl = 3 * g * lq;
+        for (int comp = 0; comp < 2; comp++) {
+          Point acc = d.infinity(g);
+          for (int r = 0; r < s->world; r++) {
+            Point p = load_point((const uint64_t*)gathered + ((size_t)r * 3 + i) * pl + off + comp * nl, nl);
+            acc = d.ec_add(g, acc, p);
+          }
+          (comp ? ps->b : ps->a) = acc;
+        }
+      }
+    }
+    s->combined_ready = true;
+    s->cv.notify_all();
+  });
+}
+
+// Joins the party threads.  proofs_out: 3 x (A | B | C) packed affine; h_a/h_b: optional HOST buffers (3 each) for h.
+extern "C" int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, void* const* h_a, void* const* h_b) {
+  if (!s || !proofs_out) return fail("cohost_rep3_prove_end: null argument");
+  if (!s->running) return fail("cohost_rep3_prove_end: no proof in flight");
+  for (auto& t : s->th)
+    if (t.joinable()) t.join();
+  s->running = false;
+  for (int i = 0; i < 3; i++)
+    if (!s->errs[i].empty()) {
+      std::string first = s->errs[i];
+      s->failed = true;  // channels were closed: the session is not reusable after a failure
+      return fail("party " + std::to_string(i) + ": " + first);
+    }
+  return guarded([&] {
+    const size_t lq = s->zkey->lq;
+    for (int i = 0; i < 3; i++) {
+      uint64_t* o = (uint64_t*)proofs_out + (size_t)i * 8 * lq;
+      memcpy(o, s->proofs[i].pi_a.l, 2 * lq * 8);
+      memcpy(o + 2 * lq, s->proofs[i].pi_b.l, 4 * lq * 8);
+      memcpy(o + 6 * lq, s->proofs[i].pi_c.l, 2 * lq * 8);
+      if (h_a && h_a[i]) s->drv[i]->download(s->prover[i]->last_h.a, h_a[i]);
+      if (h_b && h_b[i]) s->drv[i]->download(s->prover[i]->last_h.b, h_b[i]);
+    }
+  });
+}
+
+extern "C" uint64_t cohost_rep3_launch_count(cohost_rep3_session* s) {
+  uint64_t t = 0;
+  if (s)
+    for (int i = 0; i < 3; i++) t += cocg_launch_count(s->drv[i]->ctx);
+  return t;
+}

@@ -1,0 +1,364 @@
+// MPC drivers over the cocg C ABI: the C++ mirror of the reference's trait implementations
+//   PlainDriver   /root/reference/mpc-core/src/protocols/plain.rs:111-416
+//   Rep3Protocol  /root/reference/mpc-core/src/protocols/rep3.rs:491-947
+// for the traits PrimeFieldMpcProtocol, EcMpcProtocol, PairingEcMpcProtocol, FFTProvider, MSMProvider
+// (/root/reference/mpc-core/src/traits.rs:43-223, 472-568).  Method names, argument meaning and the party-id rules are
+// the reference's; the bodies enqueue kernels on the driver's cocg context instead of looping on the CPU.  Share
+// vectors live in HBM between calls; only the MPC network rounds cross PCIe.
+#pragma once
+#include <map>
+#include <memory>
+
+#include "../csrc/ec.cuh"  // host branch: Fr / point arithmetic for the O(1) bookkeeping
+#include "network.hpp"
+
+namespace cohost {
+
+// ---------------------------------------------------------------- host scalar-field helpers (curve chosen at run time)
+struct FrOps {
+  int curve;
+  template <class Fn>
+  Fr un(const Fr& a, Fn fn) const {
+    Fr r;
+    if (curve == COCG_BN254) { cocg::Bn254Fr x; memcpy(x.l, a.l, 32); auto y = fn(x); memcpy(r.l, y.l, 32); }
+    else { cocg::Bls381Fr x; memcpy(x.l, a.l, 32); auto y = fn(x); memcpy(r.l, y.l, 32); }
+    return r;
+  }
+  template <class Fn>
+  Fr bin(const Fr& a, const Fr& b, Fn fn) const {
+    Fr r;
+    if (curve == COCG_BN254) { cocg::Bn254Fr x, y; memcpy(x.l, a.l, 32); memcpy(y.l, b.l, 32); auto z = fn(x, y); memcpy(r.l, z.l, 32); }
+    else { cocg::Bls381Fr x, y; memcpy(x.l, a.l, 32); memcpy(y.l, b.l, 32); auto z = fn(x, y); memcpy(r.l, z.l, 32); }
+    return r;
+  }
+  Fr add(const Fr& a, const Fr& b) const { return bin(a, b, [](auto x, auto y) { return cocg::fp_add(x, y); }); }
+  Fr sub(const Fr& a, const Fr& b) const { return bin(a, b, [](auto x, auto y) { return cocg::fp_sub(x, y); }); }
+  Fr mul(const Fr& a, const Fr& b) const { return bin(a, b, [](auto x, auto y) { return cocg::fp_mul(x, y); }); }
+  Fr from_mont(const Fr& a) const { return un(a, [](auto x) { return cocg::fp_from_mont(x); }); }
+  Fr zero() const { Fr z; memset(z.l, 0, 32); return z; }
+  Fr one() const { return un(zero(), [](auto x) { return decltype(x)::one(); }); }
+};
+
+// ---------------------------------------------------------------- shared plumbing of both drivers
+class DeviceDriver {
+ public:
+  DeviceDriver(int curve, int device) : fr{curve} {
+    if (cocg_create(&ctx, device, curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
+    lq = curve == COCG_BN254 ? 4 : 6;
+  }
+  virtual ~DeviceDriver() {
+    if (ctx) {
+      for (auto& kv : free_) for (void* p : kv.second) cocg_free(ctx, p);
+      for (auto& kv : pinned_free_) for (void* p : kv.second) cocg_host_free(ctx, p);
+      cocg_destroy(ctx);
+    }
+  }
+  DeviceDriver(const DeviceDriver&) = delete;
+
+  // size-bucketed free lists: share vectors of one proof have a handful of distinct lengths and are recycled across
+  // proofs (cudaFree would serialise the device)
+  DevVec alloc(size_t n) {
+    DevVec v;
+    v.n = n;
+    auto& fl = free_[n];
+    if (!fl.empty()) { v.p = fl.back(); fl.pop_back(); return v; }
+    check(ctx, cocg_malloc(ctx, (n ? n : 1) * 32, &v.p), "cocg_malloc");
+    return v;
+  }
+  void release(DevVec& v) {
+    if (v.p) free_[v.n].push_back(v.p);
+    v.p = nullptr;
+    v.n = 0;
+  }
+  void release(FieldShareVec& v) { release(v.a); release(v.b); }
+  std::shared_ptr<void> pinned(size_t bytes) {
+    void* p = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(pin_mu_);
+      auto& fl = pinned_free_[bytes];
+      if (!fl.empty()) { p = fl.back(); fl.pop_back(); }
+    }
+    if (!p) check(ctx, cocg_host_alloc(ctx, bytes, &p), "cocg_host_alloc");
+    // the receiver may drop the buffer from another thread: return it to the pool under the lock
+    return std::shared_ptr<void>(p, [this, bytes](void* q) {
+      std::lock_guard<std::mutex> lk(pin_mu_);
+      pinned_free_[bytes].push_back(q);
+    });
+  }
+  DevVec upload(const void* host, size_t n) {
+    DevVec v = alloc(n);
+    check(ctx, cocg_h2d(ctx, v.p, host, n * 32), "cocg_h2d");
+    return v;
+  }
+  void download(const DevVec& v, void* host) { check(ctx, cocg_d2h(ctx, host, v.p, v.n * 32), "cocg_d2h"); }
+
+  // ---- O(1) group operations on host Jacobian points (K7)
+  Point ec(int group, int op, const Point* a, const void* b = nullptr) {
+    Point r;
+    check(ctx, cocg_ec_op(ctx, group, op, a ? a->l : nullptr, b, r.l), "cocg_ec_op");
+    return r;
+  }
+  Point ec_add(int group, const Point& a, const Point& b) { return ec(group, 0, &a, b.l); }
+  Point ec_neg(int group, const Point& a) { return ec(group, 4, &a); }
+  Point ec_sub(int group, const Point& a, const Point& b) { Point nb = ec_neg(group, b); return ec_add(group, a, nb); }
+  Point ec_mul(int group, const Point& a, const Fr& k_mont) { Fr k = fr.from_mont(k_mont); return ec(group, 1, &a, k.l); }
+  Point from_affine(int group, const Point& a) { return ec(group, 3, &a); }
+  Point to_affine(int group, const Point& a) { return ec(group, 2, &a); }
+  Point generator(int group) { return ec(group, 6, nullptr); }
+  Point infinity(int group) { Point z; return from_affine(group, z); }
+
+  cocg_ctx* ctx = nullptr;
+  FrOps fr;
+  int lq = 4;
+
+ protected:
+  std::map<size_t, std::vector<void*>> free_;
+  std::map<size_t, std::vector<void*>> pinned_free_;
+  std::mutex pin_mu_;
+};
+
+// Values a test may inject in place of the drivers' randomness (the reference draws them from entropy and so pins no
+// proof bytes, plain.rs:202-205 / rep3.rs:595-598).  Consumed in call order.
+struct InjectedRandomness {
+  std::vector<FieldShare> rand;               // results of rand()
+  std::vector<Fr> mul_masks;                  // masking_field_element for mul()
+  std::vector<const void*> mul_vec_masks;     // HOST vectors, one per mul_vec call
+  std::vector<Point> ec_masks;                // Jacobian, masking_ec_element for scalar_mul()
+  size_t i_rand = 0, i_mul = 0, i_vec = 0, i_ec = 0;
+};
+
+// ---------------------------------------------------------------- PlainDriver
+class PlainDriver : public DeviceDriver {
+ public:
+  PlainDriver(int curve, int device) : DeviceDriver(curve, device) {}
+  static constexpr int kComponents = 1;
+  InjectedRandomness* injected = nullptr;
+  uint8_t seed[32] = {};
+  uint32_t ctr = 0;
+
+  FieldShare rand() {  // plain.rs:202-205
+    if (injected && injected->i_rand < injected->rand.size()) return injected->rand[injected->i_rand++];
+    FieldShare r;
+    cocg_prf_field_host(fr.curve, seed, ctr++, 0, r.a.l);
+    r.b = fr.zero();
+    return r;
+  }
+  FieldShare mul(const FieldShare& a, const FieldShare& b) { return FieldShare{fr.mul(a.a, b.a), fr.zero()}; }  // plain.rs:119-121
+  FieldShareVec share_vec_from_host(const void* a, const void*, size_t n) { return FieldShareVec{upload(a, n), DevVec{}}; }
+
+  FieldShareVec evaluate_constraints(uint64_t csr, size_t rows, size_t out_len, const DevVec& public_inputs, const FieldShareVec& witness) {
+    FieldShareVec o{alloc(out_len), DevVec{}};  // plain.rs:243-251, one row per thread
+    check(ctx, cocg_spmv(ctx, csr, public_inputs.p, public_inputs.n, witness.a.p, o.a.p), "cocg_spmv");
+    if (out_len > rows) check(ctx, cocg_memset0(ctx, o.a.at(rows), (out_len - rows) * 32), "cocg_memset0");
+    return o;
+  }
+  FieldShareVec promote_to_trivial_shares(const DevVec& pub) {  // plain.rs:231-233
+    FieldShareVec o{alloc(pub.n), DevVec{}};
+    check(ctx, cocg_d2d(ctx, o.a.p, pub.p, pub.n * 32), "cocg_d2d");
+    return o;
+  }
+  void clone_from_slice(FieldShareVec& dst, const FieldShareVec& src, size_t dst_off, size_t src_off, size_t len) {
+    if (dst.len() < dst_off + len || src.len() < src_off + len || len == 0) throw Error("clone_from_slice: range");  // plain.rs:253-265 asserts
+    check(ctx, cocg_d2d(ctx, dst.a.at(dst_off), src.a.at(src_off), len * 32), "cocg_d2d");
+  }
+  FieldShareVec mul_vec(const FieldShareVec& a, const FieldShareVec& b) {  // plain.rs:220-229
+    FieldShareVec o{alloc(a.len()), DevVec{}};
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.a.p, b.a.p, o.a.p, a.len()), "cocg_vec_op");
+    return o;
+  }
+  void sub_assign_vec(FieldShareVec& a, const FieldShareVec& b) { check(ctx, cocg_vec_op(ctx, COCG_OP_SUB, a.a.p, b.a.p, a.a.p, a.len()), "cocg_vec_op"); }
+  void distribute_powers_and_mul_by_const(FieldShareVec& v, const Fr& g, const Fr& c) {
+    check(ctx, cocg_vec_scale_powers(ctx, v.a.p, v.len(), g.l, c.l), "cocg_vec_scale_powers");
+  }
+  // FFTProvider (plain.rs:369-400).  coset_g != nullptr fuses the distribute_powers_and_mul_by_const(g, 1) call that
+  // follows ifft (precedes fft) in witness_map_from_matrices into the transform.
+  void fft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 0, coset_g); }
+  void ifft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 1, coset_g); }
+  // MSMProvider (plain.rs:408-416)
+  PointShare msm_public_points(int group, uint64_t bases, size_t off, size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
+    PointShare r;
+    const void* sc[1] = {scalars.a.at(scalar_off)};
+    check(ctx, cocg_msm(ctx, bases, off, n, sc, 1, 1, r.a.l), "cocg_msm");
+    return r;
+  }
+  // EcMpcProtocol (plain.rs:287-357)
+  void add_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_add(g, a.a, b.a); }
+  void sub_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_sub(g, a.a, b.a); }
+  void add_assign_points_public(int g, PointShare& a, const Point& b) { a.a = ec_add(g, a.a, b); }
+  void add_assign_points_public_affine(int g, PointShare& a, const Point& b_aff) { a.a = ec_add(g, a.a, from_affine(g, b_aff)); }
+  PointShare scalar_mul_public_point(int g, const Point& a, const FieldShare& b) { PointShare r; r.a = ec_mul(g, a, b.a); return r; }
+  PointShare scalar_mul(int g, const PointShare& a, const FieldShare& b) { PointShare r; r.a = ec_mul(g, a.a, b.a); return r; }
+  Point open_point(int, const PointShare& a) { return a.a; }
+  std::pair<Point, Point> open_two_points(const PointShare& a, const PointShare& b) { return {a.a, b.a}; }
+
+ private:
+  void ntt(FieldShareVec& v, const Domain& d, int inverse, const Fr* coset_g) {
+    if (v.len() != d.size()) throw Error("fft: vector length != domain size");
+    void* vecs[1] = {v.a.p};
+    check(ctx, cocg_ntt(ctx, vecs, 1, d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
+  }
+};
+
+// ---------------------------------------------------------------- Rep3Protocol
+class Rep3Protocol : public DeviceDriver {
+ public:
+  static constexpr int kComponents = 2;
+  // Rep3Protocol::new: PRF setup = send own seed to next, receive prev's (rep3.rs:343-349)
+  Rep3Protocol(int curve, int device, Rep3Network* network, const uint8_t own_seed[32]) : DeviceDriver(curve, device), net(network) {
+    memcpy(seed1, own_seed, 32);
+    net->send_next_bytes(seed1, 32);
+  }
+  void finish_setup() { net->recv_prev_bytes(seed2, 32); }  // split so three drivers can be built on one thread
+
+  Rep3Network* net;
+  InjectedRandomness* injected = nullptr;
+  uint8_t seed1[32], seed2[32];
+  uint32_t ctr = 0;  // advanced in lock-step by the three parties (every consumer below is called by all of them)
+  int id() const { return net->get_id(); }
+
+  // ---- PrimeFieldMpcProtocol
+  FieldShare rand() {  // rep3.rs:595-598 -> Rep3Rand::random_fes
+    if (injected && injected->i_rand < injected->rand.size()) return injected->rand[injected->i_rand++];
+    FieldShare r;
+    cocg_prf_field_host(fr.curve, seed1, ctr, 0, r.a.l);
+    cocg_prf_field_host(fr.curve, seed2, ctr, 0, r.b.l);
+    ctr++;
+    return r;
+  }
+  Fr masking_field_element() {
+    if (injected && injected->i_mul < injected->mul_masks.size()) return injected->mul_masks[injected->i_mul++];
+    FieldShare r = rand();
+    return fr.sub(r.a, r.b);
+  }
+  FieldShare mul(const FieldShare& a, const FieldShare& b) {  // rep3.rs:503-511
+    Fr local_a = fr.add(fr.add(fr.mul(a.a, fr.add(b.a, b.b)), fr.mul(a.b, b.a)), masking_field_element());
+    net->send_next_bytes(local_a.l, 32);
+    FieldShare r;
+    r.a = local_a;
+    net->recv_prev_bytes(r.b.l, 32);
+    return r;
+  }
+  FieldShareVec share_vec_from_host(const void* a, const void* b, size_t n) { return FieldShareVec{upload(a, n), upload(b, n)}; }
+
+  // evaluate_constraint for every row of a matrix (rep3.rs:690-708): public terms enter party 0's `a` and party 1's `b`
+  // only (add_with_public, rep3.rs:600-608)
+  FieldShareVec evaluate_constraints(uint64_t csr, size_t rows, size_t out_len, const DevVec& public_inputs, const FieldShareVec& witness) {
+    FieldShareVec o{alloc(out_len), alloc(out_len)};
+    check(ctx, cocg_spmv(ctx, csr, id() == 0 ? public_inputs.p : nullptr, public_inputs.n, witness.a.p, o.a.p), "cocg_spmv");
+    check(ctx, cocg_spmv(ctx, csr, id() == 1 ? public_inputs.p : nullptr, public_inputs.n, witness.b.p, o.b.p), "cocg_spmv");
+    if (out_len > rows) {
+      check(ctx, cocg_memset0(ctx, o.a.at(rows), (out_len - rows) * 32), "cocg_memset0");
+      check(ctx, cocg_memset0(ctx, o.b.at(rows), (out_len - rows) * 32), "cocg_memset0");
+    }
+    return o;
+  }
+  FieldShareVec promote_to_trivial_shares(const DevVec& pub) {  // fieldshare.rs:254-283: (x,0) / (0,x) / (0,0)
+    FieldShareVec o{alloc(pub.n), alloc(pub.n)};
+    if (id() == 0) check(ctx, cocg_d2d(ctx, o.a.p, pub.p, pub.n * 32), "cocg_d2d");
+    else check(ctx, cocg_memset0(ctx, o.a.p, pub.n * 32), "cocg_memset0");
+    if (id() == 1) check(ctx, cocg_d2d(ctx, o.b.p, pub.p, pub.n * 32), "cocg_d2d");
+    else check(ctx, cocg_memset0(ctx, o.b.p, pub.n * 32), "cocg_memset0");
+    return o;
+  }
+  void clone_from_slice(FieldShareVec& dst, const FieldShareVec& src, size_t dst_off, size_t src_off, size_t len) {  // rep3.rs:710-725
+    if (dst.len() < dst_off + len || src.len() < src_off + len || len == 0) throw Error("clone_from_slice: range");
+    check(ctx, cocg_d2d(ctx, dst.a.at(dst_off), src.a.at(src_off), len * 32), "cocg_d2d");
+    check(ctx, cocg_d2d(ctx, dst.b.at(dst_off), src.b.at(src_off), len * 32), "cocg_d2d");
+  }
+  // rep3.rs:650-670: local product + zero-mask on the GPU, then send_next_many / recv_prev_many over the host network
+  FieldShareVec mul_vec(const FieldShareVec& a, const FieldShareVec& b) {
+    size_t n = a.len();
+    if (b.len() != n) throw Error("mul_vec: length mismatch");
+    FieldShareVec o{alloc(n), alloc(n)};
+    if (injected && injected->i_vec < injected->mul_vec_masks.size()) {
+      DevVec m = upload(injected->mul_vec_masks[injected->i_vec++], n);
+      check(ctx, cocg_rep3_mul_local(ctx, a.a.p, a.b.p, b.a.p, b.b.p, m.p, o.a.p, n), "cocg_rep3_mul_local");
+      check(ctx, cocg_sync(ctx), "cocg_sync");
+      release(m);
+    } else {
+      check(ctx, cocg_rep3_mul_local_prf(ctx, a.a.p, a.b.p, b.a.p, b.b.p, seed1, seed2, ctr++, o.a.p, n), "cocg_rep3_mul_local_prf");
+    }
+    std::shared_ptr<void> buf = pinned(n * 32);
+    check(ctx, cocg_d2h(ctx, buf.get(), o.a.p, n * 32), "cocg_d2h");
+    net->send_next(Message{buf, n * 32});
+    buf.reset();
+    Message m = net->recv_prev();
+    if (m.bytes != n * 32) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
+    check(ctx, cocg_h2d(ctx, o.b.p, m.data.get(), n * 32), "cocg_h2d");
+    return o;
+  }
+  void sub_assign_vec(FieldShareVec& a, const FieldShareVec& b) {  // rep3.rs:672-679
+    check(ctx, cocg_vec_op(ctx, COCG_OP_SUB, a.a.p, b.a.p, a.a.p, a.len()), "cocg_vec_op");
+    check(ctx, cocg_vec_op(ctx, COCG_OP_SUB, a.b.p, b.b.p, a.b.p, a.len()), "cocg_vec_op");
+  }
+  void distribute_powers_and_mul_by_const(FieldShareVec& v, const Fr& g, const Fr& c) {  // rep3.rs:681-688
+    check(ctx, cocg_vec_scale_powers(ctx, v.a.p, v.len(), g.l, c.l), "cocg_vec_scale_powers");
+    check(ctx, cocg_vec_scale_powers(ctx, v.b.p, v.len(), g.l, c.l), "cocg_vec_scale_powers");
+  }
+  // ---- FFTProvider (rep3.rs:880-921): both components in one launch sequence
+  void fft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 0, coset_g); }
+  void ifft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 1, coset_g); }
+  // ---- MSMProvider (rep3.rs:934-947): a and b components against the same resident bases
+  PointShare msm_public_points(int group, uint64_t bases, size_t off, size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
+    Point out[2];
+    const void* sc[2] = {scalars.a.at(scalar_off), scalars.b.at(scalar_off)};
+    // Point is wider than a Jacobian: gather the two results from a packed buffer
+    std::vector<uint64_t> packed(2 * 3 * group * lq);
+    check(ctx, cocg_msm(ctx, bases, off, n, sc, 2, 1, packed.data()), "cocg_msm");
+    memcpy(out[0].l, packed.data(), 3 * group * lq * 8);
+    memcpy(out[1].l, packed.data() + 3 * group * lq, 3 * group * lq * 8);
+    return PointShare{out[0], out[1]};
+  }
+  // ---- EcMpcProtocol (rep3.rs:769-862)
+  void add_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_add(g, a.a, b.a); a.b = ec_add(g, a.b, b.b); }
+  void sub_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_sub(g, a.a, b.a); a.b = ec_sub(g, a.b, b.b); }
+  void add_assign_points_public(int g, PointShare& a, const Point& b) {
+    if (id() == 0) a.a = ec_add(g, a.a, b);
+    else if (id() == 1) a.b = ec_add(g, a.b, b);
+  }
+  void add_assign_points_public_affine(int g, PointShare& a, const Point& b_aff) { add_assign_points_public(g, a, from_affine(g, b_aff)); }
+  PointShare scalar_mul_public_point(int g, const Point& a, const FieldShare& b) { return PointShare{ec_mul(g, a, b.a), ec_mul(g, a, b.b)}; }
+  Point masking_ec_element(int g) {  // rngs.rs:48-57; a PRF scalar times the generator instead of C::rand
+    if (injected && injected->i_ec < injected->ec_masks.size()) return injected->ec_masks[injected->i_ec++];
+    FieldShare r = rand();
+    return ec_mul(g, generator(g), fr.sub(r.a, r.b));
+  }
+  PointShare scalar_mul(int g, const PointShare& a, const FieldShare& b) {  // rep3.rs:835-847, pointshare.rs Mul
+    Point local_a = ec_add(g, ec_mul(g, a.a, fr.add(b.a, b.b)), ec_mul(g, a.b, b.a));
+    local_a = ec_add(g, local_a, masking_ec_element(g));
+    size_t nb = 3 * g * lq * 8;
+    net->send_next_bytes(local_a.l, nb);
+    PointShare r;
+    r.a = local_a;
+    net->recv_prev_bytes(r.b.l, nb);
+    return r;
+  }
+  Point open_point(int g, const PointShare& a) {  // rep3.rs:849-853
+    size_t nb = 3 * g * lq * 8;
+    net->send_next_bytes(a.b.l, nb);
+    Point c;
+    net->recv_prev_bytes(c.l, nb);
+    return ec_add(g, ec_add(g, a.a, a.b), c);
+  }
+  std::pair<Point, Point> open_two_points(const PointShare& a, const PointShare& b) {  // rep3.rs:864-878
+    size_t n1 = 3 * lq * 8, n2 = 6 * lq * 8;
+    std::vector<uint8_t> buf(n1 + n2);
+    memcpy(buf.data(), a.b.l, n1);
+    memcpy(buf.data() + n1, b.b.l, n2);
+    net->send_next_bytes(buf.data(), buf.size());
+    net->recv_prev_bytes(buf.data(), buf.size());
+    Point r1, r2;
+    memcpy(r1.l, buf.data(), n1);
+    memcpy(r2.l, buf.data() + n1, n2);
+    return {ec_add(1, r1, ec_add(1, a.a, a.b)), ec_add(2, r2, ec_add(2, b.a, b.b))};
+  }
+
+ private:
+  void ntt(FieldShareVec& v, const Domain& d, int inverse, const Fr* coset_g) {
+    if (v.len() != d.size()) throw Error("fft: vector length != domain size");
+    void* vecs[2] = {v.a.p, v.b.p};
+    check(ctx, cocg_ntt(ctx, vecs, 2, d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
+  }
+};
+
+}  // namespace cohost

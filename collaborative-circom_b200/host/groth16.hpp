@@ -1,0 +1,221 @@
+// CoGroth16<T>: the collaborative Groth16 prover, generic over the MPC driver, as in the reference
+// (/root/reference/co-circom/co-groth16/src/groth16.rs:80-326).  Same call sequence, same names; the driver methods
+// enqueue sm_100a kernels, so between two MPC network rounds everything stays in HBM:
+//   prove                           groth16.rs:113-139
+//   witness_map_from_matrices       groth16.rs:141-204   (SpMV -> mul_vec -> 3x [iNTT, coset scale, NTT] -> mul_vec -> sub)
+//   calculate_coeff                 groth16.rs:206-235
+//   create_proof_with_assignment    groth16.rs:237-326   (5 MSM sites + O(1) group operations + 3 openings)
+// Differences from the reference, all result-preserving:
+//   * evaluate_constraint is called once per matrix (a CSR SpMV) instead of once per row;
+//   * distribute_powers_and_mul_by_const(g, 1) is folded into the ifft that precedes it (the driver's coset_g argument);
+//   * the five secret-scalar MSMs are issued before the first opening (they depend on h and the witness only), so a
+//     multi-GPU caller can combine all partial sums with ONE all-gather per proof (`MsmCombine`).
+#pragma once
+#include <functional>
+
+#include "driver.hpp"
+
+namespace cohost {
+
+// Groth16 domain generator and coset shift with the snarkjs root convention
+// (/root/reference/co-circom/co-circom-snarks/src/lib.rs:208-221 roots_of_unity; groth16.rs:57-77).
+struct Groth16Roots {
+  Fr omega, coset;
+};
+inline Groth16Roots root_of_unity_for_groth16(int curve, size_t pow) {
+  using namespace cocg;
+  Groth16Roots out;
+  auto run = [&](auto tag, int two_adicity) {
+    using F = decltype(tag);
+    constexpr int N = F::N;
+    // smallest quadratic non-residue q: q^((r-1)/2) == -1
+    uint32_t e[N], t[N];
+    for (int i = 0; i < N; i++) e[i] = F::Params::mod(i);
+    e[0] -= 1;                                    // r - 1 (r is odd)
+    for (int i = 0; i < N; i++) t[i] = e[i];
+    auto shr = [&](uint32_t* v, int k) {
+      for (int s = 0; s < k; s++) {
+        for (int i = 0; i < N - 1; i++) v[i] = (v[i] >> 1) | (v[i + 1] << 31);
+        v[N - 1] >>= 1;
+      }
+    };
+    auto pow_big = [&](F b, const uint32_t* ex) {
+      F r = F::one();
+      for (int i = 32 * N - 1; i >= 0; i--) {
+        r = fp_sqr(r);
+        if ((ex[i >> 5] >> (i & 31)) & 1) r = fp_mul(r, b);
+      }
+      return r;
+    };
+    uint32_t half[N];
+    for (int i = 0; i < N; i++) half[i] = e[i];
+    shr(half, 1);
+    F minus_one = fp_neg(F::one());
+    F q = F::one();
+    F one = F::one();
+    for (;;) {
+      if (pow_big(q, half) == minus_one) break;
+      q = fp_add(q, one);
+    }
+    shr(t, two_adicity);                          // odd part of r - 1
+    F z = pow_big(q, t);                          // order 2^s
+    // roots[k] = z^(2^(s-k))
+    auto root = [&](size_t k) {
+      F r = z;
+      for (size_t i = 0; i < (size_t)two_adicity - k; i++) r = fp_sqr(r);
+      return r;
+    };
+    if (pow > (size_t)two_adicity) throw Error("domain larger than the field's two-adicity");
+    F om = root(pow);
+    F cs = (pow == (size_t)two_adicity) ? fp_sqr(q) : root(pow + 1);
+    memcpy(out.omega.l, om.l, 32);
+    memcpy(out.coset.l, cs.l, 32);
+  };
+  if (curve == COCG_BN254) run(Bn254Fr{}, 28);
+  else run(Bls381Fr{}, 32);
+  return out;
+}
+
+// Hook for the multi-GPU path: receives this rank's partial MSM results of one proof (packed PointShares) and must
+// return them summed over ranks (one all-gather + local fold).  Null = single GPU.
+struct MsmPartials {
+  PointShare h_acc, l_acc, a_acc, b1_acc, b2_acc;  // G1, G1, G1, G1, G2
+};
+using MsmCombine = std::function<void(int party, MsmPartials&)>;
+
+// Which slice of every query this rank accumulates (index-range sharding of the bases).
+struct MsmShard {
+  int rank = 0, world = 1;
+  void range(size_t n, size_t& off, size_t& len) const {
+    size_t per = (n + world - 1) / world;
+    off = std::min(n, per * rank);
+    len = std::min(n - off, per);
+  }
+};
+
+template <class T>
+class CoGroth16 {
+ public:
+  explicit CoGroth16(T& driver) : driver(driver) {}
+  T& driver;
+  MsmShard shard;
+  MsmCombine combine;
+  FieldShareVec last_h;  // kept for parity tests (released by the next prove)
+
+  // bases/CSR handles of `zkey` valid in driver.ctx (aliases made by the session)
+  struct Handles {
+    uint64_t a_query, b_g1_query, b_g2_query, h_query, l_query, csr_a, csr_b;
+  };
+
+  // public_inputs: num_inputs = l + 1 elements (leading 1 included) in HBM; witness: n_aux share elements
+  Groth16Proof prove(const ZKey& zkey, const Handles& hd, const DevVec& public_inputs, const std::vector<Fr>& public_inputs_host,
+                     const FieldShareVec& private_witness) {
+    driver.release(last_h);
+    FieldShareVec h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
+    FieldShare r = driver.rand();
+    FieldShare s = driver.rand();
+    Groth16Proof p = create_proof_with_assignment(zkey, hd, r, s, h, public_inputs_host, private_witness);
+    last_h = h;
+    return p;
+  }
+
+  FieldShareVec witness_map_from_matrices(const ZKey& zkey, const Handles& hd, const DevVec& public_inputs, const FieldShareVec& private_witness) {
+    const size_t num_constraints = zkey.num_constraints, num_inputs = zkey.num_inputs();
+    Domain domain;
+    domain.log_n = (unsigned)zkey.pow;
+    if (num_constraints + num_inputs > domain.size()) throw Error("PolynomialDegreeTooLarge");
+    Groth16Roots roots = root_of_unity_for_groth16(zkey.curve, zkey.pow);
+    domain.group_gen = roots.omega;
+    const Fr root_of_unity = roots.coset;
+    const size_t domain_size = domain.size();
+
+    FieldShareVec a = driver.evaluate_constraints(hd.csr_a, num_constraints, domain_size, public_inputs, private_witness);
+    FieldShareVec b = driver.evaluate_constraints(hd.csr_b, num_constraints, domain_size, public_inputs, private_witness);
+    FieldShareVec promoted_public = driver.promote_to_trivial_shares(public_inputs);
+    driver.clone_from_slice(a, promoted_public, num_constraints, 0, num_inputs);
+    driver.release(promoted_public);
+
+    FieldShareVec c = driver.mul_vec(a, b);
+    driver.ifft_in_place(a, domain, &root_of_unity);  // + distribute_powers_and_mul_by_const(a, root_of_unity, 1)
+    driver.ifft_in_place(b, domain, &root_of_unity);
+    driver.fft_in_place(a, domain);
+    driver.fft_in_place(b, domain);
+    FieldShareVec ab = driver.mul_vec(a, b);
+    driver.release(a);
+    driver.release(b);
+    driver.ifft_in_place(c, domain, &root_of_unity);
+    driver.fft_in_place(c, domain);
+    driver.sub_assign_vec(ab, c);
+    driver.release(c);
+    return ab;
+  }
+
+  PointShare calculate_coeff(int g, const PointShare& initial, const std::vector<Point>& query_head, const Point& vk_param,
+                             const std::vector<Fr>& input_assignment, const PointShare& priv_acc) {
+    // pub_acc = msm_unchecked(query[1..=l], input_assignment): l is tiny, done on the host
+    Point pub_acc = driver.infinity(g);
+    for (size_t i = 0; i < input_assignment.size(); i++)
+      pub_acc = driver.ec_add(g, pub_acc, driver.ec_mul(g, driver.from_affine(g, query_head[1 + i]), input_assignment[i]));
+    PointShare res = initial;
+    driver.add_assign_points_public_affine(g, res, query_head[0]);
+    driver.add_assign_points_public_affine(g, res, vk_param);
+    driver.add_assign_points_public(g, res, pub_acc);
+    driver.add_assign_points(g, res, priv_acc);
+    return res;
+  }
+
+  Groth16Proof create_proof_with_assignment(const ZKey& zkey, const Handles& hd, const FieldShare& r, const FieldShare& s, const FieldShareVec& h,
+                                            const std::vector<Fr>& public_inputs_host, const FieldShareVec& aux_assignment) {
+    std::vector<Fr> input_assignment(public_inputs_host.begin() + 1, public_inputs_host.end());
+    const size_t l = zkey.n_public, n_aux = zkey.n_aux();
+    // ---- all secret-scalar MSMs first (msm_public_points at groth16.rs:248, 251-255 and inside calculate_coeff :221-225)
+    MsmPartials m;
+    size_t off, len;
+    shard.range(std::min(h.len(), zkey.domain_size()), off, len);
+    m.h_acc = driver.msm_public_points(1, hd.h_query, off, len, h, off);
+    shard.range(n_aux, off, len);
+    m.l_acc = driver.msm_public_points(1, hd.l_query, off, len, aux_assignment, off);
+    m.a_acc = driver.msm_public_points(1, hd.a_query, 1 + l + off, len, aux_assignment, off);
+    m.b1_acc = driver.msm_public_points(1, hd.b_g1_query, 1 + l + off, len, aux_assignment, off);
+    m.b2_acc = driver.msm_public_points(2, hd.b_g2_query, 1 + l + off, len, aux_assignment, off);
+    if (combine) combine(party_id(), m);
+
+    Point delta_g1 = driver.from_affine(1, zkey.delta_g1);
+    FieldShare rs = driver.mul(r, s);
+    PointShare r_s_delta_g1 = driver.scalar_mul_public_point(1, delta_g1, rs);
+
+    PointShare r_g1 = driver.scalar_mul_public_point(1, delta_g1, r);
+    PointShare g_a = calculate_coeff(1, r_g1, zkey.a_head, zkey.alpha_g1, input_assignment, m.a_acc);
+    Point g_a_opened = driver.open_point(1, g_a);
+    PointShare s_g_a = driver.scalar_mul_public_point(1, g_a_opened, s);
+
+    PointShare s_g1 = driver.scalar_mul_public_point(1, delta_g1, s);
+    PointShare g1_b = calculate_coeff(1, s_g1, zkey.b_g1_head, zkey.beta_g1, input_assignment, m.b1_acc);
+    PointShare r_g1_b = driver.scalar_mul(1, g1_b, r);
+
+    Point delta_g2 = driver.from_affine(2, zkey.delta_g2);
+    PointShare s_g2 = driver.scalar_mul_public_point(2, delta_g2, s);
+    PointShare g2_b = calculate_coeff(2, s_g2, zkey.b_g2_head, zkey.beta_g2, input_assignment, m.b2_acc);
+
+    PointShare g_c = s_g_a;
+    driver.add_assign_points(1, g_c, r_g1_b);
+    driver.sub_assign_points(1, g_c, r_s_delta_g1);
+    driver.add_assign_points(1, g_c, m.l_acc);
+    driver.add_assign_points(1, g_c, m.h_acc);
+
+    auto opened = driver.open_two_points(g_c, g2_b);
+    Groth16Proof proof;
+    proof.pi_a = driver.to_affine(1, g_a_opened);
+    proof.pi_b = driver.to_affine(2, opened.second);
+    proof.pi_c = driver.to_affine(1, opened.first);
+    return proof;
+  }
+
+ private:
+  template <class U = T>
+  auto party_id_impl(int) -> decltype(std::declval<U&>().id()) { return driver.id(); }
+  int party_id_impl(long) { return 0; }
+  int party_id() { return party_id_impl(0); }
+};
+
+}  // namespace cohost

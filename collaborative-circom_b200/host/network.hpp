@@ -1,0 +1,112 @@
+// The REP3 party network the drivers talk to, and its in-process implementation.
+//
+// Mirrors the reference's `Rep3Network` trait (/root/reference/mpc-core/src/protocols/rep3/network.rs:13-64:
+// get_id, send/recv, send_next(_many), recv_prev(_many)) and the test double the reference runs its provers on,
+// `Rep3TestNetwork` / `PartyTestNetwork` (/root/reference/tests/src/rep3_network.rs:6-166: one unbounded byte channel
+// per ordered pair of parties).  The MPC rounds stay on the host (north_star): a message is a host byte buffer.  Large
+// share vectors travel in page-locked buffers so the sender's D2H and the receiver's H2D run at PCIe rate; the buffer
+// is handed over by reference count instead of being copied a second time.
+// Errors: a closed channel surfaces as cohost::Error (the reference's io::ErrorKind::BrokenPipe, network.rs:157-159).
+#pragma once
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+
+#include "types.hpp"
+
+namespace cohost {
+
+struct Message {
+  std::shared_ptr<void> data;  // host memory (pinned for share vectors)
+  size_t bytes = 0;
+};
+
+class Channel {  // unbounded MPSC byte channel (std::sync::mpsc in the reference's test network)
+ public:
+  void send(Message m) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (closed_) throw Error("network: send on a closed channel (BrokenPipe)");
+      q_.push_back(std::move(m));
+    }
+    cv_.notify_one();
+  }
+  Message recv() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) throw Error("network: peer hung up (BrokenPipe)");
+    Message m = std::move(q_.front());
+    q_.pop_front();
+    return m;
+  }
+  void close() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      closed_ = true;
+    }
+    cv_.notify_all();
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Message> q_;
+  bool closed_ = false;
+};
+
+class Rep3Network {
+ public:
+  virtual ~Rep3Network() {}
+  virtual int get_id() const = 0;
+  virtual void send(int target, Message m) = 0;
+  virtual Message recv(int from) = 0;
+  void send_next(Message m) { send((get_id() + 1) % 3, std::move(m)); }
+  Message recv_prev() { return recv((get_id() + 2) % 3); }
+  // small values: copied into a heap buffer
+  void send_next_bytes(const void* p, size_t n) {
+    std::shared_ptr<void> buf(new uint8_t[n ? n : 1], [](void* q) { delete[] (uint8_t*)q; });
+    memcpy(buf.get(), p, n);
+    send_next(Message{buf, n});
+  }
+  void recv_prev_bytes(void* p, size_t n) {
+    Message m = recv_prev();
+    if (m.bytes != n) throw Error("network: invalid number of bytes received");  // rep3.rs:663-668
+    memcpy(p, m.data.get(), n);
+  }
+};
+
+class Rep3TestNetwork;
+class PartyTestNetwork : public Rep3Network {
+ public:
+  PartyTestNetwork(Rep3TestNetwork* net, int id) : net_(net), id_(id) {}
+  int get_id() const override { return id_; }
+  void send(int target, Message m) override;
+  Message recv(int from) override;
+
+ private:
+  Rep3TestNetwork* net_;
+  int id_;
+};
+
+class Rep3TestNetwork {
+ public:
+  Rep3TestNetwork() {
+    for (int i = 0; i < 3; i++) parties_[i].reset(new PartyTestNetwork(this, i));
+  }
+  PartyTestNetwork* party(int i) { return parties_[i].get(); }
+  Channel& chan(int from, int to) { return ch_[from][to]; }
+  void close_all() {
+    for (auto& row : ch_)
+      for (auto& c : row) c.close();
+  }
+
+ private:
+  Channel ch_[3][3];
+  std::unique_ptr<PartyTestNetwork> parties_[3];
+};
+
+inline void PartyTestNetwork::send(int target, Message m) { net_->chan(id_, target).send(std::move(m)); }
+inline Message PartyTestNetwork::recv(int from) { return net_->chan(from, id_).recv(); }
+
+}  // namespace cohost

@@ -1,0 +1,90 @@
+// Host-side data carriers of the proving path: the C++ mirror of the reference's share / point / zkey types.
+//   Rep3PrimeFieldShare{a,b}          mpc-core/src/protocols/rep3/fieldshare.rs:14-17
+//   Rep3PrimeFieldShareVec{a,b}       mpc-core/src/protocols/rep3/fieldshare.rs:232-236   (SoA; here: two HBM arrays)
+//   Rep3PointShare{a,b}               mpc-core/src/protocols/rep3/pointshare.rs:11-14
+//   ZKey<P>                           co-circom/circom-types/src/groth16/zkey.rs:47-71
+// (paths under /root/reference).  Everything numeric is little-endian u64 limbs in Montgomery form, exactly the bytes
+// the C ABI (include/cocg.h) takes, so nothing is converted between this layer and the kernels.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/cocg.h"
+
+namespace cohost {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+struct Fr {
+  uint64_t l[4];
+  bool operator==(const Fr& o) const { return memcmp(l, o.l, 32) == 0; }
+};
+
+// A group element: Jacobian (X, Y, Z), or packed affine (x, y); G1 or G2; coordinates of 4 (BN254) or 6 (BLS12-381)
+// limbs (G2: two of those per coordinate).  36 limbs covers Jacobian G2 over BLS12-381.
+struct Point {
+  uint64_t l[36];
+  Point() { memset(l, 0, sizeof(l)); }
+};
+
+inline void check(cocg_ctx* ctx, int rc, const char* what) {
+  if (rc) throw Error(std::string(what) + ": " + cocg_last_error(ctx));
+}
+
+// n Fr elements in HBM, owned by one driver's context; freed back to the driver's pool by the owner.
+struct DevVec {
+  void* p = nullptr;
+  size_t n = 0;
+  void* at(size_t off) const { return (char*)p + off * 32; }
+};
+
+struct FieldShare {  // b unused by the plain driver
+  Fr a, b;
+};
+struct FieldShareVec {  // b.p == nullptr for the plain driver
+  DevVec a, b;
+  size_t len() const { return a.n; }
+};
+struct PointShare {
+  Point a, b;
+};
+
+// The evaluation domain a caller hands to fft/ifft: size 2^log_n and its generator (`domain.group_gen`, overridden to
+// the snarkjs root by root_of_unity_for_groth16, co-circom/co-groth16/src/groth16.rs:57-77).
+struct Domain {
+  unsigned log_n = 0;
+  Fr group_gen;
+  size_t size() const { return (size_t)1 << log_n; }
+};
+
+// Device-resident proving key.  Query arrays live in HBM behind bases handles of `owner`; drivers alias them
+// (cocg_bases_share), as the reference's three in-process drivers borrow one &ZKey.
+struct ZKey {
+  int curve = 0;
+  cocg_ctx* owner = nullptr;
+  size_t n_public = 0;         // l  (public inputs without the leading 1)
+  size_t n_vars = 0;           // m
+  size_t pow = 0;              // log2(domain size)
+  size_t num_constraints = 0;
+  size_t domain_size() const { return (size_t)1 << pow; }
+  size_t num_inputs() const { return n_public + 1; }  // matrices.num_instance_variables
+  size_t n_aux() const { return n_vars - n_public - 1; }
+  uint64_t a_query = 0, b_g1_query = 0, b_g2_query = 0, h_query = 0, l_query = 0;  // handles in `owner`
+  uint64_t csr_a = 0, csr_b = 0;
+  // the first 1 + l points of each coefficient query stay on the host as well (calculate_coeff groth16.rs:219-231)
+  std::vector<Point> a_head, b_g1_head, b_g2_head;  // packed affine
+  Point alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2;  // packed affine
+};
+
+struct Groth16Proof {  // packed affine, Montgomery coordinates; groth16/proof.rs:7-29
+  Point pi_a, pi_b, pi_c;
+};
+
+}  // namespace cohost

@@ -1,0 +1,223 @@
+"""ctypes binding of libcohost.so (include/cohost.h): device-resident Groth16 zkeys and proving sessions.
+
+The host layer itself is C++ (collaborative-circom_b200/host): CoGroth16<T>::prove over PlainDriver / three Rep3Protocol
+drivers, mirroring /root/reference/co-circom/co-groth16/src/groth16.rs and mpc-core/src/protocols/{plain,rep3}.rs.  This
+file only marshals numpy arrays (uint64 limbs, Montgomery form) across the C boundary; nothing is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import CocgError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libcohost.so")
+HOST_SYMBOLS = [
+    "cohost_last_error", "cohost_zkey_create", "cohost_zkey_destroy", "cohost_plain_session_create",
+    "cohost_plain_session_destroy", "cohost_plain_prove", "cohost_rep3_session_create", "cohost_rep3_session_destroy",
+    "cohost_rep3_prove_begin", "cohost_rep3_partial_bytes", "cohost_rep3_prove_partials", "cohost_rep3_prove_combine",
+    "cohost_rep3_prove_end", "cohost_rep3_launch_count",
+]
+
+vp, sz, ci, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+
+
+class ZKeyDesc(ctypes.Structure):
+    _fields_ = [("curve", ci), ("device", ci), ("n_public", sz), ("n_vars", sz), ("pow", sz), ("num_constraints", sz),
+                ("a_rowptr", vp), ("a_col", vp), ("a_coeff", vp), ("a_nnz", sz),
+                ("b_rowptr", vp), ("b_col", vp), ("b_coeff", vp), ("b_nnz", sz),
+                ("a_query", vp), ("b_g1_query", vp), ("b_g2_query", vp), ("h_query", vp), ("l_query", vp),
+                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp)]
+
+
+class Rep3Randomness(ctypes.Structure):
+    _fields_ = [("r", vp), ("s", vp), ("mask_rs", vp), ("mask_pt", vp), ("masks1", vp * 3), ("masks2", vp * 3)]
+
+
+_host = None
+
+
+def load_host():
+    global _host
+    if _host is not None:
+        return _host
+    _lib.load()  # libcocg.so first (libcohost.so links it through $ORIGIN)
+    if not os.path.exists(HOST_LIB_PATH):
+        raise CocgError(f"{HOST_LIB_PATH} is missing: build it with `make -C {_HERE}/host`")
+    L = ctypes.CDLL(HOST_LIB_PATH)
+    pvp = ctypes.POINTER(vp)
+    L.cohost_last_error.restype = ctypes.c_char_p
+    L.cohost_zkey_create.argtypes = [ctypes.POINTER(ZKeyDesc), pvp]
+    L.cohost_zkey_destroy.argtypes = [vp]
+    L.cohost_zkey_destroy.restype = None
+    L.cohost_plain_session_create.argtypes = [vp, pvp]
+    L.cohost_plain_session_destroy.argtypes = [vp]
+    L.cohost_plain_session_destroy.restype = None
+    L.cohost_plain_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.cohost_rep3_session_create.argtypes = [vp, vp, ci, ci, pvp]
+    L.cohost_rep3_session_destroy.argtypes = [vp]
+    L.cohost_rep3_session_destroy.restype = None
+    L.cohost_rep3_prove_begin.argtypes = [vp, vp, pvp, pvp, ctypes.POINTER(Rep3Randomness)]
+    L.cohost_rep3_partial_bytes.argtypes = [vp]
+    L.cohost_rep3_partial_bytes.restype = sz
+    L.cohost_rep3_prove_partials.argtypes = [vp, vp]
+    L.cohost_rep3_prove_combine.argtypes = [vp, vp]
+    L.cohost_rep3_prove_end.argtypes = [vp, vp, pvp, pvp]
+    L.cohost_rep3_launch_count.argtypes = [vp]
+    L.cohost_rep3_launch_count.restype = u64
+    _host = L
+    return L
+
+
+def _ck(rc):
+    if rc:
+        raise CocgError(load_host().cohost_last_error().decode())
+
+
+def _c(a, dtype=np.uint64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Groth16ZKey:
+    """A Groth16 proving key resident in HBM (query arrays as MSM bases, A/B matrices as CSR)."""
+
+    def __init__(self, curve: int, n_public: int, n_vars: int, pow_: int, num_constraints: int, a_csr, b_csr,
+                 a_query, b_g1_query, b_g2_query, h_query, l_query, alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2, device: int = 0):
+        L = load_host()
+        self.curve, self.lq = curve, (4 if curve == _lib.BN254 else 6)
+        self.n_public, self.n_vars, self.pow, self.num_constraints = n_public, n_vars, pow_, num_constraints
+        self.n_aux = n_vars - n_public - 1
+        keep = []
+
+        def P(a, dtype=np.uint64):
+            a = _c(a, dtype)
+            keep.append(a)
+            return a.ctypes.data
+
+        d = ZKeyDesc()
+        d.curve, d.device, d.n_public, d.n_vars, d.pow, d.num_constraints = curve, device, n_public, n_vars, pow_, num_constraints
+        d.a_rowptr, d.a_col, d.a_coeff, d.a_nnz = P(a_csr[0], np.uint32), P(a_csr[1], np.uint32), P(a_csr[2]), len(a_csr[1])
+        d.b_rowptr, d.b_col, d.b_coeff, d.b_nnz = P(b_csr[0], np.uint32), P(b_csr[1], np.uint32), P(b_csr[2]), len(b_csr[1])
+        assert len(a_csr[0]) == num_constraints + 1 and len(b_csr[0]) == num_constraints + 1
+        lq = self.lq
+        for name, arr, n, w in (("a_query", a_query, n_vars, 2), ("b_g1_query", b_g1_query, n_vars, 2), ("b_g2_query", b_g2_query, n_vars, 4),
+                                ("h_query", h_query, 1 << pow_, 2), ("l_query", l_query, self.n_aux, 2)):
+            arr = _c(arr)
+            assert arr.size == n * w * lq, f"{name}: expected {n} points"
+            setattr(d, name, P(arr))
+        d.alpha_g1, d.beta_g1, d.delta_g1, d.beta_g2, d.delta_g2 = P(alpha_g1), P(beta_g1), P(delta_g1), P(beta_g2), P(delta_g2)
+        h = vp()
+        _ck(L.cohost_zkey_create(ctypes.byref(d), ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            load_host().cohost_zkey_destroy(self.h)
+            self.h = None
+
+
+class PlainSession:
+    """CoGroth16<PlainDriver>."""
+
+    def __init__(self, zkey: Groth16ZKey):
+        self.zkey = zkey
+        h = vp()
+        _ck(load_host().cohost_plain_session_create(zkey.h, ctypes.byref(h)))
+        self.h = h
+
+    def prove(self, public_inputs, witness, r=None, s=None, want_h=False):
+        zk = self.zkey
+        pub, wit = _c(public_inputs), _c(witness)
+        assert pub.size == 4 * (zk.n_public + 1) and wit.size == 4 * zk.n_aux
+        proof = np.zeros(8 * zk.lq, dtype=np.uint64)
+        hbuf = np.zeros((1 << zk.pow, 4), dtype=np.uint64) if want_h else None
+        rr = None if r is None else _c(r)
+        ss = None if s is None else _c(s)
+        _ck(load_host().cohost_plain_prove(self.h, pub.ctypes.data, wit.ctypes.data, None if rr is None else rr.ctypes.data,
+                                           None if ss is None else ss.ctypes.data, proof.ctypes.data,
+                                           None if hbuf is None else hbuf.ctypes.data))
+        return (proof, hbuf) if want_h else proof
+
+    def close(self):
+        if self.h:
+            load_host().cohost_plain_session_destroy(self.h)
+            self.h = None
+
+
+class Rep3Session:
+    """Three CoGroth16<Rep3Protocol> provers on three threads over an in-process network (one GPU, or one MSM shard of `world`)."""
+
+    def __init__(self, zkey: Groth16ZKey, seeds: bytes = bytes(range(96)), rank: int = 0, world: int = 1):
+        assert len(seeds) == 96
+        self.zkey, self.rank, self.world = zkey, rank, world
+        self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
+        h = vp()
+        _ck(load_host().cohost_rep3_session_create(zkey.h, self._seeds.ctypes.data, rank, world, ctypes.byref(h)))
+        self.h = h
+
+    def partial_bytes(self) -> int:
+        return int(load_host().cohost_rep3_partial_bytes(self.h))
+
+    def begin(self, public_inputs, wit_a, wit_b, rnd: dict | None = None):
+        zk = self.zkey
+        self._keep = [_c(public_inputs)] + [_c(x) for x in wit_a] + [_c(x) for x in wit_b]
+        pub, wa, wb = self._keep[0], self._keep[1:4], self._keep[4:7]
+        assert pub.size == 4 * (zk.n_public + 1) and all(x.size == 4 * zk.n_aux for x in wa + wb)
+        A = (vp * 3)(*[x.ctypes.data for x in wa])
+        B = (vp * 3)(*[x.ctypes.data for x in wb])
+        R = None
+        if rnd is not None:
+            R = Rep3Randomness()
+            for k in ("r", "s", "mask_rs", "mask_pt"):
+                a = _c(rnd[k])
+                self._keep.append(a)
+                setattr(R, k, a.ctypes.data)
+            for k in ("masks1", "masks2"):
+                arrs = [_c(x) for x in rnd[k]]
+                self._keep += arrs
+                setattr(R, k, (vp * 3)(*[x.ctypes.data for x in arrs]))
+            self._keep.append(R)
+        _ck(load_host().cohost_rep3_prove_begin(self.h, pub.ctypes.data, A, B, None if R is None else ctypes.byref(R)))
+
+    def partials(self) -> np.ndarray:
+        out = np.zeros(self.partial_bytes() // 8, dtype=np.uint64)
+        _ck(load_host().cohost_rep3_prove_partials(self.h, out.ctypes.data))
+        return out
+
+    def combine(self, gathered: np.ndarray):
+        g = _c(gathered)
+        assert g.nbytes == self.world * self.partial_bytes()
+        _ck(load_host().cohost_rep3_prove_combine(self.h, g.ctypes.data))
+
+    def end(self, want_h=False):
+        zk = self.zkey
+        proofs = np.zeros((3, 8 * zk.lq), dtype=np.uint64)
+        ha = hb = None
+        HA = HB = None
+        if want_h:
+            ha = [np.zeros((1 << zk.pow, 4), dtype=np.uint64) for _ in range(3)]
+            hb = [np.zeros((1 << zk.pow, 4), dtype=np.uint64) for _ in range(3)]
+            HA = (vp * 3)(*[x.ctypes.data for x in ha])
+            HB = (vp * 3)(*[x.ctypes.data for x in hb])
+        _ck(load_host().cohost_rep3_prove_end(self.h, proofs.ctypes.data, HA, HB))
+        self._keep = None
+        return (proofs, ha, hb) if want_h else proofs
+
+    def prove(self, public_inputs, wit_a, wit_b, rnd=None, want_h=False, all_gather=None):
+        """One proof.  all_gather(partials: np.ndarray) -> concatenation over ranks; required when world > 1."""
+        self.begin(public_inputs, wit_a, wit_b, rnd)
+        if self.world > 1:
+            self.combine(all_gather(self.partials()))
+        return self.end(want_h)
+
+    def launch_count(self) -> int:
+        return int(load_host().cohost_rep3_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            load_host().cohost_rep3_session_destroy(self.h)
+            self.h = None

@@ -61,6 +61,10 @@ COCG_API int cocg_free(cocg_ctx* ctx, void* dptr);
 COCG_API int cocg_h2d(cocg_ctx* ctx, void* dptr, const void* hptr, size_t bytes); /* synchronous */
 COCG_API int cocg_d2h(cocg_ctx* ctx, void* hptr, const void* dptr, size_t bytes); /* synchronous */
 COCG_API int cocg_memset0(cocg_ctx* ctx, void* dptr, size_t bytes);
+COCG_API int cocg_d2d(cocg_ctx* ctx, void* dst, const void* src, size_t bytes); /* asynchronous; clone_from_slice rep3.rs:710-725 */
+/* Page-locked host buffers: the staging memory for share vectors crossing PCIe (MPC network rounds, witness upload). */
+COCG_API int cocg_host_alloc(cocg_ctx* ctx, size_t bytes, void** hptr);
+COCG_API int cocg_host_free(cocg_ctx* ctx, void* hptr);
 
 /* ---- a7: element-wise share-vector arithmetic (DEVICE pointers, n elements) --------------------------
  * Replaces PrimeFieldMpcProtocol::{add_vec, sub_assign_vec, neg_vec_in_place, mul (plain/Shamir local)}
@@ -73,6 +77,17 @@ COCG_API int cocg_vec_scale_powers(cocg_ctx* ctx, void* x, size_t n, const void*
  * Replaces rep3.rs:656-660; the send_next/recv_prev round (rep3.rs:661-662) stays with the caller. */
 COCG_API int cocg_rep3_mul_local(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
                         const void* mask, void* out, size_t n);
+
+/* Same with the zero-mask produced inside the kernel: mask[i] = F(seed_own, ctr, i) - F(seed_prev, ctr, i), F = the
+ * counter-addressed ChaCha12 field PRF of csrc/prf.cuh.  Replaces rep3.rs:656-660 together with
+ * Rep3Rand::masking_field_element (rep3/rngs.rs:37-46).  seed_*: HOST pointers to 32 bytes; ctr: a per-call counter the
+ * three parties advance in lock-step. */
+COCG_API int cocg_rep3_mul_local_prf(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
+                            const void* seed_own, const void* seed_prev, uint32_t ctr, void* out, size_t n);
+/* out[i] = F(seed, ctr, i) (DEVICE, n elements), and the same function for one element on the HOST (no context needed):
+ * Rep3Rand::random_fes (rngs.rs:42-46) for rand() / masking of single elements. */
+COCG_API int cocg_prf_fill(cocg_ctx* ctx, const void* seed, uint32_t ctr, void* out, size_t n);
+COCG_API int cocg_prf_field_host(int curve, const void* seed, uint32_t ctr, uint64_t idx, void* out);
 
 /* ---- a4 (+a5): in-order radix-2 NTT over Fr, in place (DEVICE pointers) -------------------------------
  * Replaces FFTProvider::{fft_in_place, ifft_in_place} traits.rs:535-555; rep3.rs:880-921, shamir.rs:826-863,
@@ -94,6 +109,9 @@ COCG_API int cocg_ntt(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, c
  * mont = 1 if coordinates are Montgomery limbs, 0 if canonical. */
 COCG_API int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size_t n, size_t stride, int mont, uint64_t* handle);
 COCG_API int cocg_bases_free(cocg_ctx* ctx, uint64_t handle);
+/* Non-owning alias of another context's bases on the same device: the three REP3 drivers of one process borrow the
+ * same &ZKey (tests/tests/circom/e2e_tests/mod.rs:55-70).  The owner must outlive the alias. */
+COCG_API int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handle, uint64_t* handle);
 /* out[j] = sum_i scalars[j][i] * bases[off + i], i < n, for each of the k share components.
  * scalars: HOST array of k DEVICE pointers; scalars_mont = 1 if Montgomery form.
  * out_jacobian: HOST pointer, k Jacobian points. */
@@ -109,6 +127,7 @@ COCG_API int cocg_msm_host(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, 
 COCG_API int cocg_csr_upload(cocg_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const void* coeff, size_t rows,
                     size_t nnz, uint64_t* handle);
 COCG_API int cocg_csr_free(cocg_ctx* ctx, uint64_t handle);
+COCG_API int cocg_csr_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handle, uint64_t* handle);
 /* out[r] = sum_k coeff[k] * z[col[k]]; z = public inputs followed by the witness share, given as two DEVICE
  * arrays (z_pub: npub elements, may be NULL meaning zeros -- parties that do not add the public part,
  * rep3.rs:600-608 -- and z_wit).  out: DEVICE pointer, rows elements. */
@@ -116,7 +135,7 @@ COCG_API int cocg_spmv(cocg_ctx* ctx, uint64_t csr, const void* z_pub, size_t np
 
 /* ---- K7: O(1) group operations on HOST Jacobian points (proof assembly, groth16.rs:257-312) -----------
  * op: 0 add(a,b)  1 scalar-mul(a, b = canonical 32-byte scalar)  2 to_affine(a) -> packed affine
- *     3 from_affine(a)  4 neg(a)  5 double(a).  Replaces EcMpcProtocol::{add_points, scalar_mul_public_point,
+ *     3 from_affine(a)  4 neg(a)  5 double(a)  6 generator() (a, b ignored).  Replaces EcMpcProtocol::{add_points, scalar_mul_public_point,
  *     ...} traits.rs:472-522 for single points. */
 COCG_API int cocg_ec_op(cocg_ctx* ctx, int group, int op, const void* a, const void* b, void* out);
 

@@ -1,0 +1,84 @@
+/* cohost -- C entry points of the host layer above the cocg kernels (libcohost.so).
+ *
+ * libcocg.so (include/cocg.h) is the drop-in boundary: it replaces the arithmetic behind the reference's driver traits.
+ * This header exposes the layer ABOVE it, written in C++ because the reference's own host code is compiled Rust and no
+ * Rust toolchain exists in this image: the reference's prover structure -- CoGroth16<T>::prove
+ * (/root/reference/co-circom/co-groth16/src/groth16.rs:113-326) over PlainDriver (mpc-core/src/protocols/plain.rs) or
+ * three Rep3Protocol drivers (mpc-core/src/protocols/rep3.rs) on three threads joined by an in-process network
+ * (tests/src/rep3_network.rs) -- so tests and bench.py can run whole proofs.  All numbers are little-endian u64 limbs in
+ * Montgomery form; affine points are packed x|y (G2: x.c0|x.c1|y.c0|y.c1), all-zero = infinity.
+ * Every function returns 0 on success; cohost_last_error() describes the last failure on the calling thread. */
+#ifndef COHOST_H
+#define COHOST_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define COHOST_API __attribute__((visibility("default")))
+#else
+#define COHOST_API
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cohost_zkey cohost_zkey;
+typedef struct cohost_plain_session cohost_plain_session;
+typedef struct cohost_rep3_session cohost_rep3_session;
+
+/* A parsed Groth16 proving key (circom-types/src/groth16/zkey.rs:47-71), HOST pointers; copied to HBM once. */
+typedef struct cohost_zkey_desc {
+  int curve;                 /* COCG_BN254 | COCG_BLS12_381 */
+  int device;
+  size_t n_public;           /* l: public inputs without the constant 1 */
+  size_t n_vars;             /* m */
+  size_t pow;                /* log2(domain size) */
+  size_t num_constraints;    /* rows of A and B (public-input identity rows already dropped, zkey.rs:196-204) */
+  const uint32_t *a_rowptr, *a_col; const void* a_coeff; size_t a_nnz;   /* CSR, coefficients Montgomery Fr */
+  const uint32_t *b_rowptr, *b_col; const void* b_coeff; size_t b_nnz;
+  const void *a_query, *b_g1_query, *b_g2_query;   /* m points each (G1, G1, G2) */
+  const void *h_query;                             /* 2^pow G1 points */
+  const void *l_query;                             /* m - l - 1 G1 points */
+  const void *alpha_g1, *beta_g1, *delta_g1, *beta_g2, *delta_g2;
+} cohost_zkey_desc;
+
+/* Injected randomness for parity tests (the reference draws all of it from entropy). */
+typedef struct cohost_rep3_randomness {
+  const void* r;         /* 3 x (a | b) Fr: party i's replicated share of r */
+  const void* s;         /* 3 x (a | b) Fr */
+  const void* mask_rs;   /* 3 Fr summing to zero: masks of mul(r, s) */
+  const void* mask_pt;   /* 3 G1 Jacobian points summing to infinity: masks of scalar_mul(g1_b, r) */
+  const void* masks1[3]; /* HOST vectors (domain size) summing to zero: first mul_vec */
+  const void* masks2[3]; /* second mul_vec */
+} cohost_rep3_randomness;
+
+COHOST_API const char* cohost_last_error(void);
+COHOST_API int cohost_zkey_create(const cohost_zkey_desc* desc, cohost_zkey** out);
+COHOST_API void cohost_zkey_destroy(cohost_zkey* z);
+
+/* CoGroth16<PlainDriver>::prove.  public_inputs: l + 1 Fr (leading 1); witness: m - l - 1 Fr; r, s: one Fr each or NULL
+ * (PRF); proof_out: A | B | C packed affine; h_out: NULL or 2^pow Fr. */
+COHOST_API int cohost_plain_session_create(cohost_zkey* z, cohost_plain_session** out);
+COHOST_API void cohost_plain_session_destroy(cohost_plain_session* s);
+COHOST_API int cohost_plain_prove(cohost_plain_session* s, const void* public_inputs, const void* witness, const void* r, const void* s_rand,
+                                  void* proof_out, void* h_out);
+
+/* Three CoGroth16<Rep3Protocol> provers.  seeds: 3 x 32 bytes (each party's PRF seed, rep3.rs:343-349).
+ * rank/world: index-range sharding of every MSM over `world` GPUs (one process per GPU); world = 1 for a single GPU. */
+COHOST_API int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_rep3_session** out);
+COHOST_API void cohost_rep3_session_destroy(cohost_rep3_session* s);
+/* One proof = begin [-> partials -> (caller all-gathers) -> combine] -> end.  wit_a[i] / wit_b[i]: party i's HOST share
+ * components (m - l - 1 Fr each).  rnd: NULL for PRF-derived randomness. */
+COHOST_API int cohost_rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                       const cohost_rep3_randomness* rnd);
+COHOST_API size_t cohost_rep3_partial_bytes(cohost_rep3_session* s);
+COHOST_API int cohost_rep3_prove_partials(cohost_rep3_session* s, void* out);
+COHOST_API int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gathered);
+/* proofs_out: 3 x (A | B | C); h_a / h_b: NULL or 3 HOST buffers of 2^pow Fr receiving each party's share of h. */
+COHOST_API int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, void* const* h_a, void* const* h_b);
+COHOST_API uint64_t cohost_rep3_launch_count(cohost_rep3_session* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COHOST_H */
