@@ -23,7 +23,8 @@ SYMBOLS = [
     "cocg_vec_scale_powers", "cocg_rep3_mul_local", "cocg_ntt", "cocg_bases_upload", "cocg_bases_free",
     "cocg_msm", "cocg_msm_host", "cocg_csr_upload", "cocg_csr_free", "cocg_spmv", "cocg_ec_op",
     "cocg_d2d", "cocg_host_alloc", "cocg_host_free", "cocg_rep3_mul_local_prf", "cocg_prf_fill", "cocg_prf_field_host",
-    "cocg_bases_share", "cocg_csr_share",
+    "cocg_bases_share", "cocg_csr_share", "cocg_bases_generate", "cocg_bases_download", "cocg_profile_enable",
+    "cocg_profile_read", "cocg_profile_reset",
 ]
 
 _lib = None
@@ -76,6 +77,11 @@ def load():
         "cocg_prf_field_host": (ci, [ci, vp, ctypes.c_uint32, u64, vp]),
         "cocg_bases_share": (ci, [vp, vp, u64, ctypes.POINTER(u64)]),
         "cocg_csr_share": (ci, [vp, vp, u64, ctypes.POINTER(u64)]),
+        "cocg_bases_generate": (ci, [vp, ci, sz, vp, ctypes.POINTER(u64)]),
+        "cocg_bases_download": (ci, [vp, u64, sz, sz, vp]),
+        "cocg_profile_enable": (ci, [vp, ci]),
+        "cocg_profile_read": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),
+        "cocg_profile_reset": (ci, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

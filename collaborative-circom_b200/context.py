@@ -124,6 +124,37 @@ class Context:
         self._groups[hdl.value] = group
         return hdl.value
 
+    def bases_generate(self, group: int, n: int, seed: bytes) -> int:
+        """n synthetic curve points P0 + i*Q generated in HBM (csrc/gen.cu)."""
+        assert len(seed) == 32
+        buf = np.frombuffer(seed, dtype=np.uint8).copy()
+        hdl = ctypes.c_uint64()
+        self._ck(self.L.cocg_bases_generate(self.h, group, n, buf.ctypes.data, ctypes.byref(hdl)))
+        self._groups = getattr(self, "_groups", {})
+        self._groups[hdl.value] = group
+        return hdl.value
+
+    def bases_download(self, handle: int, off: int, n: int) -> np.ndarray:
+        group = self._groups[handle]
+        out = np.zeros((n, 2 * group * self.lq), dtype=np.uint64)
+        self._ck(self.L.cocg_bases_download(self.h, handle, off, n, out.ctypes.data))
+        return out
+
+    def profile(self, on: bool = True):
+        self._ck(self.L.cocg_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self.L.cocg_profile_reset(self.h))
+
+    def profile_read(self) -> dict:
+        names = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
+        out = {}
+        for i, name in enumerate(names):
+            ms, k = ctypes.c_double(), ctypes.c_uint64()
+            self._ck(self.L.cocg_profile_read(self.h, i, ctypes.byref(ms), ctypes.byref(k)))
+            out[name] = (ms.value, int(k.value))
+        return out
+
     def bases_free(self, handle: int):
         self._ck(self.L.cocg_bases_free(self.h, handle))
 

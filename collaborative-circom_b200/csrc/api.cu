@@ -49,6 +49,8 @@ extern "C" void cocg_destroy(cocg_ctx* ctx) {
   for (int i = 0; i < cocg_ctx::kScratchSlots; i++)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto& pr : ctx->prof_pending) { cudaEventDestroy(pr.a); cudaEventDestroy(pr.b); }
+  for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto& kv : ctx->tables) cudaFree(kv.second);
   for (auto& b : ctx->bases)
     if (b.d && b.owned) cudaFree(b.d);
@@ -114,6 +116,37 @@ extern "C" int cocg_memset0(cocg_ctx* ctx, void* dptr, size_t bytes) {
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (bytes == 0) return 0;
   COCG_CUDA(ctx, cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+  return 0;
+}
+
+static int prof_drain(cocg_ctx* ctx) {
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& pr : ctx->prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, pr.a, pr.b) == cudaSuccess) { ctx->prof_ms[pr.cls] += ms; ctx->prof_count[pr.cls]++; }
+    ctx->prof_free.push_back({pr.a, pr.b});
+  }
+  ctx->prof_pending.clear();
+  return 0;
+}
+extern "C" int cocg_profile_enable(cocg_ctx* ctx, int on) {
+  if (!ctx) return 1;
+  ctx->profile = on != 0;
+  return 0;
+}
+extern "C" int cocg_profile_read(cocg_ctx* ctx, int cls, double* total_ms, uint64_t* scopes) {
+  if (!ctx) return 1;
+  if (cls < 0 || cls >= COCG_PROF_CLASSES) return fail(ctx, "cocg_profile_read: unknown class");
+  COCG_TRY(prof_drain(ctx));
+  if (total_ms) *total_ms = ctx->prof_ms[cls];
+  if (scopes) *scopes = ctx->prof_count[cls];
+  return 0;
+}
+extern "C" int cocg_profile_reset(cocg_ctx* ctx) {
+  if (!ctx) return 1;
+  COCG_TRY(prof_drain(ctx));
+  for (int i = 0; i < COCG_PROF_CLASSES; i++) { ctx->prof_ms[i] = 0; ctx->prof_count[i] = 0; }
   return 0;
 }
 

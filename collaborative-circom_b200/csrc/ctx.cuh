@@ -49,6 +49,13 @@ struct cocg_ctx {
   std::map<std::array<uint32_t, 18>, void*> tables;
   std::vector<cocg::BasesEntry> bases;
   std::vector<cocg::CsrEntry> csrs;
+  // per-kernel-class device timing (cocg_profile_*): event pairs recorded on the launching stream
+  bool profile = false;
+  struct ProfPair { cudaEvent_t a, b; int cls; };
+  std::vector<ProfPair> prof_pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
+  double prof_ms[COCG_PROF_CLASSES] = {};
+  uint64_t prof_count[COCG_PROF_CLASSES] = {};
 };
 
 namespace cocg {
@@ -71,6 +78,22 @@ inline int fail(cocg_ctx* ctx, const std::string& msg) {
     (ctx)->launches++;                         \
     COCG_CUDA(ctx, cudaGetLastError());        \
   } while (0)
+
+// Times everything enqueued on ctx->stream during the scope (only when cocg_profile_enable is on).
+struct ProfScope {
+  cocg_ctx* c;
+  cudaEvent_t stop = nullptr;
+  ProfScope(cocg_ctx* ctx, int cls) : c(ctx) {
+    if (!c->profile) return;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->prof_free.empty()) { ev = c->prof_free.back(); c->prof_free.pop_back(); }
+    else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return;
+    cudaEventRecord(ev.first, c->stream);
+    c->prof_pending.push_back({ev.first, ev.second, cls});
+    stop = ev.second;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, c->stream); }
+};
 
 #define COCG_TRY(expr)        \
   do {                        \

@@ -304,6 +304,8 @@ int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const vo
   COCG_CUDA(ctx, cudaMemsetAsync(counts, 0, nbuckets * 4, st));
   for (int j = 0; j < k; j++) {
     COCG_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
+    {
+    ProfScope prof(ctx, COCG_PROF_MSM_SORT);
     msm_digits_kernel<FrP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars[j], n, c, nwin, mont, dig, counts);
     COCG_LAUNCH_CHECK(ctx);
     scan_block_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, start, nbuckets, bsums);
@@ -314,10 +316,15 @@ int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const vo
     COCG_LAUNCH_CHECK(ctx);
     msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dig, n, nwin, nb, start, counts, sorted);
     COCG_LAUNCH_CHECK(ctx);
+    }
+    {
+    ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
     msm_accumulate_kernel<F><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(base_ptr, sorted, start, nbuckets, buckets, heavy + 1, heavy);
     COCG_LAUNCH_CHECK(ctx);
     msm_heavy_kernel<F><<<kNumSMs, 128, 0, st>>>(base_ptr, sorted, start, buckets, heavy + 1, heavy);
     COCG_LAUNCH_CHECK(ctx);
+    }
+    ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
     msm_reduce_segments_kernel<F><<<(unsigned)((total_segs + 127) / 128), 128, 0, st>>>(buckets, nb, segs, total_segs, pieces);
     COCG_LAUNCH_CHECK(ctx);
     msm_sum_pieces_kernel<F><<<nwin, 128, 0, st>>>(pieces, segs, wsums + (size_t)j * nwin);

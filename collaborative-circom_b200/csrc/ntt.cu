@@ -188,6 +188,7 @@ static int ntt_impl(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, con
   void* scratch = nullptr;
   if (np > 1) COCG_TRY(scratch_get(ctx, 0, (size_t)k * n * sizeof(F), &scratch));
   int k0 = 0;
+  ProfScope prof(ctx, COCG_PROF_NTT);
   for (int p = 0; p < np; p++) {
     int s = sbase + (p < extra ? 1 : 0);
     bool last = (p == np - 1);

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(const uint32_t* __restrict__ 
 template <class P>
 static int spmv_impl(cocg_ctx* ctx, const CsrEntry& m, const void* z_pub, size_t npub, const void* z_wit, void* out) {
   if (m.rows == 0) return 0;
+  ProfScope prof(ctx, COCG_PROF_SPMV);
   spmv_kernel<P><<<(unsigned)((m.rows + 255) / 256), 256, 0, ctx->stream>>>(m.rowptr, m.col, m.coeff, z_pub, (uint32_t)npub, z_wit, out, m.rows);
   COCG_LAUNCH_CHECK(ctx);
   return 0;

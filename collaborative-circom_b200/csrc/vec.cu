@@ -113,6 +113,7 @@ template <class P>
 static int vec_op_impl(cocg_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n) {
   if (n == 0) return 0;
   int grid = grid_for(n, 256, 8);
+  ProfScope prof(ctx, COCG_PROF_VEC);
   switch (op) {
     case COCG_OP_MUL: vec_op_kernel<P, COCG_OP_MUL><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
     case COCG_OP_ADD: vec_op_kernel<P, COCG_OP_ADD><<<grid, 256, 0, ctx->stream>>>(a, b, out, n); break;
@@ -131,6 +132,7 @@ static int rep3_mul_local_impl(cocg_ctx* ctx, const void* aa, const void* ab, co
                                const void* mask, void* out, size_t n) {
   if (n == 0) return 0;
   int grid = grid_for(n, 256, 8);
+  ProfScope prof(ctx, COCG_PROF_VEC);
   if (mask) rep3_mul_local_kernel<P, true><<<grid, 256, 0, ctx->stream>>>(aa, ab, ba, bb, mask, out, n);
   else rep3_mul_local_kernel<P, false><<<grid, 256, 0, ctx->stream>>>(aa, ab, ba, bb, mask, out, n);
   COCG_LAUNCH_CHECK(ctx);
@@ -144,6 +146,7 @@ static int rep3_mul_local_prf_impl(cocg_ctx* ctx, const void* aa, const void* ab
   PrfKey k1, k2;
   memcpy(k1.k, seed_own, 32);
   memcpy(k2.k, seed_prev, 32);
+  ProfScope prof(ctx, COCG_PROF_VEC);
   rep3_mul_local_prf_kernel<P><<<grid_for(n, 256, 8), 256, 0, ctx->stream>>>(aa, ab, ba, bb, k1, k2, ctr, out, n);
   COCG_LAUNCH_CHECK(ctx);
   return 0;

@@ -89,23 +89,57 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
     const size_t m = zk.n_vars, l = zk.n_public;
     const size_t g1b = 2 * lq * 8, g2b = 4 * lq * 8;
     cocg_ctx* c = zk.owner;
-    check(c, cocg_bases_upload(c, COCG_G1, d->a_query, m, g1b, 1, &zk.a_query), "a_query");
-    check(c, cocg_bases_upload(c, COCG_G1, d->b_g1_query, m, g1b, 1, &zk.b_g1_query), "b_g1_query");
-    check(c, cocg_bases_upload(c, COCG_G2, d->b_g2_query, m, g2b, 1, &zk.b_g2_query), "b_g2_query");
-    check(c, cocg_bases_upload(c, COCG_G1, d->h_query, zk.domain_size(), g1b, 1, &zk.h_query), "h_query");
-    check(c, cocg_bases_upload(c, COCG_G1, d->l_query, zk.n_aux(), g1b, 1, &zk.l_query), "l_query");
+    // a query is uploaded from the caller's array, or generated in HBM when the pointer is NULL and a seed is given
+    auto bases = [&](int group, const void* pts, size_t n, int salt, uint64_t* handle, const char* what) {
+      if (pts) {
+        check(c, cocg_bases_upload(c, group, pts, n, group == COCG_G1 ? g1b : g2b, 1, handle), what);
+      } else {
+        if (!d->synthetic_seed) throw Error(std::string("zkey: ") + what + " is NULL and no synthetic_seed was given");
+        uint8_t sd[32];
+        memcpy(sd, d->synthetic_seed, 32);
+        sd[31] ^= (uint8_t)salt;
+        check(c, cocg_bases_generate(c, group, n, sd, handle), what);
+      }
+    };
+    bases(COCG_G1, d->a_query, m, 1, &zk.a_query, "a_query");
+    bases(COCG_G1, d->b_g1_query, m, 2, &zk.b_g1_query, "b_g1_query");
+    bases(COCG_G2, d->b_g2_query, m, 3, &zk.b_g2_query, "b_g2_query");
+    bases(COCG_G1, d->h_query, zk.domain_size(), 4, &zk.h_query, "h_query");
+    bases(COCG_G1, d->l_query, zk.n_aux(), 5, &zk.l_query, "l_query");
     check(c, cocg_csr_upload(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, &zk.csr_a), "csr_a");
     check(c, cocg_csr_upload(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, &zk.csr_b), "csr_b");
-    for (size_t i = 0; i <= l; i++) {
-      zk.a_head.push_back(load_point((const char*)d->a_query + i * g1b, 2 * lq));
-      zk.b_g1_head.push_back(load_point((const char*)d->b_g1_query + i * g1b, 2 * lq));
-      zk.b_g2_head.push_back(load_point((const char*)d->b_g2_query + i * g2b, 4 * lq));
+    zk.a_head.resize(l + 1);
+    zk.b_g1_head.resize(l + 1);
+    zk.b_g2_head.resize(l + 1);
+    {
+      std::vector<uint64_t> buf((l + 1) * 4 * lq);
+      auto heads = [&](uint64_t handle, size_t limbs, std::vector<Point>& dst, const char* what) {
+        check(c, cocg_bases_download(c, handle, 0, l + 1, buf.data()), what);
+        for (size_t i = 0; i <= l; i++) dst[i] = load_point(buf.data() + i * limbs, limbs);
+      };
+      heads(zk.a_query, 2 * lq, zk.a_head, "a_query head");
+      heads(zk.b_g1_query, 2 * lq, zk.b_g1_head, "b_g1_query head");
+      heads(zk.b_g2_query, 4 * lq, zk.b_g2_head, "b_g2_query head");
     }
-    zk.alpha_g1 = load_point(d->alpha_g1, 2 * lq);
-    zk.beta_g1 = load_point(d->beta_g1, 2 * lq);
-    zk.delta_g1 = load_point(d->delta_g1, 2 * lq);
-    zk.beta_g2 = load_point(d->beta_g2, 4 * lq);
-    zk.delta_g2 = load_point(d->delta_g2, 4 * lq);
+    // vk points: given, or three G1 / two G2 synthetic points
+    uint64_t vk1[3][12], vk2[2][24];
+    if (!d->alpha_g1 || !d->beta_g1 || !d->delta_g1 || !d->beta_g2 || !d->delta_g2) {
+      uint64_t h1 = 0, h2 = 0;
+      bases(COCG_G1, nullptr, 3, 6, &h1, "vk g1");
+      bases(COCG_G2, nullptr, 2, 7, &h2, "vk g2");
+      std::vector<uint64_t> b1(3 * 2 * lq), b2(2 * 4 * lq);
+      check(c, cocg_bases_download(c, h1, 0, 3, b1.data()), "vk g1");
+      check(c, cocg_bases_download(c, h2, 0, 2, b2.data()), "vk g2");
+      for (int i = 0; i < 3; i++) memcpy(vk1[i], b1.data() + i * 2 * lq, 2 * lq * 8);
+      for (int i = 0; i < 2; i++) memcpy(vk2[i], b2.data() + i * 4 * lq, 4 * lq * 8);
+      cocg_bases_free(c, h1);
+      cocg_bases_free(c, h2);
+    }
+    zk.alpha_g1 = load_point(d->alpha_g1 ? d->alpha_g1 : vk1[0], 2 * lq);
+    zk.beta_g1 = load_point(d->beta_g1 ? d->beta_g1 : vk1[1], 2 * lq);
+    zk.delta_g1 = load_point(d->delta_g1 ? d->delta_g1 : vk1[2], 2 * lq);
+    zk.beta_g2 = load_point(d->beta_g2 ? d->beta_g2 : vk2[0], 4 * lq);
+    zk.delta_g2 = load_point(d->delta_g2 ? d->delta_g2 : vk2[1], 4 * lq);
     *out = z.release();
   });
 }
@@ -243,8 +277,18 @@ static void pack_partials(const MsmPartials& m, size_t lq, uint64_t* o) {
 
 // Starts one proof on the three party threads.  wit_a[i] / wit_b[i]: HOST share components of party i (n_aux elements).
 // rnd may be NULL (PRF-derived randomness).
+static int rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                            const cohost_rep3_randomness* rnd, bool wit_on_device);
 extern "C" int cohost_rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
                                        const cohost_rep3_randomness* rnd) {
+  return rep3_prove_begin(s, public_inputs, wit_a, wit_b, rnd, false);
+}
+extern "C" int cohost_rep3_prove_begin_device(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a,
+                                              const void* const* wit_b, const cohost_rep3_randomness* rnd) {
+  return rep3_prove_begin(s, public_inputs, wit_a, wit_b, rnd, true);
+}
+static int rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                            const cohost_rep3_randomness* rnd, bool wit_on_device) {
   if (!s || !public_inputs || !wit_a || !wit_b) return fail("cohost_rep3_prove_begin: null argument");
   if (s->running) return fail("cohost_rep3_prove_begin: a proof is already in flight");
   if (s->failed) return fail("cohost_rep3_prove_begin: the session's network is closed after an earlier failure");
@@ -287,9 +331,15 @@ extern "C" int cohost_rep3_prove_begin(cohost_rep3_session* s, const void* publi
         memcpy(pub_host.data(), public_inputs, zk.num_inputs() * 32);
         d.release(s->pub[i]);
         s->pub[i] = d.upload(public_inputs, zk.num_inputs());
-        FieldShareVec wit = d.share_vec_from_host(wit_a_i, wit_b_i, zk.n_aux());
+        FieldShareVec wit;
+        if (wit_on_device) {  // borrowed: the caller keeps ownership
+          wit.a = DevVec{const_cast<void*>(wit_a_i), zk.n_aux()};
+          wit.b = DevVec{const_cast<void*>(wit_b_i), zk.n_aux()};
+        } else {
+          wit = d.share_vec_from_host(wit_a_i, wit_b_i, zk.n_aux());
+        }
         s->proofs[i] = s->prover[i]->prove(zk, s->hd[i], s->pub[i], pub_host, wit);
-        d.release(wit);
+        if (!wit_on_device) d.release(wit);
         d.injected = nullptr;
       } catch (const std::exception& e) {
         s->errs[i] = e.what();
@@ -379,4 +429,30 @@ extern "C" uint64_t cohost_rep3_launch_count(cohost_rep3_session* s) {
   if (s)
     for (int i = 0; i < 3; i++) t += cocg_launch_count(s->drv[i]->ctx);
   return t;
+}
+
+extern "C" int cohost_rep3_profile_enable(cohost_rep3_session* s, int on) {
+  if (!s) return fail("null session");
+  for (int i = 0; i < 3; i++) cocg_profile_enable(s->drv[i]->ctx, on);
+  return 0;
+}
+extern "C" int cohost_rep3_profile_read(cohost_rep3_session* s, int cls, double* total_ms, uint64_t* scopes) {
+  if (!s) return fail("null session");
+  double t = 0;
+  uint64_t n = 0;
+  for (int i = 0; i < 3; i++) {
+    double ms = 0;
+    uint64_t k = 0;
+    if (cocg_profile_read(s->drv[i]->ctx, cls, &ms, &k)) return fail(cocg_last_error(s->drv[i]->ctx));
+    t += ms;
+    n += k;
+  }
+  if (total_ms) *total_ms = t;
+  if (scopes) *scopes = n;
+  return 0;
+}
+extern "C" int cohost_rep3_profile_reset(cohost_rep3_session* s) {
+  if (!s) return fail("null session");
+  for (int i = 0; i < 3; i++) cocg_profile_reset(s->drv[i]->ctx);
+  return 0;
 }

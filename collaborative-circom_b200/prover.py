@@ -20,8 +20,10 @@ HOST_SYMBOLS = [
     "cohost_last_error", "cohost_zkey_create", "cohost_zkey_destroy", "cohost_plain_session_create",
     "cohost_plain_session_destroy", "cohost_plain_prove", "cohost_rep3_session_create", "cohost_rep3_session_destroy",
     "cohost_rep3_prove_begin", "cohost_rep3_partial_bytes", "cohost_rep3_prove_partials", "cohost_rep3_prove_combine",
-    "cohost_rep3_prove_end", "cohost_rep3_launch_count",
+    "cohost_rep3_prove_end", "cohost_rep3_launch_count", "cohost_rep3_prove_begin_device", "cohost_rep3_profile_enable",
+    "cohost_rep3_profile_read", "cohost_rep3_profile_reset",
 ]
+PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
 vp, sz, ci, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
 
@@ -31,7 +33,7 @@ class ZKeyDesc(ctypes.Structure):
                 ("a_rowptr", vp), ("a_col", vp), ("a_coeff", vp), ("a_nnz", sz),
                 ("b_rowptr", vp), ("b_col", vp), ("b_coeff", vp), ("b_nnz", sz),
                 ("a_query", vp), ("b_g1_query", vp), ("b_g2_query", vp), ("h_query", vp), ("l_query", vp),
-                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp)]
+                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp)]
 
 
 class Rep3Randomness(ctypes.Structure):
@@ -62,6 +64,10 @@ def load_host():
     L.cohost_rep3_session_destroy.argtypes = [vp]
     L.cohost_rep3_session_destroy.restype = None
     L.cohost_rep3_prove_begin.argtypes = [vp, vp, pvp, pvp, ctypes.POINTER(Rep3Randomness)]
+    L.cohost_rep3_prove_begin_device.argtypes = [vp, vp, pvp, pvp, ctypes.POINTER(Rep3Randomness)]
+    L.cohost_rep3_profile_enable.argtypes = [vp, ci]
+    L.cohost_rep3_profile_read.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
+    L.cohost_rep3_profile_reset.argtypes = [vp]
     L.cohost_rep3_partial_bytes.argtypes = [vp]
     L.cohost_rep3_partial_bytes.restype = sz
     L.cohost_rep3_prove_partials.argtypes = [vp, vp]
@@ -86,7 +92,9 @@ class Groth16ZKey:
     """A Groth16 proving key resident in HBM (query arrays as MSM bases, A/B matrices as CSR)."""
 
     def __init__(self, curve: int, n_public: int, n_vars: int, pow_: int, num_constraints: int, a_csr, b_csr,
-                 a_query, b_g1_query, b_g2_query, h_query, l_query, alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2, device: int = 0):
+                 a_query=None, b_g1_query=None, b_g2_query=None, h_query=None, l_query=None, alpha_g1=None, beta_g1=None,
+                 delta_g1=None, beta_g2=None, delta_g2=None, device: int = 0, synthetic_seed: bytes | None = None):
+        """Query / vk arrays left as None are generated in HBM from `synthetic_seed` (32 bytes)."""
         L = load_host()
         self.curve, self.lq = curve, (4 if curve == _lib.BN254 else 6)
         self.n_public, self.n_vars, self.pow, self.num_constraints = n_public, n_vars, pow_, num_constraints
@@ -106,10 +114,18 @@ class Groth16ZKey:
         lq = self.lq
         for name, arr, n, w in (("a_query", a_query, n_vars, 2), ("b_g1_query", b_g1_query, n_vars, 2), ("b_g2_query", b_g2_query, n_vars, 4),
                                 ("h_query", h_query, 1 << pow_, 2), ("l_query", l_query, self.n_aux, 2)):
+            if arr is None:
+                assert synthetic_seed is not None, f"{name} missing and no synthetic_seed"
+                continue
             arr = _c(arr)
             assert arr.size == n * w * lq, f"{name}: expected {n} points"
             setattr(d, name, P(arr))
-        d.alpha_g1, d.beta_g1, d.delta_g1, d.beta_g2, d.delta_g2 = P(alpha_g1), P(beta_g1), P(delta_g1), P(beta_g2), P(delta_g2)
+        for name, arr in (("alpha_g1", alpha_g1), ("beta_g1", beta_g1), ("delta_g1", delta_g1), ("beta_g2", beta_g2), ("delta_g2", delta_g2)):
+            if arr is not None:
+                setattr(d, name, P(arr))
+        if synthetic_seed is not None:
+            assert len(synthetic_seed) == 32
+            d.synthetic_seed = P(np.frombuffer(synthetic_seed, dtype=np.uint8), np.uint8)
         h = vp()
         _ck(L.cohost_zkey_create(ctypes.byref(d), ctypes.byref(h)))
         self.h = h
@@ -162,13 +178,24 @@ class Rep3Session:
     def partial_bytes(self) -> int:
         return int(load_host().cohost_rep3_partial_bytes(self.h))
 
-    def begin(self, public_inputs, wit_a, wit_b, rnd: dict | None = None):
+    def begin(self, public_inputs, wit_a, wit_b, rnd: dict | None = None, device_ptrs: bool = False):
+        """wit_a / wit_b: three host arrays each (numpy, or raw HOST addresses of pinned buffers given as int), or -- with
+        device_ptrs=True -- three DEVICE addresses each."""
         zk = self.zkey
-        self._keep = [_c(public_inputs)] + [_c(x) for x in wit_a] + [_c(x) for x in wit_b]
-        pub, wa, wb = self._keep[0], self._keep[1:4], self._keep[4:7]
-        assert pub.size == 4 * (zk.n_public + 1) and all(x.size == 4 * zk.n_aux for x in wa + wb)
-        A = (vp * 3)(*[x.ctypes.data for x in wa])
-        B = (vp * 3)(*[x.ctypes.data for x in wb])
+        self._keep = [_c(public_inputs)]
+        pub = self._keep[0]
+        assert pub.size == 4 * (zk.n_public + 1)
+
+        def addr(x):
+            if isinstance(x, int):
+                return x
+            a = _c(x)
+            assert a.size == 4 * zk.n_aux
+            self._keep.append(a)
+            return a.ctypes.data
+
+        A = (vp * 3)(*[addr(x) for x in wit_a])
+        B = (vp * 3)(*[addr(x) for x in wit_b])
         R = None
         if rnd is not None:
             R = Rep3Randomness()
@@ -181,7 +208,8 @@ class Rep3Session:
                 self._keep += arrs
                 setattr(R, k, (vp * 3)(*[x.ctypes.data for x in arrs]))
             self._keep.append(R)
-        _ck(load_host().cohost_rep3_prove_begin(self.h, pub.ctypes.data, A, B, None if R is None else ctypes.byref(R)))
+        fn = load_host().cohost_rep3_prove_begin_device if device_ptrs else load_host().cohost_rep3_prove_begin
+        _ck(fn(self.h, pub.ctypes.data, A, B, None if R is None else ctypes.byref(R)))
 
     def partials(self) -> np.ndarray:
         out = np.zeros(self.partial_bytes() // 8, dtype=np.uint64)
@@ -207,9 +235,23 @@ class Rep3Session:
         self._keep = None
         return (proofs, ha, hb) if want_h else proofs
 
-    def prove(self, public_inputs, wit_a, wit_b, rnd=None, want_h=False, all_gather=None):
+    def profile(self, on: bool = True):
+        _ck(load_host().cohost_rep3_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        _ck(load_host().cohost_rep3_profile_reset(self.h))
+
+    def profile_read(self) -> dict:
+        out = {}
+        for i, name in enumerate(PROF_CLASSES):
+            ms, k = ctypes.c_double(), u64()
+            _ck(load_host().cohost_rep3_profile_read(self.h, i, ctypes.byref(ms), ctypes.byref(k)))
+            out[name] = (ms.value, int(k.value))
+        return out
+
+    def prove(self, public_inputs, wit_a, wit_b, rnd=None, want_h=False, all_gather=None, device_ptrs=False):
         """One proof.  all_gather(partials: np.ndarray) -> concatenation over ranks; required when world > 1."""
-        self.begin(public_inputs, wit_a, wit_b, rnd)
+        self.begin(public_inputs, wit_a, wit_b, rnd, device_ptrs)
         if self.world > 1:
             self.combine(all_gather(self.partials()))
         return self.end(want_h)

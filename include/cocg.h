@@ -55,6 +55,14 @@ COCG_API int cocg_sync(cocg_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench.py's `gpu_launches`). */
 COCG_API uint64_t cocg_launch_count(cocg_ctx* ctx);
 
+/* Device-side timing per kernel class (CUDA events on the launching stream; bench.py's roofline numbers).  read: waits
+ * for the stream, then returns the summed milliseconds and the number of timed scopes of `cls` since the last reset. */
+enum { COCG_PROF_MSM_SORT = 0, COCG_PROF_MSM_ACCUMULATE = 1, COCG_PROF_MSM_REDUCE = 2, COCG_PROF_NTT = 3, COCG_PROF_VEC = 4,
+       COCG_PROF_SPMV = 5, COCG_PROF_CLASSES = 6 };
+COCG_API int cocg_profile_enable(cocg_ctx* ctx, int on);
+COCG_API int cocg_profile_read(cocg_ctx* ctx, int cls, double* total_ms, uint64_t* scopes);
+COCG_API int cocg_profile_reset(cocg_ctx* ctx);
+
 /* ---- device memory (so that share vectors can stay resident between MPC network rounds) ------------- */
 COCG_API int cocg_malloc(cocg_ctx* ctx, size_t bytes, void** dptr);
 COCG_API int cocg_free(cocg_ctx* ctx, void* dptr);
@@ -109,6 +117,11 @@ COCG_API int cocg_ntt(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, c
  * mont = 1 if coordinates are Montgomery limbs, 0 if canonical. */
 COCG_API int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size_t n, size_t stride, int mont, uint64_t* handle);
 COCG_API int cocg_bases_free(cocg_ctx* ctx, uint64_t handle);
+/* Synthetic bases generated in HBM: P0 + i*Q for two points derived from `seed` (HOST pointer, 32 bytes) -- valid, distinct
+ * curve points for the 2^20..2^22 benchmark configurations, for which no zkey ships (csrc/gen.cu). */
+COCG_API int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const void* seed, uint64_t* handle);
+/* Copy n packed affine points starting at `off` back to the HOST. */
+COCG_API int cocg_bases_download(cocg_ctx* ctx, uint64_t handle, size_t off, size_t n, void* out);
 /* Non-owning alias of another context's bases on the same device: the three REP3 drivers of one process borrow the
  * same &ZKey (tests/tests/circom/e2e_tests/mod.rs:55-70).  The owner must outlive the alias. */
 COCG_API int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handle, uint64_t* handle);

@@ -40,6 +40,9 @@ typedef struct cohost_zkey_desc {
   const void *h_query;                             /* 2^pow G1 points */
   const void *l_query;                             /* m - l - 1 G1 points */
   const void *alpha_g1, *beta_g1, *delta_g1, *beta_g2, *delta_g2;
+  /* NULL, or 32 bytes: every query / vk pointer above that is NULL is filled with synthetic curve points generated in HBM
+   * (cocg_bases_generate) -- the shape-faithful 2^20-constraint benchmark key, for which no zkey ships. */
+  const void* synthetic_seed;
 } cohost_zkey_desc;
 
 /* Injected randomness for parity tests (the reference draws all of it from entropy). */
@@ -71,6 +74,13 @@ COHOST_API void cohost_rep3_session_destroy(cohost_rep3_session* s);
  * components (m - l - 1 Fr each).  rnd: NULL for PRF-derived randomness. */
 COHOST_API int cohost_rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
                                        const cohost_rep3_randomness* rnd);
+/* Same with the witness share components already resident in HBM (DEVICE pointers on the session's device). */
+COHOST_API int cohost_rep3_prove_begin_device(cohost_rep3_session* s, const void* public_inputs, const void* const* wit_a,
+                                              const void* const* wit_b, const cohost_rep3_randomness* rnd);
+/* Per-kernel-class device time summed over the three drivers (cocg_profile_*; classes COCG_PROF_*). */
+COHOST_API int cohost_rep3_profile_enable(cohost_rep3_session* s, int on);
+COHOST_API int cohost_rep3_profile_read(cohost_rep3_session* s, int cls, double* total_ms, uint64_t* scopes);
+COHOST_API int cohost_rep3_profile_reset(cohost_rep3_session* s);
 COHOST_API size_t cohost_rep3_partial_bytes(cohost_rep3_session* s);
 COHOST_API int cohost_rep3_prove_partials(cohost_rep3_session* s, void* out);
 COHOST_API int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gathered);
