@@ -17,8 +17,9 @@ namespace cocg {
 constexpr int kNumSMs = 148;  // B200; grids are sized in multiples of this
 
 struct BasesEntry {
-  void* d = nullptr;  // packed Montgomery affine points
+  void* d = nullptr;  // table T[j][i] = 2^(c*j) P_i of packed Montgomery affine points, j < nwin (T[0] = the bases)
   size_t n = 0;
+  int c = 0, nwin = 1;  // window bits the table was built for (msm_impl.cuh)
   int group = 0;
   size_t point_bytes = 0;
   bool owned = true;  // false: alias of another context's allocation (cocg_bases_share)

@@ -11,6 +11,8 @@
 #include "prf.cuh"
 
 namespace cocg {
+int msm_table_windows(int curve, size_t n);
+int msm_precompute(cocg_ctx* ctx, BasesEntry& be);
 
 constexpr int kGenRun = 16;
 
@@ -92,7 +94,7 @@ extern "C" int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const voi
   be.n = n;
   be.group = group;
   be.point_bytes = (ctx->curve == COCG_BN254 ? 32 : 48) * 2 * (size_t)group;
-  COCG_CUDA(ctx, cudaMalloc(&be.d, n ? n * be.point_bytes : 16));
+  COCG_CUDA(ctx, cudaMalloc(&be.d, n ? (size_t)msm_table_windows(ctx->curve, n) * n * be.point_bytes : 16));
   if (n) {
     int rc;
     const uint8_t* sd = (const uint8_t*)seed;
@@ -100,6 +102,8 @@ extern "C" int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const voi
     else rc = group == COCG_G1 ? generate_impl<Bls381Fq>(ctx, group, n, sd, be.d) : generate_impl<Bls381Fq2>(ctx, group, n, sd, be.d);
     if (rc) { cudaFree(be.d); return rc; }
   }
+  COCG_TRY(msm_precompute(ctx, be));
+  COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < ctx->bases.size(); i++)
     if (!ctx->bases[i].d) { ctx->bases[i] = be; *handle = i + 1; return 0; }
   ctx->bases.push_back(be);

@@ -4,10 +4,26 @@
 #include "ctx.cuh"
 
 namespace cocg {
-int msm_bn254_g1(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
-int msm_bn254_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
-int msm_bls381_g1(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
-int msm_bls381_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
+#define COCG_MSM_DECL(NAME)                                                                                                           \
+  int msm_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac); \
+  int msm_precompute_##NAME(cocg_ctx* ctx, BasesEntry& be);
+COCG_MSM_DECL(bn254_g1)
+COCG_MSM_DECL(bn254_g2)
+COCG_MSM_DECL(bls381_g1)
+COCG_MSM_DECL(bls381_g2)
+
+// window bits / count for a query of n points: must match msm_impl.cuh (the table is allocated before it is built)
+int msm_table_windows(int curve, size_t n) {
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= n) lg++;
+  int c = lg < 4 ? 4 : (lg > 20 ? 20 : lg);
+  int bits = curve == COCG_BN254 ? 254 : 255;
+  return (bits + c) / c;
+}
+int msm_precompute(cocg_ctx* ctx, BasesEntry& be) {
+  if (ctx->curve == COCG_BN254) return be.group == COCG_G1 ? msm_precompute_bn254_g1(ctx, be) : msm_precompute_bn254_g2(ctx, be);
+  return be.group == COCG_G1 ? msm_precompute_bls381_g1(ctx, be) : msm_precompute_bls381_g2(ctx, be);
+}
 
 template <class F>
 __global__ void __launch_bounds__(256) bases_to_mont_kernel(void* pts, size_t ncoords) {
@@ -33,7 +49,7 @@ extern "C" int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size
   if (stride < pb) return fail(ctx, "cocg_bases_upload: stride smaller than a packed point");
   BasesEntry be;
   be.n = n; be.group = group; be.point_bytes = pb;
-  COCG_CUDA(ctx, cudaMalloc(&be.d, n ? n * pb : 16));
+  COCG_CUDA(ctx, cudaMalloc(&be.d, n ? (size_t)msm_table_windows(ctx->curve, n) * n * pb : 16));
   if (n) {
     COCG_CUDA(ctx, cudaMemcpy2DAsync(be.d, pb, pts, stride, pb, n, cudaMemcpyHostToDevice, ctx->stream));
     if (!mont) {
@@ -42,8 +58,10 @@ extern "C" int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size
       else bases_to_mont_kernel<Bls381Fq><<<(unsigned)((ncoords + 255) / 256), 256, 0, ctx->stream>>>(be.d, ncoords);
       COCG_LAUNCH_CHECK(ctx);
     }
-    COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  COCG_TRY(msm_precompute(ctx, be));  // T[j] = 2^(c*j) * bases, j < nwin
+  if (be.nwin != msm_table_windows(ctx->curve, n)) return fail(ctx, "cocg_bases_upload: window plan mismatch");
+  COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // reuse a free slot if any
   for (size_t i = 0; i < ctx->bases.size(); i++)
     if (!ctx->bases[i].d) { ctx->bases[i] = be; *handle = i + 1; return 0; }
@@ -103,7 +121,7 @@ extern "C" int cocg_msm_host(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n
   if (k > 8) return fail(ctx, "cocg_msm_host: at most 8 components");
   if (!scalars) return fail(ctx, "cocg_msm_host: null argument");
   void* dev = nullptr;
-  COCG_TRY(scratch_get(ctx, 10, (size_t)k * n * 32 + 32, &dev));
+  COCG_TRY(scratch_get(ctx, 11, (size_t)k * n * 32 + 32, &dev));
   const void* dptr[8];
   for (int j = 0; j < k; j++) {
     if (n && !scalars[j]) return fail(ctx, "cocg_msm_host: null scalar vector");

@@ -4,4 +4,5 @@ namespace cocg {
 int msm_bn254_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac) {
   return msm_impl<Bn254Fq2, Bn254FrP>(ctx, be, off, n, scalars, k, mont, out_jac);
 }
+int msm_precompute_bn254_g2(cocg_ctx* ctx, BasesEntry& be) { return msm_precompute_impl<Bn254Fq2, Bn254FrP>(ctx, be); }
 }  // namespace cocg

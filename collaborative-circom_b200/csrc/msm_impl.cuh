@@ -4,19 +4,25 @@
 // plain.rs:408-416; the algorithm itself is ark-ec 0.4.2's Pippenger, not vendored).  The result is the same
 // group element; only its Jacobian representative may differ.
 //
+// B200-first design: the bases of a zkey query are public and reused by every proof (the reference borrows &ZKey for
+// the whole prove, groth16.rs:113-117), and HBM is the abundant resource (180 GB), so the window structure of Pippenger
+// is moved into memory.  At upload time the table T[j][i] = 2^(c*j) * P_i, j < nwin = ceil((bits+1)/c), is built once
+// (affine, 13 x the query at c = 20).  A signed digit d of window j of scalar s_i then contributes
+// sign(d) * T[j][i] to bucket |d| of ONE shared bucket set, so that
+//     sum_i s_i P_i = sum_b b * B_b,      B_b = sum of the table points whose digit is +-b,
+// with a single bucket reduction per MSM instead of one per window and no doublings at all on the path.
 // Pipeline per share component (all on the context's stream):
 //   1. digits      scalars leave Montgomery form and are recoded into signed c-bit digits (|d| <= 2^(c-1));
-//                  a histogram of (window, |d|) is taken with global atomics
+//                  histogram of |d| with global atomics
 //   2. scan        exclusive prefix sum of the histogram -> bucket offsets
-//   3. scatter     counting sort: point indices (sign in bit 31) grouped by (window, bucket)
-//   4. accumulate  one thread per bucket walks its index run, gathers affine points with 128-bit loads and
-//                  adds them into an XYZZ accumulator (8M + 2S per point); runs longer than kHeavy (skewed
-//                  scalars) are deferred to a warp-per-bucket kernel that tree-combines with warp shuffles
-//   5. reduce      sum_b (b+1) * B_b per window: threads take 16-bucket segments (running-sum trick) and
-//                  lift them by a short double-and-add; a CTA per window sums the lifted pieces
-//   6. fold        the <= 64 window sums go to the host, which does the 2^c Horner fold (sequential doublings
-//                  are latency-bound on a GPU and O(1) for the caller)
-// Shares are uniformly random, so buckets are balanced (N / 2^(c-1) ~ 32 points each at c = log2 N - 4).
+//   3. scatter     counting sort: (window, point index, sign) entries grouped by bucket
+//   4. accumulate  one thread per bucket walks its run, gathers affine table points with 128-bit loads and adds them
+//                  into an XYZZ accumulator (8M + 2S per point); runs longer than kHeavy (skewed scalars: plain-driver
+//                  witnesses) are deferred to a warp-per-bucket kernel that tree-combines with warp shuffles
+//   5. reduce      sum_b (b+1) B_b with b = hi*L + lo:  sum_hi (L*hi + 1) R_hi + sum_lo lo * C_lo  for the row sums
+//                  R_hi = sum_lo B and column sums C_lo = sum_hi B -- two parallel marginal reductions (a warp per
+//                  row / column) instead of a sequential running sum, then one small tree sum
+// Shares are uniformly random, so buckets are balanced (N * nwin / 2^(c-1) ~ 26 points each at N = 2^20, c = 20).
 #pragma once
 #include <string.h>
 
@@ -24,17 +30,64 @@
 
 namespace cocg {
 
-constexpr int kMaxWindows = 96;
-constexpr int kHeavy = 256;     // runs longer than this go to the warp-per-bucket kernel
-constexpr int kSeg = 16;        // buckets per thread in the reduce kernel
+constexpr int kHeavy = 512;          // runs longer than this go to the warp-per-bucket kernel
+constexpr int kMsmMaxC = 20;         // 2^19 buckets; table = 13 x the query for 254/255-bit scalars
+constexpr int kIdxBits = 25;         // entry = sign << 31 | window << 25 | point index
 
 static int msm_window_bits(size_t n) {
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg - 4;
+  int c = lg;
   if (c < 4) c = 4;
-  if (c > 16) c = 16;
+  if (c > kMsmMaxC) c = kMsmMaxC;
   return c;
+}
+template <class FrP>
+static int msm_num_windows(int c) {
+  return (FrP::BITS + c) / c;  // ceil((BITS+1)/c): room for the final carry of the signed recoding
+}
+
+// ------------------------------------------------------------------ 0. table precompute (upload time)
+// thread i: T[j][i] = 2^(c*j) P_i for j = 1..nwin-1, normalised to affine with one shared inversion per group of
+// kPreGroup windows
+constexpr int kPreGroup = 16;
+template <class F>
+__global__ void __launch_bounds__(128) msm_precompute_kernel(Affine<F>* __restrict__ table, size_t n, int c, int nwin) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = table[i];
+  if (p.is_inf()) {
+    for (int j = 1; j < nwin; j++) table[(size_t)j * n + i] = p;
+    return;
+  }
+  XYZZ<F> pts[kPreGroup];
+  F pref[kPreGroup];
+  XYZZ<F> acc = xyzz_from_affine(p);
+  for (int j0 = 1; j0 < nwin; j0 += kPreGroup) {
+    const int cnt = nwin - j0 < kPreGroup ? nwin - j0 : kPreGroup;
+    F run = F::one();
+    for (int t = 0; t < cnt; t++) {
+      for (int q = 0; q < c; q++) acc = xyzz_dbl(acc);
+      pts[t] = acc;
+      pref[t] = run;
+      if (!acc.is_inf()) run = f_mul(run, acc.zzz);
+    }
+    F inv = f_inv(run);
+    for (int t = cnt - 1; t >= 0; t--) {
+      Affine<F> a;
+      if (pts[t].is_inf()) {
+        a.x = F::zero();
+        a.y = F::zero();
+      } else {
+        F w = f_mul(inv, pref[t]);   // 1 / zzz_t
+        inv = f_mul(inv, pts[t].zzz);
+        F zi = f_mul(pts[t].zz, w);  // 1 / z
+        a.x = f_mul(pts[t].x, f_sqr(zi));
+        a.y = f_mul(pts[t].y, w);
+      }
+      table[(size_t)(j0 + t) * n + i] = a;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ 1. digits + histogram
@@ -63,7 +116,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void* __restrict_
     }
     uint32_t d = raw + carry;
     carry = 0;
-    uint32_t enc = 0;  // 0 = skip; else (bucket+1) | sign << 31
+    uint32_t enc = 0;  // 0 = skip; else |digit| | sign << 31
     if (d > nb) {
       enc = ((1u << c) - d) | 0x80000000u;
       carry = 1;
@@ -72,7 +125,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void* __restrict_
       enc = d;
     }
     dig[(size_t)w * n + i] = enc;
-    if (enc & 0x7fffffffu) atomicAdd(&counts[(size_t)w * nb + ((enc & 0x7fffffffu) - 1)], 1u);
+    if (enc & 0x7fffffffu) atomicAdd(&counts[(enc & 0x7fffffffu) - 1], 1u);
   }
 }
 
@@ -132,8 +185,42 @@ static __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(uint32_t*
   if (blockIdx.x == 0 && threadIdx.x == 0) out[m] = *total;
 }
 
+// ------------------------------------------------------------------ 2b. bucket order by size
+// Threads of a warp walk their buckets in lock-step, so a warp costs as much as its largest bucket.  Buckets are handed
+// out in descending size order (counting sort on the size, sizes > kHeavy share the first bin).
+constexpr int kSizeBins = kHeavy + 2;
+static __global__ void __launch_bounds__(256) bucket_size_hist_kernel(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kSizeBins];
+  for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+    uint32_t s = counts[b];
+    atomicAdd(&sh[s > (uint32_t)kHeavy ? kHeavy + 1 : s], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// hist[s] <- number of buckets larger than s (start of size class s in the descending order); one thread, 514 steps
+static __global__ void bucket_size_scan_kernel(uint32_t* hist) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t run = 0;
+  for (int s = kSizeBins - 1; s >= 0; s--) {
+    uint32_t v = hist[s];
+    hist[s] = run;
+    run += v;
+  }
+}
+static __global__ void __launch_bounds__(256) bucket_order_kernel(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ pos,
+                                                            uint32_t* __restrict__ order) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t s = counts[b];
+  order[atomicAdd(&pos[s > (uint32_t)kHeavy ? kHeavy + 1 : s], 1u)] = b;
+}
+
 // ------------------------------------------------------------------ 3. scatter (counting sort by bucket)
-static __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __restrict__ dig, size_t n, int nwin, uint32_t nb,
+static __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* __restrict__ dig, size_t n, int nwin,
                                                            const uint32_t* __restrict__ start, uint32_t* __restrict__ counts,
                                                            uint32_t* __restrict__ sorted) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,9 +229,8 @@ static __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t*
     uint32_t enc = dig[(size_t)w * n + i];
     uint32_t b = enc & 0x7fffffffu;
     if (!b) continue;
-    size_t gb = (size_t)w * nb + (b - 1);
-    uint32_t slot = atomicSub(&counts[gb], 1u) - 1u;  // counts[] drains back to zero
-    sorted[start[gb] + slot] = (uint32_t)i | (enc & 0x80000000u);
+    uint32_t slot = atomicSub(&counts[b - 1], 1u) - 1u;  // counts[] drains back to zero
+    sorted[start[b - 1] + slot] = (uint32_t)i | ((uint32_t)w << kIdxBits) | (enc & 0x80000000u);
   }
 }
 
@@ -172,11 +258,14 @@ __device__ __forceinline__ T warp_shfl_down(const T& v, int delta) {
   for (int k = 0; k < W; k++) d[k] = __shfl_down_sync(0xffffffffu, s[k], delta);
   return r;
 }
+// table: T[w][off + i], window stride `tstride` points
 template <class F>
-__device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const void* bases, const uint32_t* sorted, uint32_t beg, uint32_t end, uint32_t step) {
+__device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const void* table, size_t tstride, const uint32_t* sorted, uint32_t beg, uint32_t end,
+                                               uint32_t step) {
   for (uint32_t e = beg; e < end; e += step) {
     uint32_t v = sorted[e];
-    Affine<F> p = load_affine<F>(bases, v & 0x7fffffffu);
+    size_t idx = (size_t)((v >> kIdxBits) & 63u) * tstride + (v & ((1u << kIdxBits) - 1));
+    Affine<F> p = load_affine<F>(table, idx);
     if (v >> 31) p.y = f_neg(p.y);
     xyzz_madd(acc, p);
   }
@@ -184,23 +273,25 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const void* bases, 
 
 // ------------------------------------------------------------------ 4. bucket accumulation
 template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                              const uint32_t* __restrict__ start, size_t nbuckets, XYZZ<F>* __restrict__ buckets,
-                                                              uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
-  size_t gb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gb >= nbuckets) return;
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
+                                                              const uint32_t* __restrict__ start, const uint32_t* __restrict__ order, uint32_t nbuckets,
+                                                              XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_list,
+                                                              uint32_t* __restrict__ heavy_count) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets) return;
+  const uint32_t gb = order[t];
   uint32_t beg = start[gb], end = start[gb + 1];
   if (end - beg > (uint32_t)kHeavy) {
-    heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)gb;
+    heavy_list[atomicAdd(heavy_count, 1u)] = gb;
     return;
   }
   XYZZ<F> acc = xyzz_inf<F>();
-  accumulate_run<F>(acc, bases, sorted, beg, end, 1);
+  accumulate_run<F>(acc, table, tstride, sorted, beg, end, 1);
   buckets[gb] = acc;
 }
 // one warp per heavy bucket: lanes stride through the run, then a shuffle tree combines the 32 partial sums
 template <class F>
-__global__ void __launch_bounds__(128) msm_heavy_kernel(const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128) msm_heavy_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
                                                          const uint32_t* __restrict__ start, XYZZ<F>* __restrict__ buckets,
                                                          const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count) {
   const uint32_t lane = threadIdx.x & 31;
@@ -209,7 +300,7 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const void* __restrict__
   for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < total; h += nwarps) {
     uint32_t gb = heavy_list[h];
     XYZZ<F> acc = xyzz_inf<F>();
-    accumulate_run<F>(acc, bases, sorted, start[gb] + lane, start[gb + 1], 32);
+    accumulate_run<F>(acc, table, tstride, sorted, start[gb] + lane, start[gb + 1], 32);
     for (int delta = 16; delta >= 1; delta >>= 1) {
       XYZZ<F> other = warp_shfl_down(acc, delta);
       if (lane < (uint32_t)delta) xyzz_add(acc, other);
@@ -218,41 +309,49 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const void* __restrict__
   }
 }
 
-// ------------------------------------------------------------------ 5. per-window bucket reduction
+// ------------------------------------------------------------------ 5. bucket reduction
 template <class F>
 __device__ __forceinline__ XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) {
   XYZZ<F> acc = xyzz_inf<F>();
-  for (int b = 31 - __clz(k | 1); b >= 0; b--) {
+  if (k == 0) return acc;
+  for (int b = 31 - __clz(k); b >= 0; b--) {
     acc = xyzz_dbl(acc);
     if ((k >> b) & 1) xyzz_add(acc, p);
   }
   return acc;
 }
-// thread (w, g): buckets [g*kSeg, g*kSeg + len) of window w hold weights g*kSeg+1 .. ; emits
-//   piece = sum_t (t+1) * B[g*kSeg+t] + (g*kSeg) * sum_t B[g*kSeg+t]
+// Buckets form an H x L matrix (b = hi * L + lo).  Warp w < H: weighted row sum (L*w + 1) * sum_lo B[w][lo];
+// warp H + w: weighted column sum w * sum_hi B[hi][w].  Output: H + L points whose plain sum is the MSM.
 template <class F>
-__global__ void __launch_bounds__(128) msm_reduce_segments_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t nb, uint32_t segs_per_window,
-                                                                   size_t total_segs, XYZZ<F>* __restrict__ pieces) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total_segs) return;
-  uint32_t w = (uint32_t)(t / segs_per_window), g = (uint32_t)(t % segs_per_window);
-  uint32_t lo = g * kSeg, hi = lo + kSeg < nb ? lo + kSeg : nb;
-  const XYZZ<F>* B = buckets + (size_t)w * nb;
-  XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>();
-  for (uint32_t b = hi; b-- > lo;) {
-    xyzz_add(run, B[b]);
-    xyzz_add(acc, run);
-  }
-  if (lo) xyzz_add(acc, xyzz_mul_small(run, lo));
-  pieces[t] = acc;
-}
-// one CTA per window: sum the window's pieces
-template <class F>
-__global__ void __launch_bounds__(128) msm_sum_pieces_kernel(const XYZZ<F>* __restrict__ pieces, uint32_t segs_per_window, XYZZ<F>* __restrict__ window_sums) {
-  __shared__ XYZZ<F> sh[4];
-  const XYZZ<F>* Pw = pieces + (size_t)blockIdx.x * segs_per_window;
+__global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
+                                                             XYZZ<F>* __restrict__ out) {
+  const uint32_t H = 1u << logH, L = 1u << logL;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= H + L) return;
   XYZZ<F> acc = xyzz_inf<F>();
-  for (uint32_t i = threadIdx.x; i < segs_per_window; i += blockDim.x) xyzz_add(acc, Pw[i]);
+  uint32_t weight;
+  if (warp < H) {
+    const XYZZ<F>* row = buckets + ((size_t)warp << logL);
+    for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add(acc, row[lo]);
+    weight = (warp << logL) + 1;
+  } else {
+    const uint32_t lo = warp - H;
+    for (uint32_t hi = lane; hi < H; hi += 32) xyzz_add(acc, buckets[((size_t)hi << logL) + lo]);
+    weight = lo;
+  }
+  for (int delta = 16; delta >= 1; delta >>= 1) {
+    XYZZ<F> other = warp_shfl_down(acc, delta);
+    if (lane < (uint32_t)delta) xyzz_add(acc, other);
+  }
+  if (lane == 0) out[warp] = xyzz_mul_small(acc, weight);
+}
+// one CTA: plain sum of m points
+template <class F>
+__global__ void __launch_bounds__(256) msm_sum_kernel(const XYZZ<F>* __restrict__ in, uint32_t m, XYZZ<F>* __restrict__ out) {
+  __shared__ XYZZ<F> sh[8];
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) xyzz_add(acc, in[i]);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int delta = 16; delta >= 1; delta >>= 1) {
     XYZZ<F> other = warp_shfl_down(acc, delta);
@@ -261,12 +360,22 @@ __global__ void __launch_bounds__(128) msm_sum_pieces_kernel(const XYZZ<F>* __re
   if (lane == 0) sh[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < 4; k++) xyzz_add(acc, sh[k]);
-    window_sums[blockIdx.x] = acc;
+    for (int k = 1; k < 8; k++) xyzz_add(acc, sh[k]);
+    *out = acc;
   }
 }
 
-// ------------------------------------------------------------------ driver
+// ------------------------------------------------------------------ drivers
+template <class F, class FrP>
+int msm_precompute_impl(cocg_ctx* ctx, BasesEntry& be) {
+  be.c = msm_window_bits(be.n);
+  be.nwin = msm_num_windows<FrP>(be.c);
+  if (be.n == 0) return 0;
+  msm_precompute_kernel<F><<<(unsigned)((be.n + 127) / 128), 128, 0, ctx->stream>>>(reinterpret_cast<Affine<F>*>(be.d), be.n, be.c, be.nwin);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 template <class F, class FrP>
 int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac) {
   using X = XYZZ<F>;
@@ -276,83 +385,84 @@ int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const vo
     for (int j = 0; j < k; j++) memcpy(out + (size_t)j * sizeof(inf), &inf, sizeof(inf));
     return 0;
   }
-  if (n >= ((size_t)1 << 31)) return fail(ctx, "cocg_msm: n must be < 2^31");
-  const int c = msm_window_bits(n);
-  const int nwin = (FrP::BITS + c) / c;  // ceil((BITS+1)/c): room for the final carry
-  if (nwin > kMaxWindows) return fail(ctx, "cocg_msm: too many windows");
+  if (be.n >= ((size_t)1 << kIdxBits)) return fail(ctx, "cocg_msm: at most 2^25 - 1 bases per query");
+  const int c = be.c, nwin = be.nwin;
   const uint32_t nb = 1u << (c - 1);
-  const size_t nbuckets = (size_t)nwin * nb;
-  const uint32_t segs = (nb + kSeg - 1) / kSeg;
-  const size_t total_segs = (size_t)nwin * segs;
-  const size_t scan_blocks = (nbuckets + kScanBlock - 1) / kScanBlock;
+  const uint32_t logL = (uint32_t)(c - 1) / 2, logH = (uint32_t)(c - 1) - logL;
+  const uint32_t nmarg = (1u << logH) + (1u << logL);
+  const size_t scan_blocks = ((size_t)nb + kScanBlock - 1) / kScanBlock;
 
-  uint32_t *dig, *sorted, *counts, *start, *bsums, *heavy;
-  X *buckets, *pieces, *wsums;
+  uint32_t *dig, *sorted, *counts, *start, *bsums, *heavy, *order, *shist;
+  X *buckets, *marg, *result;
   void* p;
   COCG_TRY(scratch_get(ctx, 1, (size_t)nwin * n * 4, &p)); dig = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 2, (size_t)nwin * n * 4, &p)); sorted = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 3, nbuckets * 4, &p)); counts = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 4, (nbuckets + 1) * 4, &p)); start = (uint32_t*)p;
+  COCG_TRY(scratch_get(ctx, 3, (size_t)nb * 4, &p)); counts = (uint32_t*)p;
+  COCG_TRY(scratch_get(ctx, 4, ((size_t)nb + 1) * 4, &p)); start = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 5, (scan_blocks + 2) * 4, &p)); bsums = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 6, (nbuckets + 1) * 4, &p)); heavy = (uint32_t*)p;  // [0] = count, [1..] = list
-  COCG_TRY(scratch_get(ctx, 7, nbuckets * sizeof(X), &p)); buckets = (X*)p;
-  COCG_TRY(scratch_get(ctx, 8, total_segs * sizeof(X), &p)); pieces = (X*)p;
-  COCG_TRY(scratch_get(ctx, 9, (size_t)k * nwin * sizeof(X), &p)); wsums = (X*)p;
-  const char* base_ptr = (const char*)be.d + off * be.point_bytes;
+  COCG_TRY(scratch_get(ctx, 6, ((size_t)nb + 1) * 4, &p)); heavy = (uint32_t*)p;  // [0] = count, [1..] = list
+  COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
+  COCG_TRY(scratch_get(ctx, 8, (size_t)nmarg * sizeof(X), &p)); marg = (X*)p;
+  COCG_TRY(scratch_get(ctx, 9, (size_t)k * sizeof(X), &p)); result = (X*)p;
+  COCG_TRY(scratch_get(ctx, 10, ((size_t)nb + kSizeBins) * 4, &p)); order = (uint32_t*)p; shist = order + nb;
+  const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
   cudaStream_t st = ctx->stream;
 
-  COCG_CUDA(ctx, cudaMemsetAsync(counts, 0, nbuckets * 4, st));
+  COCG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
   for (int j = 0; j < k; j++) {
     COCG_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
     {
-    ProfScope prof(ctx, COCG_PROF_MSM_SORT);
-    msm_digits_kernel<FrP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars[j], n, c, nwin, mont, dig, counts);
-    COCG_LAUNCH_CHECK(ctx);
-    scan_block_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, start, nbuckets, bsums);
-    COCG_LAUNCH_CHECK(ctx);
-    scan_top_kernel<<<1, kScanThreads, 0, st>>>(bsums, scan_blocks, bsums + scan_blocks);
-    COCG_LAUNCH_CHECK(ctx);
-    scan_add_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(start, nbuckets, bsums, bsums + scan_blocks);
-    COCG_LAUNCH_CHECK(ctx);
-    msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dig, n, nwin, nb, start, counts, sorted);
-    COCG_LAUNCH_CHECK(ctx);
+      ProfScope prof(ctx, COCG_PROF_MSM_SORT);
+      msm_digits_kernel<FrP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars[j], n, c, nwin, mont, dig, counts);
+      COCG_LAUNCH_CHECK(ctx);
+      scan_block_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, start, nb, bsums);
+      COCG_LAUNCH_CHECK(ctx);
+      scan_top_kernel<<<1, kScanThreads, 0, st>>>(bsums, scan_blocks, bsums + scan_blocks);
+      COCG_LAUNCH_CHECK(ctx);
+      scan_add_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(start, nb, bsums, bsums + scan_blocks);
+      COCG_LAUNCH_CHECK(ctx);
+      COCG_CUDA(ctx, cudaMemsetAsync(shist, 0, kSizeBins * 4, st));
+      bucket_size_hist_kernel<<<grid_for(nb, 256, 2), 256, 0, st>>>(counts, nb, shist);
+      COCG_LAUNCH_CHECK(ctx);
+      bucket_size_scan_kernel<<<1, 32, 0, st>>>(shist);
+      COCG_LAUNCH_CHECK(ctx);
+      bucket_order_kernel<<<(nb + 255) / 256, 256, 0, st>>>(counts, nb, shist, order);
+      COCG_LAUNCH_CHECK(ctx);
+      msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dig, n, nwin, start, counts, sorted);
+      COCG_LAUNCH_CHECK(ctx);
     }
     {
-    ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
-    msm_accumulate_kernel<F><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(base_ptr, sorted, start, nbuckets, buckets, heavy + 1, heavy);
-    COCG_LAUNCH_CHECK(ctx);
-    msm_heavy_kernel<F><<<kNumSMs, 128, 0, st>>>(base_ptr, sorted, start, buckets, heavy + 1, heavy);
-    COCG_LAUNCH_CHECK(ctx);
+      ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
+      msm_accumulate_kernel<F><<<(nb + 127) / 128, 128, 0, st>>>(table, be.n, sorted, start, order, nb, buckets, heavy + 1, heavy);
+      COCG_LAUNCH_CHECK(ctx);
+      msm_heavy_kernel<F><<<kNumSMs, 128, 0, st>>>(table, be.n, sorted, start, buckets, heavy + 1, heavy);
+      COCG_LAUNCH_CHECK(ctx);
     }
     ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
-    msm_reduce_segments_kernel<F><<<(unsigned)((total_segs + 127) / 128), 128, 0, st>>>(buckets, nb, segs, total_segs, pieces);
+    msm_marginals_kernel<F><<<(nmarg * 32 + 127) / 128, 128, 0, st>>>(buckets, logH, logL, marg);
     COCG_LAUNCH_CHECK(ctx);
-    msm_sum_pieces_kernel<F><<<nwin, 128, 0, st>>>(pieces, segs, wsums + (size_t)j * nwin);
+    msm_sum_kernel<F><<<1, 256, 0, st>>>(marg, nmarg, result + j);
     COCG_LAUNCH_CHECK(ctx);
   }
-  // 6. window sums -> host, Horner fold sum_w 2^(c*w) W_w
   void* hp;
-  COCG_TRY(pinned_get(ctx, (size_t)k * nwin * sizeof(X), &hp));
-  COCG_CUDA(ctx, cudaMemcpyAsync(hp, wsums, (size_t)k * nwin * sizeof(X), cudaMemcpyDeviceToHost, st));
+  COCG_TRY(pinned_get(ctx, (size_t)k * sizeof(X), &hp));
+  COCG_CUDA(ctx, cudaMemcpyAsync(hp, result, (size_t)k * sizeof(X), cudaMemcpyDeviceToHost, st));
   COCG_CUDA(ctx, cudaStreamSynchronize(st));
   const X* hw = reinterpret_cast<const X*>(hp);
   for (int j = 0; j < k; j++) {
-    X acc = hw[(size_t)j * nwin + nwin - 1];
-    for (int w = nwin - 2; w >= 0; w--) {
-      for (int q = 0; q < c; q++) acc = xyzz_dbl(acc);
-      xyzz_add(acc, hw[(size_t)j * nwin + w]);
-    }
-    Jacobian<F> jr = xyzz_to_jacobian(acc);
+    Jacobian<F> jr = xyzz_to_jacobian(hw[j]);
     memcpy(out + (size_t)j * sizeof(jr), &jr, sizeof(jr));
   }
   return 0;
 }
 
-
 // per-(curve, group) entry points, one translation unit each (msm_<curve>_<group>.cu)
-int msm_bn254_g1(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
-int msm_bn254_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
-int msm_bls381_g1(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
-int msm_bls381_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac);
+#define COCG_MSM_DECL(NAME)                                                                                                           \
+  int msm_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac); \
+  int msm_precompute_##NAME(cocg_ctx* ctx, BasesEntry& be);
+COCG_MSM_DECL(bn254_g1)
+COCG_MSM_DECL(bn254_g2)
+COCG_MSM_DECL(bls381_g1)
+COCG_MSM_DECL(bls381_g2)
 
 }  // namespace cocg
