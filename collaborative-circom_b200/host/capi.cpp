@@ -456,3 +456,13 @@ extern "C" int cohost_rep3_profile_reset(cohost_rep3_session* s) {
   for (int i = 0; i < 3; i++) cocg_profile_reset(s->drv[i]->ctx);
   return 0;
 }
+
+// The index-range partition of an n-term MSM over `world` ranks (MsmShard::range); no GPU needed.
+extern "C" int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len) {
+  if (!off || !len || world < 1 || rank < 0 || rank >= world) return fail("cohost_msm_shard_range: bad argument");
+  MsmShard sh;
+  sh.rank = rank;
+  sh.world = world;
+  sh.range(n, *off, *len);
+  return 0;
+}

@@ -21,7 +21,7 @@ HOST_SYMBOLS = [
     "cohost_plain_session_destroy", "cohost_plain_prove", "cohost_rep3_session_create", "cohost_rep3_session_destroy",
     "cohost_rep3_prove_begin", "cohost_rep3_partial_bytes", "cohost_rep3_prove_partials", "cohost_rep3_prove_combine",
     "cohost_rep3_prove_end", "cohost_rep3_launch_count", "cohost_rep3_prove_begin_device", "cohost_rep3_profile_enable",
-    "cohost_rep3_profile_read", "cohost_rep3_profile_reset",
+    "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -75,6 +75,7 @@ def load_host():
     L.cohost_rep3_prove_end.argtypes = [vp, vp, pvp, pvp]
     L.cohost_rep3_launch_count.argtypes = [vp]
     L.cohost_rep3_launch_count.restype = u64
+    L.cohost_msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     _host = L
     return L
 

@@ -87,6 +87,8 @@ COHOST_API int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gat
 /* proofs_out: 3 x (A | B | C); h_a / h_b: NULL or 3 HOST buffers of 2^pow Fr receiving each party's share of h. */
 COHOST_API int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, void* const* h_a, void* const* h_b);
 COHOST_API uint64_t cohost_rep3_launch_count(cohost_rep3_session* s);
+/* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
+COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 
 #ifdef __cplusplus
 }
