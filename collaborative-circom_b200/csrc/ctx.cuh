@@ -41,7 +41,7 @@ struct cocg_ctx {
   std::string err;
   uint64_t launches = 0;
   // scratch arenas (grow-only, reused across calls)
-  enum { kScratchSlots = 12 };
+  enum { kScratchSlots = 16 };
   void* scratch[kScratchSlots] = {};
   size_t scratch_bytes[kScratchSlots] = {};
   void* pinned = nullptr;
@@ -131,6 +131,18 @@ inline int pinned_get(cocg_ctx* ctx, size_t bytes, void** out) {
   }
   *out = ctx->pinned;
   return 0;
+}
+
+// Window width c of the MSM table built for a query of n points (msm_impl.cuh): about log2(n) - 3, so that buckets hold a few
+// hundred points each and the bucket reduction stays a few percent of the accumulation; 17 bits (15 windows) at n = 2^20.
+inline int msm_plan_window_bits(size_t n) {
+  int lg = 0;
+  size_t v = n + n / 2;  // round to the nearest power of two
+  while (((size_t)1 << (lg + 1)) <= v) lg++;
+  int c = lg - 3;
+  if (c < 4) c = 4;
+  if (c > 20) c = 20;
+  return c;
 }
 
 inline int grid_for(size_t work_items, int threads, int max_waves = 16) {

@@ -14,9 +14,7 @@ COCG_MSM_DECL(bls381_g2)
 
 // window bits / count for a query of n points: must match msm_impl.cuh (the table is allocated before it is built)
 int msm_table_windows(int curve, size_t n) {
-  int lg = 0;
-  while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg < 4 ? 4 : (lg > 20 ? 20 : lg);
+  int c = msm_plan_window_bits(n);
   int bits = curve == COCG_BN254 ? 254 : 255;
   return (bits + c) / c;
 }

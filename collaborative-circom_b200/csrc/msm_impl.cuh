@@ -30,18 +30,11 @@
 
 namespace cocg {
 
-constexpr int kHeavy = 512;          // runs longer than this go to the warp-per-bucket kernel
-constexpr int kMsmMaxC = 20;         // 2^19 buckets; table = 13 x the query for 254/255-bit scalars
+constexpr int kHeavy = 1024;         // runs longer than this are cut into kHeavy-entry chunks, one warp each
 constexpr int kIdxBits = 25;         // entry = sign << 31 | window << 25 | point index
+constexpr int kLanesPerBucket = 4;   // threads that share one bucket's run in the accumulate kernel
 
-static int msm_window_bits(size_t n) {
-  int lg = 0;
-  while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg;
-  if (c < 4) c = 4;
-  if (c > kMsmMaxC) c = kMsmMaxC;
-  return c;
-}
+static int msm_window_bits(size_t n) { return msm_plan_window_bits(n); }  // ctx.cuh: shared with the table allocation
 template <class FrP>
 static int msm_num_windows(int c) {
   return (FrP::BITS + c) / c;  // ceil((BITS+1)/c): room for the final carry of the signed recoding
@@ -272,40 +265,81 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const void* table, 
 }
 
 // ------------------------------------------------------------------ 4. bucket accumulation
+// kLanesPerBucket adjacent lanes share one bucket: they stride through its run and combine with shuffles, which keeps
+// >= 2^18 threads in flight at 2^16 buckets.  Buckets are taken in descending size order so a warp's groups finish together.
+struct HeavyRec {
+  uint32_t bucket, first_chunk, nchunks;
+};
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
                                                               const uint32_t* __restrict__ start, const uint32_t* __restrict__ order, uint32_t nbuckets,
-                                                              XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_list,
-                                                              uint32_t* __restrict__ heavy_count) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbuckets) return;
-  const uint32_t gb = order[t];
-  uint32_t beg = start[gb], end = start[gb + 1];
-  if (end - beg > (uint32_t)kHeavy) {
-    heavy_list[atomicAdd(heavy_count, 1u)] = gb;
-    return;
+                                                              XYZZ<F>* __restrict__ buckets, HeavyRec* __restrict__ heavy_list,
+                                                              uint32_t* __restrict__ chunk_owner,
+                                                              uint32_t* __restrict__ heavy_count /* [0] buckets, [1] chunks */) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t slot = t / kLanesPerBucket, sub = t % kLanesPerBucket;
+  const bool live = slot < nbuckets;
+  const uint32_t gb = live ? order[slot] : 0;
+  uint32_t beg = 0, end = 0;
+  if (live) { beg = start[gb]; end = start[gb + 1]; }
+  const bool heavy = end - beg > (uint32_t)kHeavy;
+  if (heavy) {
+    if (sub == 0) {
+      uint32_t nch = (end - beg + kHeavy - 1) / kHeavy;
+      uint32_t h = atomicAdd(&heavy_count[0], 1u);
+      uint32_t first = atomicAdd(&heavy_count[1], nch);
+      heavy_list[h] = HeavyRec{gb, first, nch};
+      for (uint32_t q = 0; q < nch; q++) chunk_owner[first + q] = h;
+    }
+    end = beg;  // nothing to do here; still take part in the shuffles below
   }
   XYZZ<F> acc = xyzz_inf<F>();
-  accumulate_run<F>(acc, table, tstride, sorted, beg, end, 1);
-  buckets[gb] = acc;
+  accumulate_run<F>(acc, table, tstride, sorted, beg + sub, end, kLanesPerBucket);
+#pragma unroll
+  for (int delta = kLanesPerBucket / 2; delta >= 1; delta >>= 1) {
+    XYZZ<F> other = warp_shfl_down(acc, delta);
+    if (sub < (uint32_t)delta) xyzz_add(acc, other);
+  }
+  if (live && !heavy && sub == 0) buckets[gb] = acc;
 }
-// one warp per heavy bucket: lanes stride through the run, then a shuffle tree combines the 32 partial sums
+// skewed scalars (plain-driver witnesses, or a top window narrower than c bits): a warp per kHeavy-entry chunk ...
 template <class F>
-__global__ void __launch_bounds__(128) msm_heavy_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
-                                                         const uint32_t* __restrict__ start, XYZZ<F>* __restrict__ buckets,
-                                                         const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count) {
+__global__ void __launch_bounds__(128) msm_heavy_chunks_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
+                                                                const uint32_t* __restrict__ start, const HeavyRec* __restrict__ heavy_list,
+                                                                const uint32_t* __restrict__ chunk_owner, const uint32_t* __restrict__ heavy_count,
+                                                                XYZZ<F>* __restrict__ partial) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t total = *heavy_count;
-  for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < total; h += nwarps) {
-    uint32_t gb = heavy_list[h];
+  const uint32_t nchunks = heavy_count[1];
+  for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < nchunks; ch += nwarps) {
+    const HeavyRec rec = heavy_list[chunk_owner[ch]];
+    uint32_t beg = start[rec.bucket] + (ch - rec.first_chunk) * kHeavy;
+    uint32_t end = min(beg + (uint32_t)kHeavy, start[rec.bucket + 1]);
     XYZZ<F> acc = xyzz_inf<F>();
-    accumulate_run<F>(acc, table, tstride, sorted, start[gb] + lane, start[gb + 1], 32);
+    accumulate_run<F>(acc, table, tstride, sorted, beg + lane, end, 32);
     for (int delta = 16; delta >= 1; delta >>= 1) {
       XYZZ<F> other = warp_shfl_down(acc, delta);
       if (lane < (uint32_t)delta) xyzz_add(acc, other);
     }
-    if (lane == 0) buckets[gb] = acc;
+    if (lane == 0) partial[ch] = acc;
+  }
+}
+// ... then a warp per heavy bucket folds its chunk sums
+template <class F>
+__global__ void __launch_bounds__(128) msm_heavy_fold_kernel(const HeavyRec* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
+                                                              const XYZZ<F>* __restrict__ partial, XYZZ<F>* __restrict__ buckets) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nheavy = heavy_count[0];
+  for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nheavy; h += nwarps) {
+    const HeavyRec rec = heavy_list[h];
+    XYZZ<F> acc = xyzz_inf<F>();
+    for (uint32_t q = lane; q < rec.nchunks; q += 32) xyzz_add(acc, partial[rec.first_chunk + q]);
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+      XYZZ<F> other = warp_shfl_down(acc, delta);
+      if (lane < (uint32_t)delta) xyzz_add(acc, other);
+    }
+    if (lane == 0) buckets[rec.bucket] = acc;
   }
 }
 
@@ -393,14 +427,18 @@ int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const vo
   const size_t scan_blocks = ((size_t)nb + kScanBlock - 1) / kScanBlock;
 
   uint32_t *dig, *sorted, *counts, *start, *bsums, *heavy, *order, *shist;
-  X *buckets, *marg, *result;
+  X *buckets, *marg, *result, *hpartial;
+  const size_t max_heavy = (size_t)nwin * n / kHeavy + 1;  // buckets with more than kHeavy entries; chunks <= 2 x that
   void* p;
   COCG_TRY(scratch_get(ctx, 1, (size_t)nwin * n * 4, &p)); dig = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 2, (size_t)nwin * n * 4, &p)); sorted = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 3, (size_t)nb * 4, &p)); counts = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 4, ((size_t)nb + 1) * 4, &p)); start = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 5, (scan_blocks + 2) * 4, &p)); bsums = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 6, ((size_t)nb + 1) * 4, &p)); heavy = (uint32_t*)p;  // [0] = count, [1..] = list
+  COCG_TRY(scratch_get(ctx, 6, 16 + max_heavy * sizeof(HeavyRec), &p)); heavy = (uint32_t*)p;  // [0], [1] = counters, records from +16 B
+  HeavyRec* heavy_list = reinterpret_cast<HeavyRec*>(heavy + 4);
+  COCG_TRY(scratch_get(ctx, 12, 2 * max_heavy * sizeof(X), &p)); hpartial = (X*)p;
+  COCG_TRY(scratch_get(ctx, 13, 2 * max_heavy * 4, &p)); uint32_t* chunk_owner = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
   COCG_TRY(scratch_get(ctx, 8, (size_t)nmarg * sizeof(X), &p)); marg = (X*)p;
   COCG_TRY(scratch_get(ctx, 9, (size_t)k * sizeof(X), &p)); result = (X*)p;
@@ -410,7 +448,7 @@ int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const vo
 
   COCG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
   for (int j = 0; j < k; j++) {
-    COCG_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
+    COCG_CUDA(ctx, cudaMemsetAsync(heavy, 0, 16, st));
     {
       ProfScope prof(ctx, COCG_PROF_MSM_SORT);
       msm_digits_kernel<FrP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars[j], n, c, nwin, mont, dig, counts);
@@ -433,9 +471,11 @@ int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const vo
     }
     {
       ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
-      msm_accumulate_kernel<F><<<(nb + 127) / 128, 128, 0, st>>>(table, be.n, sorted, start, order, nb, buckets, heavy + 1, heavy);
+      msm_accumulate_kernel<F><<<(nb * kLanesPerBucket + 127) / 128, 128, 0, st>>>(table, be.n, sorted, start, order, nb, buckets, heavy_list, chunk_owner, heavy);
       COCG_LAUNCH_CHECK(ctx);
-      msm_heavy_kernel<F><<<kNumSMs, 128, 0, st>>>(table, be.n, sorted, start, buckets, heavy + 1, heavy);
+      msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, sorted, start, heavy_list, chunk_owner, heavy, hpartial);
+      COCG_LAUNCH_CHECK(ctx);
+      msm_heavy_fold_kernel<F><<<kNumSMs, 128, 0, st>>>(heavy_list, heavy, hpartial, buckets);
       COCG_LAUNCH_CHECK(ctx);
     }
     ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);

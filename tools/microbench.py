@@ -1,17 +1,17 @@
 #!/usr/bin/env python3
-"""Per-kernel timings on one B200 (CUDA events on the context's stream).  Development aid; bench.py is the contract."""
+"""Per-kernel-class timings on one B200, one context, one stream (cocg_profile_*: CUDA events on the launching stream).
+Development aid; bench.py is the contract."""
 import json
 import os
 import sys
 import time
 
 import numpy as np
-import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cocg  # noqa: E402
-from oracle import cref, ntt as ontt  # noqa: E402
-from oracle.curves import BN254  # noqa: E402
+
+R1 = pow(2, 256, 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001)
 
 
 def rand_fr(n, seed):
@@ -20,63 +20,51 @@ def rand_fr(n, seed):
     return a
 
 
-def timeit(fn, iters=5, warm=2):
+def prof(ctx, fn, iters=5, warm=2):
     for _ in range(warm):
         fn()
-    torch.cuda.synchronize()
-    ts = []
+    ctx.profile(True)
+    ctx.profile_reset()
+    t0 = time.perf_counter()
     for _ in range(iters):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
         fn()
-        e.record()
-        torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e))
-    return float(np.median(ts)), float(min(ts))
+    ctx.sync()
+    wall = (time.perf_counter() - t0) / iters * 1e3
+    out = {k: round(v[0] / iters, 4) for k, v in ctx.profile_read().items() if v[1]}
+    ctx.profile(False)
+    out["wall_ms"] = round(wall, 4)
+    return out
 
 
 def main():
     res = {}
-    torch.cuda.init()
     ctx = cocg.Context(cocg.BN254, 0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    c = BN254
-    # ---- element-wise, 2^24 elements = 512 MiB per vector (>> L2)
-    n = 1 << 24
-    a, b = ctx.upload(rand_fr(n, 1)), ctx.upload(rand_fr(n, 2))
-    o = ctx.zeros(n)
-    for name, op, nbytes in (("add", cocg.OP_ADD, 96), ("sub", cocg.OP_SUB, 96), ("mul", cocg.OP_MUL, 96), ("neg", cocg.OP_NEG, 64)):
-        med, mn = timeit(lambda: ctx.vec_op(op, a, b, out=o))
-        res["vec_" + name] = {"ms": med, "GBps": n * nbytes / med / 1e6, "Gelem_s": n / med / 1e6}
-    med, mn = timeit(lambda: ctx.rep3_mul_local(a, b, b, a, None, out=o))
-    res["rep3_mul_local"] = {"ms": med, "GBps": n * 160 / med / 1e6, "Gmul_s": 2 * n / med / 1e6}
-    for v in (a, b, o):
-        v.free()
-    # ---- NTT 2^20, 2 components (and 2^22, 2^24 single)
-    for logn, k in ((20, 2), (20, 1), (22, 1), (24, 1)):
+    sizes = [int(x) for x in sys.argv[1:]] or [20]
+    for logn in sizes:
         n = 1 << logn
-        omega, g = ontt.groth16_roots(c, logn)
-        om = cref.fr_to_mont(c, [omega])
-        vs = [ctx.upload(rand_fr(n, 3 + i)) for i in range(k)]
-        med, mn = timeit(lambda: ctx.ntt(vs, logn, om))
-        res[f"ntt_2^{logn}_k{k}"] = {"ms": med, "GBps_algorithmic": k * n * 64 / med / 1e6}
-        for v in vs:
-            v.free()
-    # ---- MSM G1 / G2
-    for group, logn in ((1, 16), (1, 18), (1, 20), (2, 18), (2, 20)):
-        n = 1 << logn
-        p0 = cref.g_to_mont(c, [c.mul(c.gen(group), 12345, group)], group)
-        q = cref.g_to_mont(c, [c.mul(c.gen(group), 6789, group)], group)
-        t0 = time.time()
-        pts = cref.gen_chain(c, group, p0[0], q[0], n)
-        tgen = time.time() - t0
-        h = ctx.bases_upload(group, pts)
-        sc = ctx.upload(rand_fr(n, 9))
-        pb = 64 * group + 32
-        med, mn = timeit(lambda: ctx.msm(h, [sc]), iters=5, warm=2)
-        res[f"msm_g{group}_2^{logn}"] = {"ms": med, "min_ms": mn, "GBps_algorithmic": n * pb / med / 1e6, "gen_s": tgen}
-        ctx.bases_free(h)
-        sc.free()
+        for group in (1, 2):
+            h = ctx.bases_generate(group, n, bytes([group] * 32))
+            sc = [ctx.upload(rand_fr(n, 9)), ctx.upload(rand_fr(n, 10))]
+            r = prof(ctx, lambda: ctx.msm(h, sc[:1]))
+            r["alg_GBps"] = round(n * (64 * group + 32) / r["wall_ms"] / 1e6, 2)
+            res[f"msm_g{group}_2^{logn}_k1"] = r
+            res[f"msm_g{group}_2^{logn}_k2"] = prof(ctx, lambda: ctx.msm(h, sc))
+            ctx.bases_free(h)
+            for v in sc:
+                v.free()
+        # NTT: root of unity is irrelevant for timing; use any element
+        vs = [ctx.upload(rand_fr(n, 3 + i)) for i in range(2)]
+        om = np.array([[R1 & (2**64 - 1), (R1 >> 64) & (2**64 - 1), (R1 >> 128) & (2**64 - 1), R1 >> 192]], dtype=np.uint64)
+        r = prof(ctx, lambda: ctx.ntt(vs, logn, om))
+        r["alg_GBps"] = round(2 * n * 64 / r["ntt"] / 1e6, 1)
+        res[f"ntt_2^{logn}_k2"] = r
+        o = ctx.zeros(n)
+        r = prof(ctx, lambda: ctx.vec_op(cocg.OP_SUB, vs[0], vs[1], out=o))
+        r["alg_GBps"] = round(n * 96 / r["vec"] / 1e6, 1)
+        res[f"vec_sub_2^{logn}"] = r
+        r = prof(ctx, lambda: ctx.rep3_mul_local(vs[0], vs[1], vs[1], vs[0], None, out=o))
+        r["alg_GBps"] = round(n * 160 / r["vec"] / 1e6, 1)
+        res[f"rep3_mul_local_2^{logn}"] = r
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
