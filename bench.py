@@ -234,13 +234,8 @@ def run_own(args):
     pub = np.stack([limbs_of(r1), limbs_of(12345 * r1 % BN254_R)])
     setup_s = time.perf_counter() - t_setup
 
-    gather_in = torch.empty(sess.partial_bytes() // 8, dtype=torch.int64, device="cuda") if world > 1 else None
-    gather_out = torch.empty(world * sess.partial_bytes() // 8, dtype=torch.int64, device="cuda") if world > 1 else None
-
-    def all_gather(partials):
-        gather_in.copy_(torch.from_numpy(partials.view(np.int64)))
-        dist.all_gather_into_tensor(gather_out, gather_in)
-        return gather_out.cpu().numpy().view(np.uint64)
+    from importlib import import_module
+    all_gather = import_module("collaborative-circom_b200.distributed").make_all_gather(world, torch.device("cuda", local))
 
     def step(device_resident):
         if device_resident:
