@@ -242,3 +242,48 @@ def vk_from_json(text: str) -> VerifyingKey:
 
 def vk_from_zkey(zk: Groth16ZKey) -> VerifyingKey:
     return VerifyingKey(zk.curve, zk.alpha_g1, zk.beta_g2, zk.gamma_g2, zk.delta_g2, zk.ic)
+
+
+# ----------------------------------------------------------------------------
+# Plonk zkey (circom-types/src/plonk/zkey.rs:47-90, 160-330): only what round 1 needs
+# ----------------------------------------------------------------------------
+class PlonkZKey:
+    def __init__(self):
+        self.curve = None
+        self.n_vars = self.n_public = self.domain_size = self.n_additions = self.n_constraints = self.pow = 0
+        self.additions = []       # (signal_id1, signal_id2, factor1, factor2), factors canonical
+        self.map_a = self.map_b = self.map_c = None
+        self.p_tau = None         # domain_size + 6 G1 points (zkey.rs:222-225)
+
+
+def parse_plonk_zkey(data: bytes) -> PlonkZKey:
+    _, sec = read_binfile(data, b"zkey")
+    if _u32(sec[1], 0) != 2:
+        raise ValueError("not a plonk zkey")
+    rd = _Rd(sec[2])                                   # PlonkHeader::read, zkey.rs:375-420
+    n8q = rd.u32()
+    c = curve_from_q(rd.int_le(n8q))
+    n8r = rd.u32()
+    if rd.int_le(n8r) != c.r:
+        raise ValueError("invalid prime in header")
+    zk = PlonkZKey()
+    zk.curve = c
+    zk.n_vars, zk.n_public, zk.domain_size, zk.n_additions, zk.n_constraints = (rd.u32() for _ in range(5))
+    if zk.domain_size == 0 or zk.domain_size & (zk.domain_size - 1):
+        raise ValueError("domain size must be a power of two")
+    zk.pow = zk.domain_size.bit_length() - 1
+    rri = _mont_inv(c.Rr, c.r)
+    rd = _Rd(sec[3])                                   # additions_indices, zkey.rs:159-177: factors are Montgomery limbs
+    for _ in range(zk.n_additions):
+        s1, s2 = rd.u32(), rd.u32()
+        f1, f2 = rd.int_le(n8r), rd.int_le(n8r)
+        zk.additions.append((s1, s2, (f1 * rri) % c.r, (f2 * rri) % c.r))
+    maps = []
+    for sid in (4, 5, 6):                              # id_map, zkey.rs:179-185
+        rd = _Rd(sec[sid])
+        maps.append([rd.u32() for _ in range(zk.n_constraints)])
+    zk.map_a, zk.map_b, zk.map_c = maps
+    rqi = _mont_inv(c.Rq, c.q)
+    rd = _Rd(sec[14])                                  # taus
+    zk.p_tau = [read_g1(rd, c, rqi) for _ in range(zk.domain_size + 6)]
+    return zk

@@ -312,3 +312,34 @@ def test_ec_ops_match_oracle(cocg, bn, bls, curve, group):
     assert np.array_equal(ctx.ec_op(group, cocg.EC_TO_AFFINE, s), cref.ec_op(curve, group, 2, cref.ec_op(curve, group, 1, jp, k)))
     inf = ctx.ec_op(group, cocg.EC_ADD, jp, ctx.ec_op(group, cocg.EC_NEG, jp))
     assert cref.jac_from_mont(curve, inf, group) is None
+
+
+# ------------------------------------------------------------------------------------------------ reference KAT on the GPU
+@pytest.mark.parametrize("curve,circ", [("bn254", "multiplier2"), ("bls12_381", "poseidon")])
+def test_plonk_round1_kat_on_gpu(cocg, bn, bls, curve, circ):
+    """co-plonk/src/round1.rs:344-427 (bit-exact commitments with blinders b_i = i): wire buffers -> cocg_ntt (inverse, snarkjs
+    root) -> blinding -> cocg_msm over p_tau must give the reference's literal points."""
+    from oracle import formats, plonk
+    d = os.path.join(G, "plonk", curve, circ)
+    zk = formats.parse_plonk_zkey(open(os.path.join(d, "circuit.round1.zkey"), "rb").read())
+    _, wt = formats.parse_wtns(open(os.path.join(d, "witness.wtns"), "rb").read())
+    kat = json.load(open(os.path.join(G, "plonk_round1_kats.json")))[curve + "/" + circ]
+    c = zk.curve
+    ctx = ctx_for(c, bn, bls)
+    n = zk.domain_size
+    get = plonk.witness_with_additions(zk, wt)
+    _, roots = ontt.roots_of_unity(c)
+    om = cref.fr_to_mont(c, [roots[zk.pow]])
+    h = ctx.bases_upload(1, cref.g_to_mont(c, zk.p_tau[:n + 2], 1))
+    for k, (m, name) in enumerate(((zk.map_a, "commit_a"), (zk.map_b, "commit_b"), (zk.map_c, "commit_c"))):
+        buf = cref.fr_to_mont(c, [get(i) for i in m] + [0] * (n - zk.n_constraints))
+        dv = ctx.upload(buf)
+        ctx.ntt([dv], zk.pow, om, inverse=True)
+        coeffs = cref.fr_from_mont(c, dv.to_host())
+        b_lo, b_hi = 2 * k, 2 * k + 1                       # Round1Challenges::deterministic, blind_coefficients
+        coeffs[0] = (coeffs[0] - b_hi) % c.r
+        coeffs[1] = (coeffs[1] - b_lo) % c.r
+        poly = cref.fr_to_mont(c, coeffs + [b_hi, b_lo])
+        out = ctx.msm(h, [ctx.upload(poly)], n=n + 2)
+        assert cref.jac_from_mont(c, out[0], 1) == (int(kat[name][0]), int(kat[name][1])), name
+    ctx.bases_free(h)

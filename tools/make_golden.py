@@ -74,9 +74,42 @@ def rep3_mul_kat():
     return {"x": nums[0:4], "y": nums[4:8], "xy": nums[8:12]}
 
 
+def plonk_round1():
+    """co-plonk/src/round1.rs:344-427: fixtures + the literal commitments.  The 6.4 MB poseidon zkey is trimmed to the sections
+    round 1 reads (header, additions, wire maps, p_tau) -- still a valid binfile."""
+    import struct
+    text = open(os.path.join(REF, "co-circom/co-plonk/src/round1.rs")).read()
+    out = {}
+    for fn, curve, circ in (("test_round1_multiplier2", "bn254", "multiplier2"), ("test_round1_poseidon_bls12_381", "bls12_381", "poseidon")):
+        i = text.index("fn %s()" % fn)
+        j = text.index("\n    }\n", i)
+        pts = re.findall(r'from_xy!\(\s*"(\d+)",\s*"(\d+)"\s*\)', text[i:j])
+        assert len(pts) == 3
+        out[curve + "/" + circ] = {"commit_a": pts[0], "commit_b": pts[1], "commit_c": pts[2]}
+        src = os.path.join(REF, "test_vectors", "Plonk", curve, circ)
+        dst = os.path.join(OUT, "plonk", curve, circ)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copyfile(os.path.join(src, "witness.wtns"), os.path.join(dst, "witness.wtns"))
+        data = open(os.path.join(src, "circuit.zkey"), "rb").read()
+        nsec = struct.unpack_from("<I", data, 8)[0]
+        off, keep = 12, []
+        for _ in range(nsec):
+            sid, slen = struct.unpack_from("<IQ", data, off)
+            if sid in (1, 2, 3, 4, 5, 6, 14):
+                keep.append(data[off:off + 12 + slen])
+            off += 12 + slen
+        with open(os.path.join(dst, "circuit.round1.zkey"), "wb") as f:
+            f.write(data[:8] + struct.pack("<I", len(keep)) + b"".join(keep))
+        for f in ("witness.wtns", "circuit.round1.zkey"):
+            os.chmod(os.path.join(dst, f), 0o644)
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     copy_fixtures()
+    with open(os.path.join(OUT, "plonk_round1_kats.json"), "w") as f:
+        json.dump(plonk_round1(), f, indent=1)
     with open(os.path.join(OUT, "zkey_kats.json"), "w") as f:
         json.dump(zkey_kats(), f, indent=1)
     with open(os.path.join(OUT, "rep3_mul_vec_bn.json"), "w") as f:
