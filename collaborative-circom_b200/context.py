@@ -169,6 +169,20 @@ class Context:
         self._ck(self.L.cocg_msm(self.h, bases, off, n, arr, len(scalars), 1 if mont else 0, out.ctypes.data))
         return out
 
+    def msm_multi(self, bases, offs, scalars, n: int | None = None, mont: bool = True):
+        """Several queries times the same scalars (one shared digit sort): list of (k, 3*group*LQ) Jacobian arrays."""
+        scalars = list(scalars)
+        if n is None:
+            n = scalars[0].n
+        nq, k = len(bases), len(scalars)
+        outs = [np.zeros((k, 3 * self._groups[b] * self.lq), dtype=np.uint64) for b in bases]
+        B = (ctypes.c_uint64 * nq)(*bases)
+        O = (ctypes.c_size_t * nq)(*offs)
+        S = (ctypes.c_void_p * k)(*[s.ptr for s in scalars])
+        P = (ctypes.c_void_p * nq)(*[o.ctypes.data for o in outs])
+        self._ck(self.L.cocg_msm_multi(self.h, B, O, nq, n, S, k, 1 if mont else 0, P))
+        return outs
+
     def msm_host(self, bases: int, scalars, off: int = 0, n: int | None = None, mont: bool = True) -> np.ndarray:
         """Same with host numpy scalar arrays (the drop-in call of a host-resident caller)."""
         scalars = [np.ascontiguousarray(s, dtype=np.uint64) for s in scalars]

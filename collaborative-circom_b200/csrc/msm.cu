@@ -1,17 +1,11 @@
 // C-ABI entry points of the MSM path (bases residency + dispatch); the pipeline itself is msm_impl.cuh.
 #include <string.h>
 
-#include "ctx.cuh"
+#include <vector>
+
+#include "msm_impl.cuh"
 
 namespace cocg {
-#define COCG_MSM_DECL(NAME)                                                                                                           \
-  int msm_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac); \
-  int msm_precompute_##NAME(cocg_ctx* ctx, BasesEntry& be);
-COCG_MSM_DECL(bn254_g1)
-COCG_MSM_DECL(bn254_g2)
-COCG_MSM_DECL(bls381_g1)
-COCG_MSM_DECL(bls381_g2)
-
 // window bits / count for a query of n points: must match msm_impl.cuh (the table is allocated before it is built)
 int msm_table_windows(int curve, size_t n) {
   int c = msm_plan_window_bits(n);
@@ -92,23 +86,91 @@ extern "C" int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_h
   return 0;
 }
 
+namespace {
+struct MsmOps {
+  int (*accumulate)(cocg_ctx*, const BasesEntry&, size_t, const MsmSorted&, void*);
+  void (*finish)(const void*, void*);
+  size_t xyzz_bytes, jac_bytes;
+};
+MsmOps msm_ops(int curve, int group) {
+  const size_t cb = curve == COCG_BN254 ? 32 : 48;
+  MsmOps o;
+  if (curve == COCG_BN254) {
+    o.accumulate = group == COCG_G1 ? msm_accumulate_bn254_g1 : msm_accumulate_bn254_g2;
+    o.finish = group == COCG_G1 ? msm_finish_bn254_g1 : msm_finish_bn254_g2;
+  } else {
+    o.accumulate = group == COCG_G1 ? msm_accumulate_bls381_g1 : msm_accumulate_bls381_g2;
+    o.finish = group == COCG_G1 ? msm_finish_bls381_g1 : msm_finish_bls381_g2;
+  }
+  o.xyzz_bytes = 4 * cb * group;
+  o.jac_bytes = 3 * cb * group;
+  return o;
+}
+constexpr size_t kResultSlot = 512;  // bytes reserved per XYZZ result (G2 over BLS12-381 needs 384)
+}  // namespace
+
+extern "C" int cocg_msm_multi(cocg_ctx* ctx, const uint64_t* bases, const size_t* offs, int nq, size_t n, const void* const* scalars, int k,
+                              int scalars_mont, void* const* out_jacobian) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (nq <= 0 || k <= 0) return 0;
+  if (nq > 16 || k > 8) return fail(ctx, "cocg_msm_multi: at most 16 queries and 8 components");
+  if (!bases || !offs || !scalars || !out_jacobian) return fail(ctx, "cocg_msm_multi: null argument");
+  const BasesEntry* be[16];
+  for (int q = 0; q < nq; q++) {
+    if (bases[q] == 0 || bases[q] > ctx->bases.size() || !ctx->bases[bases[q] - 1].d) return fail(ctx, "cocg_msm: bad bases handle");
+    be[q] = &ctx->bases[bases[q] - 1];
+    if (offs[q] > be[q]->n || n > be[q]->n - offs[q]) return fail(ctx, "cocg_msm: range exceeds the uploaded bases");
+    if (!out_jacobian[q]) return fail(ctx, "cocg_msm: null output");
+    if (be[q]->n >= ((size_t)1 << kIdxBits)) return fail(ctx, "cocg_msm: at most 2^25 - 1 bases per query");
+  }
+  for (int j = 0; j < k; j++)
+    if (n && !scalars[j]) return fail(ctx, "cocg_msm: null scalar vector");
+  if (n == 0) {  // empty sum: arkworks' zero()
+    for (int q = 0; q < nq; q++) {
+      MsmOps o = msm_ops(ctx->curve, be[q]->group);
+      std::vector<uint8_t> inf(o.xyzz_bytes, 0);
+      for (int j = 0; j < k; j++) o.finish(inf.data(), (char*)out_jacobian[q] + (size_t)j * o.jac_bytes);
+    }
+    return 0;
+  }
+  void* d_res;
+  COCG_TRY(scratch_get(ctx, 9, (size_t)nq * k * kResultSlot, &d_res));
+  // queries are grouped by window width so that each group shares one digit sort per component
+  bool done[16] = {};
+  for (int q0 = 0; q0 < nq; q0++) {
+    if (done[q0]) continue;
+    const int c = be[q0]->c;
+    for (int j = 0; j < k; j++) {
+      MsmSorted S;
+      if (ctx->curve == COCG_BN254) COCG_TRY(msm_sort_impl<Bn254FrP>(ctx, scalars[j], n, c, scalars_mont, S));
+      else COCG_TRY(msm_sort_impl<Bls381FrP>(ctx, scalars[j], n, c, scalars_mont, S));
+      for (int q = q0; q < nq; q++) {
+        if (be[q]->c != c) continue;
+        COCG_TRY(msm_ops(ctx->curve, be[q]->group).accumulate(ctx, *be[q], offs[q], S, (char*)d_res + ((size_t)q * k + j) * kResultSlot));
+      }
+    }
+    for (int q = q0; q < nq; q++)
+      if (be[q]->c == c) done[q] = true;
+  }
+  void* hp;
+  COCG_TRY(pinned_get(ctx, (size_t)nq * k * kResultSlot, &hp));
+  COCG_CUDA(ctx, cudaMemcpyAsync(hp, d_res, (size_t)nq * k * kResultSlot, cudaMemcpyDeviceToHost, ctx->stream));
+  COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int q = 0; q < nq; q++) {
+    MsmOps o = msm_ops(ctx->curve, be[q]->group);
+    for (int j = 0; j < k; j++) o.finish((const char*)hp + ((size_t)q * k + j) * kResultSlot, (char*)out_jacobian[q] + (size_t)j * o.jac_bytes);
+  }
+  return 0;
+}
+
 extern "C" int cocg_msm(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, const void* const* scalars, int k, int scalars_mont,
                         void* out_jacobian) {
   if (!ctx) return 1;
-  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (bases == 0 || bases > ctx->bases.size() || !ctx->bases[bases - 1].d) return fail(ctx, "cocg_msm: bad bases handle");
   if (k <= 0) return 0;
-  if (!scalars || !out_jacobian) return fail(ctx, "cocg_msm: null argument");
-  const BasesEntry& be = ctx->bases[bases - 1];
-  if (off > be.n || n > be.n - off) return fail(ctx, "cocg_msm: range exceeds the uploaded bases");
-  for (int j = 0; j < k; j++)
-    if (n && !scalars[j]) return fail(ctx, "cocg_msm: null scalar vector");
-  if (ctx->curve == COCG_BN254) {
-    if (be.group == COCG_G1) return msm_bn254_g1(ctx, be, off, n, scalars, k, scalars_mont, out_jacobian);
-    return msm_bn254_g2(ctx, be, off, n, scalars, k, scalars_mont, out_jacobian);
-  }
-  if (be.group == COCG_G1) return msm_bls381_g1(ctx, be, off, n, scalars, k, scalars_mont, out_jacobian);
-  return msm_bls381_g2(ctx, be, off, n, scalars, k, scalars_mont, out_jacobian);
+  if (!out_jacobian) return fail(ctx, "cocg_msm: null argument");
+  void* outs[1] = {out_jacobian};
+  return cocg_msm_multi(ctx, &bases, &off, 1, n, scalars, k, scalars_mont, outs);
 }
 
 extern "C" int cocg_msm_host(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, const void* const* scalars, int k, int scalars_mont,

@@ -1,8 +1,9 @@
 // One (curve, group) instantiation of the MSM pipeline per translation unit, so that they compile in parallel.
 #include "msm_impl.cuh"
 namespace cocg {
-int msm_bls381_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac) {
-  return msm_impl<Bls381Fq2, Bls381FrP>(ctx, be, off, n, scalars, k, mont, out_jac);
+int msm_accumulate_bls381_g2(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, void* d_result) {
+  return msm_accumulate_impl<Bls381Fq2>(ctx, be, off, S, d_result);
 }
+void msm_finish_bls381_g2(const void* h_xyzz, void* out_jac) { msm_finish_impl<Bls381Fq2>(h_xyzz, out_jac); }
 int msm_precompute_bls381_g2(cocg_ctx* ctx, BasesEntry& be) { return msm_precompute_impl<Bls381Fq2, Bls381FrP>(ctx, be); }
 }  // namespace cocg

@@ -410,95 +410,105 @@ int msm_precompute_impl(cocg_ctx* ctx, BasesEntry& be) {
   return 0;
 }
 
-template <class F, class FrP>
-int msm_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac) {
-  using X = XYZZ<F>;
-  char* out = reinterpret_cast<char*>(out_jac);  // caller memory: no alignment assumed
-  if (n == 0) {
-    Jacobian<F> inf = jac_inf<F>();
-    for (int j = 0; j < k; j++) memcpy(out + (size_t)j * sizeof(inf), &inf, sizeof(inf));
-    return 0;
-  }
-  if (be.n >= ((size_t)1 << kIdxBits)) return fail(ctx, "cocg_msm: at most 2^25 - 1 bases per query");
-  const int c = be.c, nwin = be.nwin;
-  const uint32_t nb = 1u << (c - 1);
-  const uint32_t logL = (uint32_t)(c - 1) / 2, logH = (uint32_t)(c - 1) - logL;
-  const uint32_t nmarg = (1u << logH) + (1u << logL);
-  const size_t scan_blocks = ((size_t)nb + kScanBlock - 1) / kScanBlock;
+// State left in the context's scratch by the digit sort of one scalar vector; consumed by any number of accumulate +
+// reduce passes over tables built with the same window width (the four Groth16 queries that take aux_assignment,
+// /root/reference/co-circom/co-groth16/src/groth16.rs:221-225, 251-255, share it).
+struct MsmSorted {
+  size_t n = 0;
+  int c = 0, nwin = 0;
+  uint32_t nb = 0;
+  uint32_t *sorted = nullptr, *start = nullptr, *order = nullptr, *heavy = nullptr, *chunk_owner = nullptr;
+  HeavyRec* heavy_list = nullptr;
+  size_t max_heavy = 0;
+};
 
-  uint32_t *dig, *sorted, *counts, *start, *bsums, *heavy, *order, *shist;
-  X *buckets, *marg, *result, *hpartial;
-  const size_t max_heavy = (size_t)nwin * n / kHeavy + 1;  // buckets with more than kHeavy entries; chunks <= 2 x that
+template <class FrP>
+int msm_sort_impl(cocg_ctx* ctx, const void* scalars, size_t n, int c, int mont, MsmSorted& S) {
+  const int nwin = msm_num_windows<FrP>(c);
+  const uint32_t nb = 1u << (c - 1);
+  const size_t scan_blocks = ((size_t)nb + kScanBlock - 1) / kScanBlock;
+  uint32_t *dig, *counts, *bsums, *shist;
+  S.n = n; S.c = c; S.nwin = nwin; S.nb = nb;
+  S.max_heavy = (size_t)nwin * n / kHeavy + 1;  // buckets with more than kHeavy entries; chunks <= 2 x that
   void* p;
   COCG_TRY(scratch_get(ctx, 1, (size_t)nwin * n * 4, &p)); dig = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 2, (size_t)nwin * n * 4, &p)); sorted = (uint32_t*)p;
+  COCG_TRY(scratch_get(ctx, 2, (size_t)nwin * n * 4, &p)); S.sorted = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 3, (size_t)nb * 4, &p)); counts = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 4, ((size_t)nb + 1) * 4, &p)); start = (uint32_t*)p;
+  COCG_TRY(scratch_get(ctx, 4, ((size_t)nb + 1) * 4, &p)); S.start = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 5, (scan_blocks + 2) * 4, &p)); bsums = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 6, 16 + max_heavy * sizeof(HeavyRec), &p)); heavy = (uint32_t*)p;  // [0], [1] = counters, records from +16 B
-  HeavyRec* heavy_list = reinterpret_cast<HeavyRec*>(heavy + 4);
-  COCG_TRY(scratch_get(ctx, 12, 2 * max_heavy * sizeof(X), &p)); hpartial = (X*)p;
-  COCG_TRY(scratch_get(ctx, 13, 2 * max_heavy * 4, &p)); uint32_t* chunk_owner = (uint32_t*)p;
-  COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
-  COCG_TRY(scratch_get(ctx, 8, (size_t)nmarg * sizeof(X), &p)); marg = (X*)p;
-  COCG_TRY(scratch_get(ctx, 9, (size_t)k * sizeof(X), &p)); result = (X*)p;
-  COCG_TRY(scratch_get(ctx, 10, ((size_t)nb + kSizeBins) * 4, &p)); order = (uint32_t*)p; shist = order + nb;
-  const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
+  COCG_TRY(scratch_get(ctx, 6, 16 + S.max_heavy * sizeof(HeavyRec), &p)); S.heavy = (uint32_t*)p;  // [0], [1] = counters, records from +16 B
+  S.heavy_list = reinterpret_cast<HeavyRec*>(S.heavy + 4);
+  COCG_TRY(scratch_get(ctx, 13, 2 * S.max_heavy * 4, &p)); S.chunk_owner = (uint32_t*)p;
+  COCG_TRY(scratch_get(ctx, 10, ((size_t)nb + kSizeBins) * 4, &p)); S.order = (uint32_t*)p; shist = S.order + nb;
   cudaStream_t st = ctx->stream;
-
+  ProfScope prof(ctx, COCG_PROF_MSM_SORT);
   COCG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
-  for (int j = 0; j < k; j++) {
-    COCG_CUDA(ctx, cudaMemsetAsync(heavy, 0, 16, st));
-    {
-      ProfScope prof(ctx, COCG_PROF_MSM_SORT);
-      msm_digits_kernel<FrP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars[j], n, c, nwin, mont, dig, counts);
-      COCG_LAUNCH_CHECK(ctx);
-      scan_block_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, start, nb, bsums);
-      COCG_LAUNCH_CHECK(ctx);
-      scan_top_kernel<<<1, kScanThreads, 0, st>>>(bsums, scan_blocks, bsums + scan_blocks);
-      COCG_LAUNCH_CHECK(ctx);
-      scan_add_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(start, nb, bsums, bsums + scan_blocks);
-      COCG_LAUNCH_CHECK(ctx);
-      COCG_CUDA(ctx, cudaMemsetAsync(shist, 0, kSizeBins * 4, st));
-      bucket_size_hist_kernel<<<grid_for(nb, 256, 2), 256, 0, st>>>(counts, nb, shist);
-      COCG_LAUNCH_CHECK(ctx);
-      bucket_size_scan_kernel<<<1, 32, 0, st>>>(shist);
-      COCG_LAUNCH_CHECK(ctx);
-      bucket_order_kernel<<<(nb + 255) / 256, 256, 0, st>>>(counts, nb, shist, order);
-      COCG_LAUNCH_CHECK(ctx);
-      msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dig, n, nwin, start, counts, sorted);
-      COCG_LAUNCH_CHECK(ctx);
-    }
-    {
-      ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
-      msm_accumulate_kernel<F><<<(nb * kLanesPerBucket + 127) / 128, 128, 0, st>>>(table, be.n, sorted, start, order, nb, buckets, heavy_list, chunk_owner, heavy);
-      COCG_LAUNCH_CHECK(ctx);
-      msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, sorted, start, heavy_list, chunk_owner, heavy, hpartial);
-      COCG_LAUNCH_CHECK(ctx);
-      msm_heavy_fold_kernel<F><<<kNumSMs, 128, 0, st>>>(heavy_list, heavy, hpartial, buckets);
-      COCG_LAUNCH_CHECK(ctx);
-    }
-    ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
-    msm_marginals_kernel<F><<<(nmarg * 32 + 127) / 128, 128, 0, st>>>(buckets, logH, logL, marg);
-    COCG_LAUNCH_CHECK(ctx);
-    msm_sum_kernel<F><<<1, 256, 0, st>>>(marg, nmarg, result + j);
-    COCG_LAUNCH_CHECK(ctx);
-  }
-  void* hp;
-  COCG_TRY(pinned_get(ctx, (size_t)k * sizeof(X), &hp));
-  COCG_CUDA(ctx, cudaMemcpyAsync(hp, result, (size_t)k * sizeof(X), cudaMemcpyDeviceToHost, st));
-  COCG_CUDA(ctx, cudaStreamSynchronize(st));
-  const X* hw = reinterpret_cast<const X*>(hp);
-  for (int j = 0; j < k; j++) {
-    Jacobian<F> jr = xyzz_to_jacobian(hw[j]);
-    memcpy(out + (size_t)j * sizeof(jr), &jr, sizeof(jr));
-  }
+  msm_digits_kernel<FrP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars, n, c, nwin, mont, dig, counts);
+  COCG_LAUNCH_CHECK(ctx);
+  scan_block_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, S.start, nb, bsums);
+  COCG_LAUNCH_CHECK(ctx);
+  scan_top_kernel<<<1, kScanThreads, 0, st>>>(bsums, scan_blocks, bsums + scan_blocks);
+  COCG_LAUNCH_CHECK(ctx);
+  scan_add_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(S.start, nb, bsums, bsums + scan_blocks);
+  COCG_LAUNCH_CHECK(ctx);
+  COCG_CUDA(ctx, cudaMemsetAsync(shist, 0, kSizeBins * 4, st));
+  bucket_size_hist_kernel<<<grid_for(nb, 256, 2), 256, 0, st>>>(counts, nb, shist);
+  COCG_LAUNCH_CHECK(ctx);
+  bucket_size_scan_kernel<<<1, 32, 0, st>>>(shist);
+  COCG_LAUNCH_CHECK(ctx);
+  bucket_order_kernel<<<(nb + 255) / 256, 256, 0, st>>>(counts, nb, shist, S.order);
+  COCG_LAUNCH_CHECK(ctx);
+  msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dig, n, nwin, S.start, counts, S.sorted);  // drains counts[] to zero
+  COCG_LAUNCH_CHECK(ctx);
   return 0;
 }
 
+// accumulate + reduce one query against a finished sort; the XYZZ result is written to d_result (device)
+template <class F>
+int msm_accumulate_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, void* d_result) {
+  using X = XYZZ<F>;
+  if (be.c != S.c) return fail(ctx, "cocg_msm: the table's window width differs from the sort's");
+  const uint32_t nb = S.nb;
+  const uint32_t logL = (uint32_t)(S.c - 1) / 2, logH = (uint32_t)(S.c - 1) - logL;
+  const uint32_t nmarg = (1u << logH) + (1u << logL);
+  X *buckets, *marg, *hpartial;
+  void* p;
+  COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
+  COCG_TRY(scratch_get(ctx, 8, (size_t)nmarg * sizeof(X), &p)); marg = (X*)p;
+  COCG_TRY(scratch_get(ctx, 12, 2 * S.max_heavy * sizeof(X), &p)); hpartial = (X*)p;
+  const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
+  cudaStream_t st = ctx->stream;
+  {
+    ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
+    COCG_CUDA(ctx, cudaMemsetAsync(S.heavy, 0, 16, st));
+    msm_accumulate_kernel<F><<<(nb * kLanesPerBucket + 127) / 128, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list,
+                                                                                    S.chunk_owner, S.heavy);
+    COCG_LAUNCH_CHECK(ctx);
+    msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.heavy_list, S.chunk_owner, S.heavy, hpartial);
+    COCG_LAUNCH_CHECK(ctx);
+    msm_heavy_fold_kernel<F><<<kNumSMs, 128, 0, st>>>(S.heavy_list, S.heavy, hpartial, buckets);
+    COCG_LAUNCH_CHECK(ctx);
+  }
+  ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
+  msm_marginals_kernel<F><<<(nmarg * 32 + 127) / 128, 128, 0, st>>>(buckets, logH, logL, marg);
+  COCG_LAUNCH_CHECK(ctx);
+  msm_sum_kernel<F><<<1, 256, 0, st>>>(marg, nmarg, reinterpret_cast<X*>(d_result));
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+// host: XYZZ result (as copied back) -> Jacobian in caller memory (no alignment assumed)
+template <class F>
+void msm_finish_impl(const void* h_xyzz, void* out_jac) {
+  XYZZ<F> x;
+  memcpy(&x, h_xyzz, sizeof(x));
+  Jacobian<F> jr = xyzz_to_jacobian(x);
+  memcpy(out_jac, &jr, sizeof(jr));
+}
+
 // per-(curve, group) entry points, one translation unit each (msm_<curve>_<group>.cu)
-#define COCG_MSM_DECL(NAME)                                                                                                           \
-  int msm_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, size_t n, const void* const* scalars, int k, int mont, void* out_jac); \
+#define COCG_MSM_DECL(NAME)                                                                                     \
+  int msm_accumulate_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, void* d_result); \
+  void msm_finish_##NAME(const void* h_xyzz, void* out_jac);                                                      \
   int msm_precompute_##NAME(cocg_ctx* ctx, BasesEntry& be);
 COCG_MSM_DECL(bn254_g1)
 COCG_MSM_DECL(bn254_g2)

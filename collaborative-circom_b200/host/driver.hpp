@@ -181,6 +181,18 @@ class PlainDriver : public DeviceDriver {
     check(ctx, cocg_msm(ctx, bases, off, n, sc, 1, 1, r.a.l), "cocg_msm");
     return r;
   }
+  // several queries times the same scalars: one digit sort shared (cocg_msm_multi)
+  std::vector<PointShare> msm_public_points_multi(const std::vector<int>& groups, const std::vector<uint64_t>& bases, const std::vector<size_t>& offs,
+                                                  size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
+    const int nq = (int)bases.size();
+    std::vector<PointShare> r(nq);
+    std::vector<void*> outs(nq);
+    for (int q = 0; q < nq; q++) outs[q] = r[q].a.l;
+    const void* sc[1] = {scalars.a.at(scalar_off)};
+    check(ctx, cocg_msm_multi(ctx, bases.data(), offs.data(), nq, n, sc, 1, 1, outs.data()), "cocg_msm_multi");
+    (void)groups;
+    return r;
+  }
   // EcMpcProtocol (plain.rs:287-357)
   void add_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_add(g, a.a, b.a); }
   void sub_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_sub(g, a.a, b.a); }
@@ -308,6 +320,25 @@ class Rep3Protocol : public DeviceDriver {
     memcpy(out[0].l, packed.data(), 3 * group * lq * 8);
     memcpy(out[1].l, packed.data() + 3 * group * lq, 3 * group * lq * 8);
     return PointShare{out[0], out[1]};
+  }
+  std::vector<PointShare> msm_public_points_multi(const std::vector<int>& groups, const std::vector<uint64_t>& bases, const std::vector<size_t>& offs,
+                                                  size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
+    const int nq = (int)bases.size();
+    std::vector<PointShare> r(nq);
+    std::vector<std::vector<uint64_t>> packed(nq);
+    std::vector<void*> outs(nq);
+    for (int q = 0; q < nq; q++) {
+      packed[q].resize(2 * 3 * groups[q] * lq);
+      outs[q] = packed[q].data();
+    }
+    const void* sc[2] = {scalars.a.at(scalar_off), scalars.b.at(scalar_off)};
+    check(ctx, cocg_msm_multi(ctx, bases.data(), offs.data(), nq, n, sc, 2, 1, outs.data()), "cocg_msm_multi");
+    for (int q = 0; q < nq; q++) {
+      const size_t nl = 3 * groups[q] * lq;
+      memcpy(r[q].a.l, packed[q].data(), nl * 8);
+      memcpy(r[q].b.l, packed[q].data() + nl, nl * 8);
+    }
+    return r;
   }
   // ---- EcMpcProtocol (rep3.rs:769-862)
   void add_assign_points(int g, PointShare& a, const PointShare& b) { a.a = ec_add(g, a.a, b.a); a.b = ec_add(g, a.b, b.b); }

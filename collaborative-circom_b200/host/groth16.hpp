@@ -174,10 +174,14 @@ class CoGroth16 {
     shard.range(std::min(h.len(), zkey.domain_size()), off, len);
     m.h_acc = driver.msm_public_points(1, hd.h_query, off, len, h, off);
     shard.range(n_aux, off, len);
-    m.l_acc = driver.msm_public_points(1, hd.l_query, off, len, aux_assignment, off);
-    m.a_acc = driver.msm_public_points(1, hd.a_query, 1 + l + off, len, aux_assignment, off);
-    m.b1_acc = driver.msm_public_points(1, hd.b_g1_query, 1 + l + off, len, aux_assignment, off);
-    m.b2_acc = driver.msm_public_points(2, hd.b_g2_query, 1 + l + off, len, aux_assignment, off);
+    {  // the four queries multiplied by aux_assignment share one digit sort per share component
+      std::vector<PointShare> r = driver.msm_public_points_multi({1, 1, 1, 2}, {hd.l_query, hd.a_query, hd.b_g1_query, hd.b_g2_query},
+                                                                 {off, 1 + l + off, 1 + l + off, 1 + l + off}, len, aux_assignment, off);
+      m.l_acc = r[0];
+      m.a_acc = r[1];
+      m.b1_acc = r[2];
+      m.b2_acc = r[3];
+    }
     if (combine) combine(party_id(), m);
 
     Point delta_g1 = driver.from_affine(1, zkey.delta_g1);

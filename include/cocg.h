@@ -130,6 +130,12 @@ COCG_API int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_han
  * out_jacobian: HOST pointer, k Jacobian points. */
 COCG_API int cocg_msm(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, const void* const* scalars, int k,
              int scalars_mont, void* out_jacobian);
+/* Several queries times the SAME scalars: out[q][j] = sum_i scalars[j][i] * bases[q][offs[q] + i].  One digit sort per component
+ * is shared by all queries whose tables have the same window width -- the a_query / b_g1_query / b_g2_query / l_query MSMs of
+ * create_proof_with_assignment all take aux_assignment (groth16.rs:221-225, 251-255).  out_jacobian: HOST array of nq HOST
+ * pointers, k Jacobian points each. */
+COCG_API int cocg_msm_multi(cocg_ctx* ctx, const uint64_t* bases, const size_t* offs, int nq, size_t n, const void* const* scalars, int k,
+                   int scalars_mont, void* const* out_jacobian);
 /* Same with HOST scalar pointers (staged through pinned memory); the drop-in call for a host-resident caller. */
 COCG_API int cocg_msm_host(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, const void* const* scalars, int k,
                   int scalars_mont, void* out_jacobian);

@@ -343,3 +343,21 @@ def test_plonk_round1_kat_on_gpu(cocg, bn, bls, curve, circ):
         out = ctx.msm(h, [ctx.upload(poly)], n=n + 2)
         assert cref.jac_from_mont(c, out[0], 1) == (int(kat[name][0]), int(kat[name][1])), name
     ctx.bases_free(h)
+
+
+def test_msm_multi_shares_one_sort(cocg, bn):
+    """cocg_msm_multi: the Groth16 shape -- l_query (n_aux points), a/b_g1 (m points, offset 1 + l), b_g2 (G2) times the same
+    two share components -- equals separate MSMs / the oracle."""
+    c = BN254
+    m, ell = 3000, 1
+    n_aux = m - ell - 1
+    g1a, g1b, g1l = make_bases(c, 1, m, seed=21), make_bases(c, 1, m, seed=22), make_bases(c, 1, n_aux, seed=23)
+    g2b = make_bases(c, 2, m, seed=24)
+    hs = [bn.bases_upload(1, g1l), bn.bases_upload(1, g1a), bn.bases_upload(1, g1b), bn.bases_upload(2, g2b)]
+    sa, sb = rand_fr(n_aux, 71), rand_fr(n_aux, 72)
+    outs = bn.msm_multi(hs, [0, 1 + ell, 1 + ell, 1 + ell], [bn.upload(sa), bn.upload(sb)], n=n_aux)
+    for out, (pts, group, off) in zip(outs, ((g1l, 1, 0), (g1a, 1, 1 + ell), (g1b, 1, 1 + ell), (g2b, 2, 1 + ell))):
+        for j, s in enumerate((sa, sb)):
+            assert same_point(c, group, out[j], cref.msm(c, group, pts[off:off + n_aux], s))
+    for h in hs:
+        bn.bases_free(h)
