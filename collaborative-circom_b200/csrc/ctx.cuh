@@ -133,13 +133,13 @@ inline int pinned_get(cocg_ctx* ctx, size_t bytes, void** out) {
   return 0;
 }
 
-// Window width c of the MSM table built for a query of n points (msm_impl.cuh): about log2(n) - 3, so that buckets hold a few
-// hundred points each and the bucket reduction stays a few percent of the accumulation; 17 bits (15 windows) at n = 2^20.
+// Window width c of the MSM table built for a query of n points (msm_impl.cuh): about log2(n), capped at 20 bits
+// (13 windows for 254/255-bit scalars, 2^19 buckets of ~26 points at n = 2^20).
 inline int msm_plan_window_bits(size_t n) {
   int lg = 0;
   size_t v = n + n / 2;  // round to the nearest power of two
   while (((size_t)1 << (lg + 1)) <= v) lg++;
-  int c = lg - 3;
+  int c = lg;
   if (c < 4) c = 4;
   if (c > 20) c = 20;
   return c;

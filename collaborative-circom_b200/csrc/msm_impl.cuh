@@ -32,7 +32,6 @@ namespace cocg {
 
 constexpr int kHeavy = 1024;         // runs longer than this are cut into kHeavy-entry chunks, one warp each
 constexpr int kIdxBits = 25;         // entry = sign << 31 | window << 25 | point index
-constexpr int kLanesPerBucket = 4;   // threads that share one bucket's run in the accumulate kernel
 
 static int msm_window_bits(size_t n) { return msm_plan_window_bits(n); }  // ctx.cuh: shared with the table allocation
 template <class FrP>
@@ -265,8 +264,8 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const void* table, 
 }
 
 // ------------------------------------------------------------------ 4. bucket accumulation
-// kLanesPerBucket adjacent lanes share one bucket: they stride through its run and combine with shuffles, which keeps
-// >= 2^18 threads in flight at 2^16 buckets.  Buckets are taken in descending size order so a warp's groups finish together.
+// One thread per bucket, buckets taken in descending size order so that the lanes of a warp finish together (ncu: 31.7 of 32
+// lanes active, fmaheavy pipe 90 % busy at 2^19 buckets of ~26 points).
 struct HeavyRec {
   uint32_t bucket, first_chunk, nchunks;
 };
@@ -277,30 +276,20 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                               uint32_t* __restrict__ chunk_owner,
                                                               uint32_t* __restrict__ heavy_count /* [0] buckets, [1] chunks */) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t slot = t / kLanesPerBucket, sub = t % kLanesPerBucket;
-  const bool live = slot < nbuckets;
-  const uint32_t gb = live ? order[slot] : 0;
-  uint32_t beg = 0, end = 0;
-  if (live) { beg = start[gb]; end = start[gb + 1]; }
-  const bool heavy = end - beg > (uint32_t)kHeavy;
-  if (heavy) {
-    if (sub == 0) {
-      uint32_t nch = (end - beg + kHeavy - 1) / kHeavy;
-      uint32_t h = atomicAdd(&heavy_count[0], 1u);
-      uint32_t first = atomicAdd(&heavy_count[1], nch);
-      heavy_list[h] = HeavyRec{gb, first, nch};
-      for (uint32_t q = 0; q < nch; q++) chunk_owner[first + q] = h;
-    }
-    end = beg;  // nothing to do here; still take part in the shuffles below
+  if (t >= nbuckets) return;
+  const uint32_t gb = order[t];
+  const uint32_t beg = start[gb], end = start[gb + 1];
+  if (end - beg > (uint32_t)kHeavy) {
+    uint32_t nch = (end - beg + kHeavy - 1) / kHeavy;
+    uint32_t h = atomicAdd(&heavy_count[0], 1u);
+    uint32_t first = atomicAdd(&heavy_count[1], nch);
+    heavy_list[h] = HeavyRec{gb, first, nch};
+    for (uint32_t q = 0; q < nch; q++) chunk_owner[first + q] = h;
+    return;
   }
   XYZZ<F> acc = xyzz_inf<F>();
-  accumulate_run<F>(acc, table, tstride, sorted, beg + sub, end, kLanesPerBucket);
-#pragma unroll
-  for (int delta = kLanesPerBucket / 2; delta >= 1; delta >>= 1) {
-    XYZZ<F> other = warp_shfl_down(acc, delta);
-    if (sub < (uint32_t)delta) xyzz_add(acc, other);
-  }
-  if (live && !heavy && sub == 0) buckets[gb] = acc;
+  accumulate_run<F>(acc, table, tstride, sorted, beg, end, 1);
+  buckets[gb] = acc;
 }
 // skewed scalars (plain-driver witnesses, or a top window narrower than c bits): a warp per kHeavy-entry chunk ...
 template <class F>
@@ -354,8 +343,8 @@ __device__ __forceinline__ XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) 
   }
   return acc;
 }
-// Buckets form an H x L matrix (b = hi * L + lo).  Warp w < H: weighted row sum (L*w + 1) * sum_lo B[w][lo];
-// warp H + w: weighted column sum w * sum_hi B[hi][w].  Output: H + L points whose plain sum is the MSM.
+// Buckets form an H x L matrix (b = hi * L + lo); sum_b (b + 1) B_b = sum_hi (L*hi + 1) R_hi + sum_lo lo * C_lo.
+// Warp w < H: row sum R_w = sum_lo B[w][lo]; warp H + w: column sum C_w = sum_hi B[hi][w].
 template <class F>
 __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
                                                              XYZZ<F>* __restrict__ out) {
@@ -364,39 +353,44 @@ __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __res
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= H + L) return;
   XYZZ<F> acc = xyzz_inf<F>();
-  uint32_t weight;
   if (warp < H) {
     const XYZZ<F>* row = buckets + ((size_t)warp << logL);
     for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add(acc, row[lo]);
-    weight = (warp << logL) + 1;
   } else {
     const uint32_t lo = warp - H;
     for (uint32_t hi = lane; hi < H; hi += 32) xyzz_add(acc, buckets[((size_t)hi << logL) + lo]);
-    weight = lo;
   }
   for (int delta = 16; delta >= 1; delta >>= 1) {
     XYZZ<F> other = warp_shfl_down(acc, delta);
     if (lane < (uint32_t)delta) xyzz_add(acc, other);
   }
-  if (lane == 0) out[warp] = xyzz_mul_small(acc, weight);
+  if (lane == 0) out[warp] = acc;
 }
-// one CTA: plain sum of m points
+// weights: one THREAD per marginal (all lanes busy, unlike a multiply on the reducing lane), then a warp tree
 template <class F>
-__global__ void __launch_bounds__(256) msm_sum_kernel(const XYZZ<F>* __restrict__ in, uint32_t m, XYZZ<F>* __restrict__ out) {
-  __shared__ XYZZ<F> sh[8];
+__global__ void __launch_bounds__(128) msm_weigh_kernel(const XYZZ<F>* __restrict__ marg, uint32_t logH, uint32_t logL, XYZZ<F>* __restrict__ partial) {
+  const uint32_t H = 1u << logH, nmarg = H + (1u << logL);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   XYZZ<F> acc = xyzz_inf<F>();
-  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) xyzz_add(acc, in[i]);
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (i < nmarg) acc = xyzz_mul_small(marg[i], i < H ? (i << logL) + 1 : i - H);
   for (int delta = 16; delta >= 1; delta >>= 1) {
     XYZZ<F> other = warp_shfl_down(acc, delta);
     if (lane < (uint32_t)delta) xyzz_add(acc, other);
   }
-  if (lane == 0) sh[warp] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; k++) xyzz_add(acc, sh[k]);
-    *out = acc;
+  if (lane == 0) partial[i >> 5] = acc;
+}
+// one warp: plain sum of m points
+template <class F>
+__global__ void __launch_bounds__(32) msm_final_kernel(const XYZZ<F>* __restrict__ in, uint32_t m, XYZZ<F>* __restrict__ out) {
+  const uint32_t lane = threadIdx.x;
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (uint32_t i = lane; i < m; i += 32) xyzz_add(acc, in[i]);
+  for (int delta = 16; delta >= 1; delta >>= 1) {
+    XYZZ<F> other = warp_shfl_down(acc, delta);
+    if (lane < (uint32_t)delta) xyzz_add(acc, other);
   }
+  if (lane == 0) *out = acc;
 }
 
 // ------------------------------------------------------------------ drivers
@@ -471,18 +465,19 @@ int msm_accumulate_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const M
   const uint32_t nb = S.nb;
   const uint32_t logL = (uint32_t)(S.c - 1) / 2, logH = (uint32_t)(S.c - 1) - logL;
   const uint32_t nmarg = (1u << logH) + (1u << logL);
+  const uint32_t maxM = 1u << logH;  // logH >= logL
   X *buckets, *marg, *hpartial;
   void* p;
   COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
-  COCG_TRY(scratch_get(ctx, 8, (size_t)nmarg * sizeof(X), &p)); marg = (X*)p;
+  COCG_TRY(scratch_get(ctx, 8, ((size_t)nmarg + 4 * maxM + 2) * sizeof(X), &p)); marg = (X*)p;  // marginals | scan ping-pong x 2 | partials
   COCG_TRY(scratch_get(ctx, 12, 2 * S.max_heavy * sizeof(X), &p)); hpartial = (X*)p;
   const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
   cudaStream_t st = ctx->stream;
   {
     ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
     COCG_CUDA(ctx, cudaMemsetAsync(S.heavy, 0, 16, st));
-    msm_accumulate_kernel<F><<<(nb * kLanesPerBucket + 127) / 128, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list,
-                                                                                    S.chunk_owner, S.heavy);
+    msm_accumulate_kernel<F><<<(nb + 127) / 128, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list, S.chunk_owner,
+                                                                S.heavy);
     COCG_LAUNCH_CHECK(ctx);
     msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.heavy_list, S.chunk_owner, S.heavy, hpartial);
     COCG_LAUNCH_CHECK(ctx);
@@ -492,7 +487,10 @@ int msm_accumulate_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const M
   ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
   msm_marginals_kernel<F><<<(nmarg * 32 + 127) / 128, 128, 0, st>>>(buckets, logH, logL, marg);
   COCG_LAUNCH_CHECK(ctx);
-  msm_sum_kernel<F><<<1, 256, 0, st>>>(marg, nmarg, reinterpret_cast<X*>(d_result));
+  const uint32_t nwarps = (nmarg + 31) / 32;
+  msm_weigh_kernel<F><<<(nmarg + 127) / 128, 128, 0, st>>>(marg, logH, logL, marg + nmarg);
+  COCG_LAUNCH_CHECK(ctx);
+  msm_final_kernel<F><<<1, 32, 0, st>>>(marg + nmarg, nwarps, reinterpret_cast<X*>(d_result));
   COCG_LAUNCH_CHECK(ctx);
   return 0;
 }
