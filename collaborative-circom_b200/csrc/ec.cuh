@@ -131,6 +131,34 @@ COCG_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
   acc.zzz = f_mul(acc.zzz, PPP);
 }
 
+// acc += q, add-2008-s; 12M + 2S.  Inline variant for the bucket-reduction loops (the out-of-line one keeps its accumulator
+// in local memory across the call).
+template <class F>
+COCG_HD void xyzz_add_inline(XYZZ<F>& acc, const XYZZ<F>& q) {
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = q; return; }
+  F U1 = f_mul(acc.x, q.zz);
+  F U2 = f_mul(q.x, acc.zz);
+  F S1 = f_mul(acc.y, q.zzz);
+  F S2 = f_mul(q.y, acc.zzz);
+  F Pd = f_sub(U2, U1);
+  F R = f_sub(S2, S1);
+  if (Pd.is_zero()) {
+    if (R.is_zero()) acc = xyzz_dbl(acc);
+    else acc = xyzz_inf<F>();
+    return;
+  }
+  F PP = f_sqr(Pd);
+  F PPP = f_mul(Pd, PP);
+  F Q = f_mul(U1, PP);
+  F X3 = f_sub(f_sub(f_sqr(R), PPP), f_dbl(Q));
+  F Y3 = f_sub(f_mul(R, f_sub(Q, X3)), f_mul(S1, PPP));
+  acc.x = X3;
+  acc.y = Y3;
+  acc.zz = f_mul(f_mul(acc.zz, q.zz), PP);
+  acc.zzz = f_mul(f_mul(acc.zzz, q.zzz), PPP);
+}
+
 // acc += q, add-2008-s; 12M + 2S
 template <class F>
 COCG_EC_OUTLINE void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
