@@ -67,6 +67,18 @@ __global__ void __launch_bounds__(256) prf_fill_kernel(PrfKey key, uint32_t ctr,
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) store_fp<P>(out, i, prf_field<P>(key, ctr, i));
 }
 
+// out[i] = a * x[i] (+ y[i]): the linear combinations of the Shamir driver (Lagrange interpolation at the king, polynomial
+// re-sharing, Vandermonde extraction: shamir.rs:302-384, 904-1010, shamir/shamir_core.rs:8-33)
+template <class P, bool ADD>
+__global__ void __launch_bounds__(256) vec_axpy_kernel(Fp<P> a, const void* __restrict__ x, const void* __restrict__ y, void* __restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fp<P> r = fp_mul(a, load_fp<P>(x, i));
+    if (ADD) r = fp_add(r, load_fp<P>(y, i));
+    store_fp<P>(out, i, r);
+  }
+}
+
 // out[i] = first * base^i.  Thread t owns a run of RUN consecutive exponents: one square-and-multiply to
 // reach base^(t*RUN), then RUN-1 dependent products.
 constexpr int kPowRun = 32;
@@ -152,6 +164,17 @@ static int rep3_mul_local_prf_impl(cocg_ctx* ctx, const void* aa, const void* ab
   return 0;
 }
 template <class P>
+static int vec_axpy_impl(cocg_ctx* ctx, const void* a, const void* x, const void* y, void* out, size_t n) {
+  if (n == 0) return 0;
+  Fp<P> av;
+  memcpy(av.l, a, 32);
+  ProfScope prof(ctx, COCG_PROF_VEC);
+  if (y) vec_axpy_kernel<P, true><<<grid_for(n, 256, 8), 256, 0, ctx->stream>>>(av, x, y, out, n);
+  else vec_axpy_kernel<P, false><<<grid_for(n, 256, 8), 256, 0, ctx->stream>>>(av, x, y, out, n);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template <class P>
 static int prf_fill_impl(cocg_ctx* ctx, const void* seed, uint32_t ctr, void* out, size_t n) {
   if (n == 0) return 0;
   PrfKey k;
@@ -171,6 +194,12 @@ extern "C" int cocg_rep3_mul_local_prf(cocg_ctx* ctx, const void* aa, const void
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!seed_own || !seed_prev || (n && (!aa || !ab || !ba || !bb || !out))) return fail(ctx, "cocg_rep3_mul_local_prf: null operand");
   return COCG_FR_DISPATCH(ctx, rep3_mul_local_prf_impl, ctx, aa, ab, ba, bb, seed_own, seed_prev, ctr, out, n);
+}
+extern "C" int cocg_vec_axpy(cocg_ctx* ctx, const void* a, const void* x, const void* y, void* out, size_t n) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!a || (n && (!x || !out))) return fail(ctx, "cocg_vec_axpy: null operand");
+  return COCG_FR_DISPATCH(ctx, vec_axpy_impl, ctx, a, x, y, out, n);
 }
 extern "C" int cocg_prf_fill(cocg_ctx* ctx, const void* seed, uint32_t ctr, void* out, size_t n) {
   if (!ctx) return 1;

@@ -7,6 +7,7 @@
 
 #include "../../include/cohost.h"
 #include "groth16.hpp"
+#include "shamir.hpp"
 
 using namespace cohost;
 
@@ -464,5 +465,86 @@ extern "C" int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off
   sh.rank = rank;
   sh.world = world;
   sh.range(n, *off, *len);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Shamir, n parties
+struct cohost_shamir_session {
+  cohost_zkey* zkey = nullptr;
+  int n = 3, t = 1;
+  std::unique_ptr<ShamirTestNetwork> net;
+  std::vector<std::unique_ptr<ShamirProtocol>> drv;
+  std::vector<std::unique_ptr<CoGroth16<ShamirProtocol>>> prover;
+  std::vector<CoGroth16<ShamirProtocol>::Handles> hd;
+  bool failed = false;
+};
+
+extern "C" int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out) {
+  if (!z || !out || !seeds) return fail("cohost_shamir_session_create: null argument");
+  if (num_parties < 3 || num_parties > 64) return fail("Shamir protocol requires at least 3 parties");  // shamir/network.rs:75-77
+  return guarded([&] {
+    std::unique_ptr<cohost_shamir_session> s(new cohost_shamir_session());
+    s->zkey = z;
+    s->n = num_parties;
+    s->t = threshold;
+    s->net.reset(new ShamirTestNetwork(num_parties));
+    s->hd.resize(num_parties);
+    for (int i = 0; i < num_parties; i++) {
+      s->drv.emplace_back(new ShamirProtocol(z->zk.curve, z->device, threshold, s->net->party(i), seeds + 32 * i));
+      s->prover.emplace_back(new CoGroth16<ShamirProtocol>(*s->drv[i]));
+      share_handles(s->drv[i]->ctx, z->zk, s->hd[i]);
+    }
+    *out = s.release();
+  });
+}
+extern "C" void cohost_shamir_session_destroy(cohost_shamir_session* s) {
+  if (!s) return;
+  for (size_t i = 0; i < s->drv.size(); i++) s->drv[i]->release(s->prover[i]->last_h);
+  delete s;
+}
+// wit[i]: party i's HOST share vector (m - l - 1 Fr).  proofs_out: n x (A | B | C); rs_out: NULL or n x (r share | s share) --
+// the parties' degree-t shares of the prover randomness, so a test can reconstruct (r, s) and compare with the plain prover.
+extern "C" int cohost_shamir_prove(cohost_shamir_session* s, const void* public_inputs, const void* const* wit, void* proofs_out, void* rs_out) {
+  if (!s || !public_inputs || !wit || !proofs_out) return fail("cohost_shamir_prove: null argument");
+  if (s->failed) return fail("cohost_shamir_prove: the session's network is closed after an earlier failure");
+  const ZKey& zk = s->zkey->zk;
+  const size_t lq = s->zkey->lq;
+  std::vector<std::thread> th(s->n);
+  std::vector<std::string> errs(s->n);
+  std::vector<Groth16Proof> proofs(s->n);
+  std::vector<const void*> w(wit, wit + s->n);
+  for (int i = 0; i < s->n; i++) {
+    th[i] = std::thread([&, i] {
+      try {
+        ShamirProtocol& d = *s->drv[i];
+        std::vector<Fr> pub_host(zk.num_inputs());
+        memcpy(pub_host.data(), public_inputs, zk.num_inputs() * 32);
+        DevVec pub = d.upload(public_inputs, zk.num_inputs());
+        FieldShareVec witv = d.share_vec_from_host(w[i], nullptr, zk.n_aux());
+        proofs[i] = s->prover[i]->prove(zk, s->hd[i], pub, pub_host, witv);
+        d.release(witv);
+        d.release(pub);
+      } catch (const std::exception& e) {
+        errs[i] = e.what();
+        s->net->close_all();
+      }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < s->n; i++)
+    if (!errs[i].empty()) {
+      s->failed = true;
+      return fail("party " + std::to_string(i) + ": " + errs[i]);
+    }
+  for (int i = 0; i < s->n; i++) {
+    uint64_t* o = (uint64_t*)proofs_out + (size_t)i * 8 * lq;
+    memcpy(o, proofs[i].pi_a.l, 2 * lq * 8);
+    memcpy(o + 2 * lq, proofs[i].pi_b.l, 4 * lq * 8);
+    memcpy(o + 6 * lq, proofs[i].pi_c.l, 2 * lq * 8);
+    if (rs_out) {
+      memcpy((char*)rs_out + 64 * i, s->prover[i]->last_r.a.l, 32);
+      memcpy((char*)rs_out + 64 * i + 32, s->prover[i]->last_s.a.l, 32);
+    }
+  }
   return 0;
 }

@@ -101,6 +101,7 @@ class CoGroth16 {
   MsmShard shard;
   MsmCombine combine;
   FieldShareVec last_h;  // kept for parity tests (released by the next prove)
+  FieldShare last_r, last_s;
 
   // bases/CSR handles of `zkey` valid in driver.ctx (aliases made by the session)
   struct Handles {
@@ -114,6 +115,8 @@ class CoGroth16 {
     FieldShareVec h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
     FieldShare r = driver.rand();
     FieldShare s = driver.rand();
+    last_r = r;
+    last_s = s;
     Groth16Proof p = create_proof_with_assignment(zkey, hd, r, s, h, public_inputs_host, private_witness);
     last_h = h;
     return p;

@@ -21,7 +21,8 @@ HOST_SYMBOLS = [
     "cohost_plain_session_destroy", "cohost_plain_prove", "cohost_rep3_session_create", "cohost_rep3_session_destroy",
     "cohost_rep3_prove_begin", "cohost_rep3_partial_bytes", "cohost_rep3_prove_partials", "cohost_rep3_prove_combine",
     "cohost_rep3_prove_end", "cohost_rep3_launch_count", "cohost_rep3_prove_begin_device", "cohost_rep3_profile_enable",
-    "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range",
+    "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range", "cohost_shamir_session_create",
+    "cohost_shamir_session_destroy", "cohost_shamir_prove",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -75,6 +76,10 @@ def load_host():
     L.cohost_rep3_prove_end.argtypes = [vp, vp, pvp, pvp]
     L.cohost_rep3_launch_count.argtypes = [vp]
     L.cohost_rep3_launch_count.restype = u64
+    L.cohost_shamir_session_create.argtypes = [vp, ci, ci, vp, pvp]
+    L.cohost_shamir_session_destroy.argtypes = [vp]
+    L.cohost_shamir_session_destroy.restype = None
+    L.cohost_shamir_prove.argtypes = [vp, vp, pvp, vp, vp]
     L.cohost_msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     _host = L
     return L
@@ -263,4 +268,34 @@ class Rep3Session:
     def close(self):
         if self.h:
             load_host().cohost_rep3_session_destroy(self.h)
+            self.h = None
+
+
+class ShamirSession:
+    """n CoGroth16<ShamirProtocol> provers (threshold t) on n threads over an in-process network."""
+
+    def __init__(self, zkey: Groth16ZKey, num_parties: int = 3, threshold: int = 1, seeds: bytes | None = None):
+        self.zkey, self.n, self.t = zkey, num_parties, threshold
+        seeds = seeds or bytes((i * 7 + 1) % 256 for i in range(32 * num_parties))
+        assert len(seeds) == 32 * num_parties
+        self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
+        h = vp()
+        _ck(load_host().cohost_shamir_session_create(zkey.h, num_parties, threshold, self._seeds.ctypes.data, ctypes.byref(h)))
+        self.h = h
+
+    def prove(self, public_inputs, wit):
+        """wit: n host share vectors.  Returns (proofs (n, A|B|C), rs (n, 2, 4): each party's shares of r and s)."""
+        zk = self.zkey
+        pub = _c(public_inputs)
+        ws = [_c(x) for x in wit]
+        assert len(ws) == self.n and pub.size == 4 * (zk.n_public + 1) and all(x.size == 4 * zk.n_aux for x in ws)
+        W = (vp * self.n)(*[x.ctypes.data for x in ws])
+        proofs = np.zeros((self.n, 8 * zk.lq), dtype=np.uint64)
+        rs = np.zeros((self.n, 2, 4), dtype=np.uint64)
+        _ck(load_host().cohost_shamir_prove(self.h, pub.ctypes.data, W, proofs.ctypes.data, rs.ctypes.data))
+        return proofs, rs
+
+    def close(self):
+        if self.h:
+            load_host().cohost_shamir_session_destroy(self.h)
             self.h = None

@@ -78,6 +78,10 @@ COCG_API int cocg_host_free(cocg_ctx* ctx, void* hptr);
  * Replaces PrimeFieldMpcProtocol::{add_vec, sub_assign_vec, neg_vec_in_place, mul (plain/Shamir local)}
  * traits.rs:67,146-149,161; rep3.rs:581-593,634-648,672-679; plain.rs:111-285.  `out` may alias `a`/`b`. */
 COCG_API int cocg_vec_op(cocg_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n);
+/* out[i] = a * x[i] + y[i] (y may be NULL: out = a * x); a: HOST pointer to one Montgomery Fr, x / y / out DEVICE, out may alias.
+ * The linear combinations of the Shamir driver: Lagrange interpolation at the king and re-sharing (shamir.rs:302-384), Vandermonde
+ * extraction of the double-random pairs (shamir.rs:904-1010), ShamirCore::share (shamir/shamir_core.rs:8-33). */
+COCG_API int cocg_vec_axpy(cocg_ctx* ctx, const void* a, const void* x, const void* y, void* out, size_t n);
 /* a5: x[i] <- x[i] * c * g^i.  Replaces distribute_powers_and_mul_by_const traits.rs:177, rep3.rs:681-688.
  * g, c: HOST pointers to one Montgomery Fr each. */
 COCG_API int cocg_vec_scale_powers(cocg_ctx* ctx, void* x, size_t n, const void* g, const void* c);

@@ -25,6 +25,7 @@ extern "C" {
 typedef struct cohost_zkey cohost_zkey;
 typedef struct cohost_plain_session cohost_plain_session;
 typedef struct cohost_rep3_session cohost_rep3_session;
+typedef struct cohost_shamir_session cohost_shamir_session;
 
 /* A parsed Groth16 proving key (circom-types/src/groth16/zkey.rs:47-71), HOST pointers; copied to HBM once. */
 typedef struct cohost_zkey_desc {
@@ -87,6 +88,12 @@ COHOST_API int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gat
 /* proofs_out: 3 x (A | B | C); h_a / h_b: NULL or 3 HOST buffers of 2^pow Fr receiving each party's share of h. */
 COHOST_API int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, void* const* h_a, void* const* h_b);
 COHOST_API uint64_t cohost_rep3_launch_count(cohost_rep3_session* s);
+/* num_parties CoGroth16<ShamirProtocol> provers (mpc-core/src/protocols/shamir.rs), threshold t with 2t + 1 <= num_parties, on
+ * one thread each over an in-process network; seeds: num_parties x 32 bytes.  wit[i]: party i's HOST share vector; proofs_out:
+ * num_parties x (A | B | C); rs_out: NULL or num_parties x (share of r | share of s) for tests. */
+COHOST_API int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out);
+COHOST_API void cohost_shamir_session_destroy(cohost_shamir_session* s);
+COHOST_API int cohost_shamir_prove(cohost_shamir_session* s, const void* public_inputs, const void* const* wit, void* proofs_out, void* rs_out);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 

@@ -197,3 +197,53 @@ def test_prf_field_host_matches_device(cocg, bn, bls):
         assert len(set(vals[0])) == n
         masks = [[(vals[i][j] - vals[(i - 1) % 3][j]) % c.r for j in range(n)] for i in range(3)]
         assert all((masks[0][j] + masks[1][j] + masks[2][j]) % c.r == 0 for j in range(n))
+
+
+# ------------------------------------------------------------------------------------------------ Shamir
+def _share_shamir(vals, n, t, rng, r):
+    """shamir/utils share_field_elements: party i holds p(i + 1) for a random degree-t polynomial with p(0) = value."""
+    out = [[] for _ in range(n)]
+    for v in vals:
+        coeffs = [rng.randrange(r) for _ in range(t)]
+        for p in range(n):
+            x = p + 1
+            out[p].append((v + sum(c * pow(x, k + 1, r) for k, c in enumerate(coeffs))) % r)
+    return out
+
+
+def _lagrange_at_zero(points, r):
+    res = []
+    for i in points:
+        num = den = 1
+        for j in points:
+            if i != j:
+                num = num * j % r
+                den = den * (j - i) % r
+        res.append(num * pow(den, -1, r) % r)
+    return res
+
+
+@pytest.mark.parametrize("curve,circ,n,t", [("bn254", "multiplier2", 3, 1), ("bn254", "poseidon", 3, 1), ("bls12_381", "poseidon", 3, 1),
+                                            ("bn254", "poseidon", 5, 2)])
+def test_shamir_prove_matches_plain_oracle(cocg, curve, circ, n, t):
+    """CoGroth16<ShamirProtocol> (mpc-core/src/protocols/shamir.rs; tests/tests/circom/e2e_tests: all parties output the same proof,
+    which verifies).  The proof must also be the plain prover's proof for the (r, s) reconstructed from the parties' shares."""
+    zk, wt, vk, public = load_fixture(curve, circ)
+    c = zk.curve
+    prover, dz = device_zkey(cocg, zk)
+    sess = prover.ShamirSession(dz, n, t)
+    rng = random.Random(55)
+    ell = zk.n_public
+    pub = cref.fr_to_mont(c, wt[:ell + 1])
+    shares = _share_shamir([v % c.r for v in wt[ell + 1:]], n, t, rng, c.r)
+    for _ in range(2):  # the session is reusable; fresh double-random pairs each time
+        proofs, rs = sess.prove(pub, [cref.fr_to_mont(c, s) for s in shares])
+        got = [proof_points(c, p) for p in proofs]
+        assert all(g == got[0] for g in got)
+        assert groth16.verify(vk, *got[0], public)
+        lag = _lagrange_at_zero(list(range(1, t + 2)), c.r)
+        r_val = sum(l * v for l, v in zip(lag, cref.fr_from_mont(c, rs[:t + 1, 0]))) % c.r
+        s_val = sum(l * v for l, v in zip(lag, cref.fr_from_mont(c, rs[:t + 1, 1]))) % c.r
+        assert got[0] == groth16.prove_plain(zk, wt, r_val, s_val)
+    sess.close()
+    dz.close()
