@@ -344,26 +344,25 @@ __device__ __forceinline__ XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) 
   return acc;
 }
 // Buckets form an H x L matrix (b = hi * L + lo); sum_b (b + 1) B_b = sum_hi (L*hi + 1) R_hi + sum_lo lo * C_lo with the
-// row sums R_hi = sum_lo B[hi][lo] and column sums C_lo = sum_hi B[hi][lo].  Every row and column is cut into kMargSeg
-// segments, one warp each (kMargSeg = 1 measured best: more segments add more tree steps than they hide latency).  out[(row * kMargSeg + seg)], then out[H * kMargSeg + col * kMargSeg + seg].
-constexpr uint32_t kMargSeg = 1;
+// row sums R_hi = sum_lo B[hi][lo] and column sums C_lo = sum_hi B[hi][lo].  One warp per row; columns (twice as long when
+// H = 2L) are cut into kColSeg segments of one warp each, so that all warps run the same number of additions.
+// out[row], then out[H + col * kColSeg + seg].
+constexpr uint32_t kColSeg = 2;
 template <class F>
 __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
                                                              XYZZ<F>* __restrict__ out) {
   const uint32_t H = 1u << logH, L = 1u << logL;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= (H + L) * kMargSeg) return;
+  if (warp >= H + L * kColSeg) return;
   XYZZ<F> acc = xyzz_inf<F>();
-  if (warp < H * kMargSeg) {
-    const uint32_t row = warp / kMargSeg, seg = warp % kMargSeg;
-    const uint32_t lo0 = (uint32_t)((uint64_t)seg * L / kMargSeg), lo1 = (uint32_t)((uint64_t)(seg + 1) * L / kMargSeg);
-    const XYZZ<F>* r = buckets + ((size_t)row << logL);
-    for (uint32_t lo = lo0 + lane; lo < lo1; lo += 32) xyzz_add_inline(acc, r[lo]);
+  if (warp < H) {
+    const XYZZ<F>* r = buckets + ((size_t)warp << logL);
+    for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add_inline(acc, r[lo]);
   } else {
-    const uint32_t w = warp - H * kMargSeg;
-    const uint32_t col = w / kMargSeg, seg = w % kMargSeg;
-    const uint32_t hi0 = (uint32_t)((uint64_t)seg * H / kMargSeg), hi1 = (uint32_t)((uint64_t)(seg + 1) * H / kMargSeg);
+    const uint32_t w = warp - H;
+    const uint32_t col = w / kColSeg, seg = w % kColSeg;
+    const uint32_t hi0 = (uint32_t)((uint64_t)seg * H / kColSeg), hi1 = (uint32_t)((uint64_t)(seg + 1) * H / kColSeg);
     for (uint32_t hi = hi0 + lane; hi < hi1; hi += 32) xyzz_add_inline(acc, buckets[((size_t)hi << logL) + col]);
   }
   for (int delta = 16; delta >= 1; delta >>= 1) {
@@ -375,11 +374,11 @@ __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __res
 // weights: one THREAD per partial marginal (all lanes busy, unlike a multiply on the reducing lane), then a warp tree
 template <class F>
 __global__ void __launch_bounds__(128) msm_weigh_kernel(const XYZZ<F>* __restrict__ marg, uint32_t logH, uint32_t logL, XYZZ<F>* __restrict__ partial) {
-  const uint32_t H = 1u << logH, nmarg = (H + (1u << logL)) * kMargSeg;
+  const uint32_t H = 1u << logH, nmarg = H + (1u << logL) * kColSeg;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
   XYZZ<F> acc = xyzz_inf<F>();
-  if (i < nmarg) acc = xyzz_mul_small(marg[i], i < H * kMargSeg ? ((i / kMargSeg) << logL) + 1 : (i - H * kMargSeg) / kMargSeg);
+  if (i < nmarg) acc = xyzz_mul_small(marg[i], i < H ? (i << logL) + 1 : (i - H) / kColSeg);
   for (int delta = 16; delta >= 1; delta >>= 1) {
     XYZZ<F> other = warp_shfl_down(acc, delta);
     if (lane < (uint32_t)delta) xyzz_add(acc, other);
@@ -470,7 +469,7 @@ int msm_accumulate_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const M
   if (be.c != S.c) return fail(ctx, "cocg_msm: the table's window width differs from the sort's");
   const uint32_t nb = S.nb;
   const uint32_t logL = (uint32_t)(S.c - 1) / 2, logH = (uint32_t)(S.c - 1) - logL;
-  const uint32_t nmarg = ((1u << logH) + (1u << logL)) * kMargSeg;
+  const uint32_t nmarg = (1u << logH) + (1u << logL) * kColSeg;
   X *buckets, *marg, *hpartial;
   void* p;
   COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;

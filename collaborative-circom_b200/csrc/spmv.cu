@@ -44,7 +44,13 @@ using namespace cocg;
 
 extern "C" int cocg_csr_upload(cocg_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const void* coeff, size_t rows, size_t nnz,
                                uint64_t* handle) {
+  return cocg_csr_upload_form(ctx, rowptr, col, coeff, rows, nnz, COCG_FORM_MONT, handle);
+}
+
+extern "C" int cocg_csr_upload_form(cocg_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const void* coeff, size_t rows, size_t nnz,
+                                    int coeff_form, uint64_t* handle) {
   if (!ctx) return 1;
+  if (coeff_form < COCG_FORM_MONT || coeff_form > COCG_FORM_CANONICAL) return fail(ctx, "cocg_csr_upload: unknown coefficient form");
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!handle || !rowptr || (nnz && (!col || !coeff))) return fail(ctx, "cocg_csr_upload: null argument");
   if (rowptr[rows] != nnz) return fail(ctx, "cocg_csr_upload: rowptr[rows] != nnz");
@@ -57,6 +63,9 @@ extern "C" int cocg_csr_upload(cocg_ctx* ctx, const uint32_t* rowptr, const uint
   if (nnz) {
     COCG_CUDA(ctx, cudaMemcpyAsync(m.col, col, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
     COCG_CUDA(ctx, cudaMemcpyAsync(m.coeff, coeff, nnz * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // zkey section 4 stores value * R^2: one Montgomery reduction gives the Montgomery form value * R (circom-types traits.rs:65-67)
+    if (coeff_form == COCG_FORM_R2) COCG_TRY(cocg_vec_op(ctx, COCG_OP_FROM_MONT, m.coeff, nullptr, m.coeff, nnz));
+    if (coeff_form == COCG_FORM_CANONICAL) COCG_TRY(cocg_vec_op(ctx, COCG_OP_TO_MONT, m.coeff, nullptr, m.coeff, nnz));
   }
   COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < ctx->csrs.size(); i++)
@@ -74,6 +83,19 @@ extern "C" int cocg_csr_free(cocg_ctx* ctx, uint64_t handle) {
   CsrEntry& m = ctx->csrs[handle - 1];
   if (m.owned) { cudaFree(m.rowptr); cudaFree(m.col); cudaFree(m.coeff); }
   m = CsrEntry();
+  return 0;
+}
+
+extern "C" int cocg_csr_download(cocg_ctx* ctx, uint64_t handle, uint32_t* rowptr, uint32_t* col, void* coeff, size_t* nnz) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (handle == 0 || handle > ctx->csrs.size() || !ctx->csrs[handle - 1].rowptr) return fail(ctx, "cocg_csr_download: bad handle");
+  const CsrEntry& m = ctx->csrs[handle - 1];
+  if (nnz) *nnz = m.nnz;
+  if (rowptr) COCG_CUDA(ctx, cudaMemcpyAsync(rowptr, m.rowptr, (m.rows + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (col && m.nnz) COCG_CUDA(ctx, cudaMemcpyAsync(col, m.col, m.nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (coeff && m.nnz) COCG_CUDA(ctx, cudaMemcpyAsync(coeff, m.coeff, m.nnz * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

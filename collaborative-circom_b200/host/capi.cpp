@@ -8,6 +8,7 @@
 #include "../../include/cohost.h"
 #include "groth16.hpp"
 #include "shamir.hpp"
+#include "formats.hpp"
 
 using namespace cohost;
 
@@ -107,8 +108,8 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
     bases(COCG_G2, d->b_g2_query, m, 3, &zk.b_g2_query, "b_g2_query");
     bases(COCG_G1, d->h_query, zk.domain_size(), 4, &zk.h_query, "h_query");
     bases(COCG_G1, d->l_query, zk.n_aux(), 5, &zk.l_query, "l_query");
-    check(c, cocg_csr_upload(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, &zk.csr_a), "csr_a");
-    check(c, cocg_csr_upload(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, &zk.csr_b), "csr_b");
+    check(c, cocg_csr_upload_form(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, d->coeff_form, &zk.csr_a), "csr_a");
+    check(c, cocg_csr_upload_form(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, d->coeff_form, &zk.csr_b), "csr_b");
     zk.a_head.resize(l + 1);
     zk.b_g1_head.resize(l + 1);
     zk.b_g2_head.resize(l + 1);
@@ -547,4 +548,90 @@ extern "C" int cohost_shamir_prove(cohost_shamir_session* s, const void* public_
     }
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ snarkjs files
+// ZKey::from_reader (circom-types/src/groth16/zkey.rs:109, :139-251): parse a Groth16 .zkey image and make it resident in HBM.
+extern "C" int cohost_zkey_load(const void* data, size_t len, int device, cohost_zkey** out) {
+  if (!data || !out) return fail("cohost_zkey_load: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    Groth16ZKeyFile f((const uint8_t*)data, len);
+    cohost_zkey_desc d;
+    memset(&d, 0, sizeof(d));
+    d.curve = f.curve;
+    d.device = device;
+    d.n_public = f.n_public;
+    d.n_vars = f.n_vars;
+    d.pow = f.pow;
+    d.num_constraints = f.num_constraints;
+    d.a_rowptr = f.rowptr[0].data(); d.a_col = f.col[0].data(); d.a_coeff = f.coeff_raw[0].data(); d.a_nnz = f.col[0].size();
+    d.b_rowptr = f.rowptr[1].data(); d.b_col = f.col[1].data(); d.b_coeff = f.coeff_raw[1].data(); d.b_nnz = f.col[1].size();
+    d.coeff_form = COCG_FORM_R2;
+    d.a_query = f.a_query; d.b_g1_query = f.b_g1_query; d.b_g2_query = f.b_g2_query; d.h_query = f.h_query; d.l_query = f.l_query;
+    d.alpha_g1 = f.alpha_g1; d.beta_g1 = f.beta_g1; d.delta_g1 = f.delta_g1; d.beta_g2 = f.beta_g2; d.delta_g2 = f.delta_g2;
+    if (cohost_zkey_create(&d, out)) throw Error(cohost_last_error());
+  });
+}
+extern "C" int cohost_zkey_load_file(const char* path, int device, cohost_zkey** out) {
+  if (!path || !out) return fail("cohost_zkey_load_file: null argument");
+  std::vector<uint8_t> buf;
+  int rc = guarded([&] { buf = read_file(path); });
+  if (rc) return rc;
+  return cohost_zkey_load(buf.data(), buf.size(), device, out);
+}
+extern "C" int cohost_zkey_get_info(cohost_zkey* z, cohost_zkey_info* info) {
+  if (!z || !info) return fail("cohost_zkey_get_info: null argument");
+  info->curve = z->zk.curve;
+  info->n_public = z->zk.n_public;
+  info->n_vars = z->zk.n_vars;
+  info->pow = z->zk.pow;
+  info->num_constraints = z->zk.num_constraints;
+  return 0;
+}
+// which: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query; packed affine Montgomery points
+extern "C" int cohost_zkey_query_download(cohost_zkey* z, int which, size_t off, size_t n, void* out) {
+  if (!z || !out) return fail("cohost_zkey_query_download: null argument");
+  const uint64_t h[5] = {z->zk.a_query, z->zk.b_g1_query, z->zk.b_g2_query, z->zk.h_query, z->zk.l_query};
+  if (which < 0 || which > 4) return fail("cohost_zkey_query_download: unknown query");
+  if (cocg_bases_download(z->zk.owner, h[which], off, n, out)) return fail(cocg_last_error(z->zk.owner));
+  return 0;
+}
+// which: 0 = A, 1 = B.  Any of rowptr (rows + 1), col (nnz), coeff (nnz Fr, Montgomery) may be NULL; nnz is always returned.
+extern "C" int cohost_zkey_matrix_download(cohost_zkey* z, int which, uint32_t* rowptr, uint32_t* col, void* coeff, size_t* nnz) {
+  if (!z) return fail("cohost_zkey_matrix_download: null argument");
+  if (which < 0 || which > 1) return fail("cohost_zkey_matrix_download: unknown matrix");
+  if (cocg_csr_download(z->zk.owner, which ? z->zk.csr_b : z->zk.csr_a, rowptr, col, coeff, nnz)) return fail(cocg_last_error(z->zk.owner));
+  return 0;
+}
+// alpha_g1 | beta_g1 | delta_g1 (G1 affine) | beta_g2 | delta_g2 (G2 affine)
+extern "C" int cohost_zkey_vk_download(cohost_zkey* z, void* out) {
+  if (!z || !out) return fail("cohost_zkey_vk_download: null argument");
+  const size_t lq = z->lq;
+  uint64_t* o = (uint64_t*)out;
+  memcpy(o, z->zk.alpha_g1.l, 2 * lq * 8);
+  memcpy(o + 2 * lq, z->zk.beta_g1.l, 2 * lq * 8);
+  memcpy(o + 4 * lq, z->zk.delta_g1.l, 2 * lq * 8);
+  memcpy(o + 6 * lq, z->zk.beta_g2.l, 4 * lq * 8);
+  memcpy(o + 10 * lq, z->zk.delta_g2.l, 4 * lq * 8);
+  return 0;
+}
+// Witness::from_reader (witness.rs:51-92): values -> Montgomery limbs (the conversion runs on the zkey's device).
+// out: NULL (only count) or n_values x 32 bytes.
+extern "C" int cohost_wtns_load_file(cohost_zkey* z, const char* path, void* out, size_t* n_values) {
+  if (!z || !path || !n_values) return fail("cohost_wtns_load_file: null argument");
+  return guarded([&] {
+    std::vector<uint8_t> buf = read_file(path);
+    WitnessFile w(buf.data(), buf.size());
+    if (w.curve != z->zk.curve) throw Error("wtns: wrong scalar field");
+    *n_values = w.n;
+    if (!out || w.n == 0) return;
+    cocg_ctx* c = z->zk.owner;
+    void* d = nullptr;
+    check(c, cocg_malloc(c, w.n * 32, &d), "cocg_malloc");
+    check(c, cocg_h2d(c, d, w.values, w.n * 32), "cocg_h2d");
+    check(c, cocg_vec_op(c, COCG_OP_TO_MONT, d, nullptr, d, w.n), "cocg_vec_op");
+    check(c, cocg_d2h(c, out, d, w.n * 32), "cocg_d2h");
+    check(c, cocg_free(c, d), "cocg_free");
+  });
 }

@@ -22,7 +22,8 @@ HOST_SYMBOLS = [
     "cohost_rep3_prove_begin", "cohost_rep3_partial_bytes", "cohost_rep3_prove_partials", "cohost_rep3_prove_combine",
     "cohost_rep3_prove_end", "cohost_rep3_launch_count", "cohost_rep3_prove_begin_device", "cohost_rep3_profile_enable",
     "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range", "cohost_shamir_session_create",
-    "cohost_shamir_session_destroy", "cohost_shamir_prove",
+    "cohost_shamir_session_destroy", "cohost_shamir_prove", "cohost_zkey_load", "cohost_zkey_load_file", "cohost_zkey_get_info",
+    "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -34,7 +35,11 @@ class ZKeyDesc(ctypes.Structure):
                 ("a_rowptr", vp), ("a_col", vp), ("a_coeff", vp), ("a_nnz", sz),
                 ("b_rowptr", vp), ("b_col", vp), ("b_coeff", vp), ("b_nnz", sz),
                 ("a_query", vp), ("b_g1_query", vp), ("b_g2_query", vp), ("h_query", vp), ("l_query", vp),
-                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp)]
+                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp), ("coeff_form", ci)]
+
+
+class ZKeyInfo(ctypes.Structure):
+    _fields_ = [("curve", ci), ("n_public", sz), ("n_vars", sz), ("pow", sz), ("num_constraints", sz)]
 
 
 class Rep3Randomness(ctypes.Structure):
@@ -76,6 +81,13 @@ def load_host():
     L.cohost_rep3_prove_end.argtypes = [vp, vp, pvp, pvp]
     L.cohost_rep3_launch_count.argtypes = [vp]
     L.cohost_rep3_launch_count.restype = u64
+    L.cohost_zkey_load.argtypes = [vp, sz, ci, pvp]
+    L.cohost_zkey_load_file.argtypes = [ctypes.c_char_p, ci, pvp]
+    L.cohost_zkey_get_info.argtypes = [vp, ctypes.POINTER(ZKeyInfo)]
+    L.cohost_zkey_query_download.argtypes = [vp, ci, sz, sz, vp]
+    L.cohost_zkey_matrix_download.argtypes = [vp, ci, vp, vp, vp, ctypes.POINTER(sz)]
+    L.cohost_zkey_vk_download.argtypes = [vp, vp]
+    L.cohost_wtns_load_file.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(sz)]
     L.cohost_shamir_session_create.argtypes = [vp, ci, ci, vp, pvp]
     L.cohost_shamir_session_destroy.argtypes = [vp]
     L.cohost_shamir_session_destroy.restype = None
@@ -135,6 +147,54 @@ class Groth16ZKey:
         h = vp()
         _ck(L.cohost_zkey_create(ctypes.byref(d), ctypes.byref(h)))
         self.h = h
+
+    @classmethod
+    def from_file(cls, path: str, device: int = 0) -> "Groth16ZKey":
+        """ZKey::from_reader: parse a snarkjs Groth16 .zkey in the C++ host layer and make it resident in HBM."""
+        L = load_host()
+        h = vp()
+        _ck(L.cohost_zkey_load_file(path.encode(), device, ctypes.byref(h)))
+        self = cls.__new__(cls)
+        self.h = h
+        info = ZKeyInfo()
+        _ck(L.cohost_zkey_get_info(h, ctypes.byref(info)))
+        self.curve, self.lq = info.curve, (4 if info.curve == _lib.BN254 else 6)
+        self.n_public, self.n_vars, self.pow, self.num_constraints = info.n_public, info.n_vars, info.pow, info.num_constraints
+        self.n_aux = self.n_vars - self.n_public - 1
+        return self
+
+    QUERIES = {"a_query": (0, 1), "b_g1_query": (1, 1), "b_g2_query": (2, 2), "h_query": (3, 1), "l_query": (4, 1)}
+
+    def query(self, name: str) -> np.ndarray:
+        which, group = self.QUERIES[name]
+        n = {"h_query": 1 << self.pow, "l_query": self.n_aux}.get(name, self.n_vars)
+        out = np.zeros((n, 2 * group * self.lq), dtype=np.uint64)
+        _ck(load_host().cohost_zkey_query_download(self.h, which, 0, n, out.ctypes.data))
+        return out
+
+    def matrix(self, which: int):
+        nnz = sz()
+        _ck(load_host().cohost_zkey_matrix_download(self.h, which, None, None, None, ctypes.byref(nnz)))
+        rowptr = np.zeros(self.num_constraints + 1, dtype=np.uint32)
+        col = np.zeros(nnz.value, dtype=np.uint32)
+        coeff = np.zeros((nnz.value, 4), dtype=np.uint64)
+        _ck(load_host().cohost_zkey_matrix_download(self.h, which, rowptr.ctypes.data, col.ctypes.data, coeff.ctypes.data, ctypes.byref(nnz)))
+        return rowptr, col, coeff
+
+    def vk(self) -> dict:
+        lq = self.lq
+        out = np.zeros(14 * lq, dtype=np.uint64)
+        _ck(load_host().cohost_zkey_vk_download(self.h, out.ctypes.data))
+        return {"alpha_g1": out[:2 * lq], "beta_g1": out[2 * lq:4 * lq], "delta_g1": out[4 * lq:6 * lq], "beta_g2": out[6 * lq:10 * lq],
+                "delta_g2": out[10 * lq:14 * lq]}
+
+    def load_witness(self, path: str) -> np.ndarray:
+        """Witness::from_reader: .wtns values as (n, 4) Montgomery limbs."""
+        n = sz()
+        _ck(load_host().cohost_wtns_load_file(self.h, path.encode(), None, ctypes.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.uint64)
+        _ck(load_host().cohost_wtns_load_file(self.h, path.encode(), out.ctypes.data, ctypes.byref(n)))
+        return out
 
     def close(self):
         if self.h:

@@ -149,6 +149,13 @@ COCG_API int cocg_msm_host(cocg_ctx* ctx, uint64_t bases, size_t off, size_t n, 
  * plain.rs:243-251).  Matrix: rowptr[rows+1], col[nnz] (u32), coeff[nnz] (Montgomery Fr); uploaded once. */
 COCG_API int cocg_csr_upload(cocg_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const void* coeff, size_t rows,
                     size_t nnz, uint64_t* handle);
+/* Same with the coefficients in another stored form: COCG_FORM_R2 = value * R^2, as section 4 of a snarkjs zkey holds them
+ * (circom-types/src/groth16/zkey.rs:181-194, traits.rs:65-67); COCG_FORM_CANONICAL = plain integers.  Converted on the device. */
+enum { COCG_FORM_MONT = 0, COCG_FORM_R2 = 1, COCG_FORM_CANONICAL = 2 };
+COCG_API int cocg_csr_upload_form(cocg_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const void* coeff, size_t rows, size_t nnz,
+                         int coeff_form, uint64_t* handle);
+/* Copy a resident matrix back to the HOST (any of rowptr / col / coeff may be NULL; *nnz is set when nnz != NULL). */
+COCG_API int cocg_csr_download(cocg_ctx* ctx, uint64_t handle, uint32_t* rowptr, uint32_t* col, void* coeff, size_t* nnz);
 COCG_API int cocg_csr_free(cocg_ctx* ctx, uint64_t handle);
 COCG_API int cocg_csr_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handle, uint64_t* handle);
 /* out[r] = sum_k coeff[k] * z[col[k]]; z = public inputs followed by the witness share, given as two DEVICE

@@ -44,7 +44,13 @@ typedef struct cohost_zkey_desc {
   /* NULL, or 32 bytes: every query / vk pointer above that is NULL is filled with synthetic curve points generated in HBM
    * (cocg_bases_generate) -- the shape-faithful 2^20-constraint benchmark key, for which no zkey ships. */
   const void* synthetic_seed;
+  int coeff_form;            /* COCG_FORM_MONT (0, default) | COCG_FORM_R2 (as stored in a zkey) | COCG_FORM_CANONICAL */
 } cohost_zkey_desc;
+
+typedef struct cohost_zkey_info {
+  int curve;
+  size_t n_public, n_vars, pow, num_constraints;
+} cohost_zkey_info;
 
 /* Injected randomness for parity tests (the reference draws all of it from entropy). */
 typedef struct cohost_rep3_randomness {
@@ -59,6 +65,18 @@ typedef struct cohost_rep3_randomness {
 COHOST_API const char* cohost_last_error(void);
 COHOST_API int cohost_zkey_create(const cohost_zkey_desc* desc, cohost_zkey** out);
 COHOST_API void cohost_zkey_destroy(cohost_zkey* z);
+/* snarkjs files straight into the device layout (circom-types/src/groth16/zkey.rs:109-251, binfile.rs:52-105, witness.rs:51-92). */
+COHOST_API int cohost_zkey_load(const void* data, size_t len, int device, cohost_zkey** out);
+COHOST_API int cohost_zkey_load_file(const char* path, int device, cohost_zkey** out);
+COHOST_API int cohost_zkey_get_info(cohost_zkey* z, cohost_zkey_info* info);
+/* which: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query -> n packed affine Montgomery points from `off` */
+COHOST_API int cohost_zkey_query_download(cohost_zkey* z, int which, size_t off, size_t n, void* out);
+/* which: 0 A, 1 B; rowptr / col / coeff may be NULL; *nnz is always set */
+COHOST_API int cohost_zkey_matrix_download(cohost_zkey* z, int which, uint32_t* rowptr, uint32_t* col, void* coeff, size_t* nnz);
+/* alpha_g1 | beta_g1 | delta_g1 | beta_g2 | delta_g2, packed affine */
+COHOST_API int cohost_zkey_vk_download(cohost_zkey* z, void* out);
+/* .wtns values as Montgomery limbs; out may be NULL to query the count */
+COHOST_API int cohost_wtns_load_file(cohost_zkey* z, const char* path, void* out, size_t* n_values);
 
 /* CoGroth16<PlainDriver>::prove.  public_inputs: l + 1 Fr (leading 1); witness: m - l - 1 Fr; r, s: one Fr each or NULL
  * (PRF); proof_out: A | B | C packed affine; h_out: NULL or 2^pow Fr. */

@@ -361,3 +361,31 @@ def test_msm_multi_shares_one_sort(cocg, bn):
             assert same_point(c, group, out[j], cref.msm(c, group, pts[off:off + n_aux], s))
     for h in hs:
         bn.bases_free(h)
+
+
+def test_bls12_381_full_size_properties(cocg, bls):
+    """BLS12-381 at the size of BASELINE config 5's shards (2^20 terms per GPU at 2^22 over 4+ GPUs): MSM linearity on generated
+    bases, a prefix against the oracle, and an NTT round trip at 2^22."""
+    c = BLS12_381
+    n = 1 << 20
+    h = bls.bases_generate(1, n, bytes([7] * 32))
+    a, b = rand_fr(n, 81), rand_fr(n, 82)
+    da, db = bls.upload(a), bls.upload(b)
+    ds = bls.vec_op(cocg.OP_ADD, da, db)
+    out = bls.msm(h, [da, db, ds])
+    assert same_point(c, 1, bls.ec_op(1, cocg.EC_ADD, out[0], out[1]), out[2])
+    m = 5000
+    pts = bls.bases_download(h, 0, m)
+    assert same_point(c, 1, bls.msm(h, [bls.upload(a[:m])], n=m)[0], cref.msm(c, 1, pts, a[:m]))
+    for v in (da, db, ds):
+        v.free()
+    bls.bases_free(h)
+    logn = 22
+    omega, _ = ontt.groth16_roots(c, logn)
+    om = cref.fr_to_mont(c, [omega])
+    x = rand_fr(1 << logn, 83)
+    dx = bls.upload(x)
+    bls.ntt([dx], logn, om)
+    bls.ntt([dx], logn, om, inverse=True)
+    assert np.array_equal(dx.to_host(), x)
+    dx.free()
