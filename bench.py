@@ -216,7 +216,7 @@ def run_own(args):
     n_aux = n_vars - n_public - 1
     seed_bytes = SEED.to_bytes(8, "little") * 4
     t_setup = time.perf_counter()
-    zk = cocg.Groth16ZKey(cocg.BN254, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes)
+    zk = cocg.Groth16ZKey(cocg.BN254, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes, rank=rank, world=world)
     sess = cocg.Rep3Session(zk, rank=rank, world=world)
     # witness: x = x0 + x1 + x2, party i holds (x_i, x_{i-1}) (rep3.rs:57-68); pinned host copies + resident device copies
     xs = []

@@ -24,7 +24,7 @@ SYMBOLS = [
     "cocg_msm", "cocg_msm_host", "cocg_csr_upload", "cocg_csr_free", "cocg_spmv", "cocg_ec_op",
     "cocg_d2d", "cocg_host_alloc", "cocg_host_free", "cocg_rep3_mul_local_prf", "cocg_prf_fill", "cocg_prf_field_host",
     "cocg_bases_share", "cocg_csr_share", "cocg_bases_generate", "cocg_bases_download", "cocg_profile_enable",
-    "cocg_profile_read", "cocg_profile_reset", "cocg_msm_multi", "cocg_vec_axpy", "cocg_csr_upload_form", "cocg_csr_download",
+    "cocg_profile_read", "cocg_profile_reset", "cocg_msm_multi", "cocg_vec_axpy", "cocg_csr_upload_form", "cocg_csr_download", "cocg_bases_generate_range",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def load():
         "cocg_bases_share": (ci, [vp, vp, u64, ctypes.POINTER(u64)]),
         "cocg_csr_share": (ci, [vp, vp, u64, ctypes.POINTER(u64)]),
         "cocg_bases_generate": (ci, [vp, ci, sz, vp, ctypes.POINTER(u64)]),
+        "cocg_bases_generate_range": (ci, [vp, ci, sz, sz, vp, ctypes.POINTER(u64)]),
         "cocg_bases_download": (ci, [vp, u64, sz, sz, vp]),
         "cocg_profile_enable": (ci, [vp, ci]),
         "cocg_profile_read": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),

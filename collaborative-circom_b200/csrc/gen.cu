@@ -17,15 +17,15 @@ int msm_precompute(cocg_ctx* ctx, BasesEntry& be);
 constexpr int kGenRun = 16;
 
 template <class F>
-__global__ void __launch_bounds__(128) bases_generate_kernel(Affine<F> p0, Affine<F> q, size_t n, Affine<F>* __restrict__ out) {
+__global__ void __launch_bounds__(128) bases_generate_kernel(Affine<F> p0, Affine<F> q, size_t first, size_t n, Affine<F>* __restrict__ out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t lo = t * kGenRun;
   if (lo >= n) return;
-  // start = p0 + lo*q
+  // start = p0 + (first + lo)*q
   XYZZ<F> step = xyzz_from_affine(q), acc = xyzz_from_affine(p0);
   {
     XYZZ<F> m = xyzz_inf<F>();
-    uint64_t k = lo;
+    uint64_t k = first + lo;
     for (int b = 63 - __clzll(k | 1); b >= 0; b--) {
       m = xyzz_dbl(m);
       if ((k >> b) & 1) xyzz_add(m, step);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) bases_generate_kernel(Affine<F> p0, Affin
 }
 
 template <class F>
-static int generate_impl(cocg_ctx* ctx, int group, size_t n, const uint8_t seed[32], void* d) {
+static int generate_impl(cocg_ctx* ctx, int group, size_t first, size_t n, const uint8_t seed[32], void* d) {
   // P0 = k0*G, Q = k1*G with k0, k1 from the field PRF; computed on the host with the O(1) group operations
   uint64_t gen[36], p0j[36], qj[36], aff[24];
   uint32_t k0[8], k1[8];
@@ -75,7 +75,7 @@ static int generate_impl(cocg_ctx* ctx, int group, size_t n, const uint8_t seed[
   COCG_TRY(cocg_ec_op(ctx, group, 2, qj, nullptr, aff));
   memcpy(&q, aff, sizeof(q));
   size_t threads = (n + kGenRun - 1) / kGenRun;
-  bases_generate_kernel<F><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(p0, q, n, reinterpret_cast<Affine<F>*>(d));
+  bases_generate_kernel<F><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(p0, q, first, n, reinterpret_cast<Affine<F>*>(d));
   COCG_LAUNCH_CHECK(ctx);
   COCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -86,6 +86,10 @@ static int generate_impl(cocg_ctx* ctx, int group, size_t n, const uint8_t seed[
 using namespace cocg;
 
 extern "C" int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const void* seed, uint64_t* handle) {
+  return cocg_bases_generate_range(ctx, group, 0, n, seed, handle);
+}
+
+extern "C" int cocg_bases_generate_range(cocg_ctx* ctx, int group, size_t first, size_t n, const void* seed, uint64_t* handle) {
   if (!ctx) return 1;
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (group != COCG_G1 && group != COCG_G2) return fail(ctx, "cocg_bases_generate: group must be 1 or 2");
@@ -98,8 +102,8 @@ extern "C" int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const voi
   if (n) {
     int rc;
     const uint8_t* sd = (const uint8_t*)seed;
-    if (ctx->curve == COCG_BN254) rc = group == COCG_G1 ? generate_impl<Bn254Fq>(ctx, group, n, sd, be.d) : generate_impl<Bn254Fq2>(ctx, group, n, sd, be.d);
-    else rc = group == COCG_G1 ? generate_impl<Bls381Fq>(ctx, group, n, sd, be.d) : generate_impl<Bls381Fq2>(ctx, group, n, sd, be.d);
+    if (ctx->curve == COCG_BN254) rc = group == COCG_G1 ? generate_impl<Bn254Fq>(ctx, group, first, n, sd, be.d) : generate_impl<Bn254Fq2>(ctx, group, first, n, sd, be.d);
+    else rc = group == COCG_G1 ? generate_impl<Bls381Fq>(ctx, group, first, n, sd, be.d) : generate_impl<Bls381Fq2>(ctx, group, first, n, sd, be.d);
     if (rc) { cudaFree(be.d); return rc; }
   }
   COCG_TRY(msm_precompute(ctx, be));

@@ -91,44 +91,68 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
     const size_t m = zk.n_vars, l = zk.n_public;
     const size_t g1b = 2 * lq * 8, g2b = 4 * lq * 8;
     cocg_ctx* c = zk.owner;
-    // a query is uploaded from the caller's array, or generated in HBM when the pointer is NULL and a seed is given
-    auto bases = [&](int group, const void* pts, size_t n, int salt, uint64_t* handle, const char* what) {
+    // a query is uploaded from the caller's array, or generated in HBM when the pointer is NULL and a seed is given; with
+    // world > 1 only this rank's slice [first, first + n) becomes resident (its window table is sized for the slice)
+    auto bases = [&](int group, const void* pts, size_t first, size_t n, int salt, uint64_t* handle, const char* what) {
+      const size_t pb = group == COCG_G1 ? g1b : g2b;
       if (pts) {
-        check(c, cocg_bases_upload(c, group, pts, n, group == COCG_G1 ? g1b : g2b, 1, handle), what);
+        check(c, cocg_bases_upload(c, group, (const char*)pts + first * pb, n, pb, 1, handle), what);
       } else {
         if (!d->synthetic_seed) throw Error(std::string("zkey: ") + what + " is NULL and no synthetic_seed was given");
         uint8_t sd[32];
         memcpy(sd, d->synthetic_seed, 32);
         sd[31] ^= (uint8_t)salt;
-        check(c, cocg_bases_generate(c, group, n, sd, handle), what);
+        check(c, cocg_bases_generate_range(c, group, first, n, sd, handle), what);
       }
     };
-    bases(COCG_G1, d->a_query, m, 1, &zk.a_query, "a_query");
-    bases(COCG_G1, d->b_g1_query, m, 2, &zk.b_g1_query, "b_g1_query");
-    bases(COCG_G2, d->b_g2_query, m, 3, &zk.b_g2_query, "b_g2_query");
-    bases(COCG_G1, d->h_query, zk.domain_size(), 4, &zk.h_query, "h_query");
-    bases(COCG_G1, d->l_query, zk.n_aux(), 5, &zk.l_query, "l_query");
+    zk.rank = d->world > 1 ? d->rank : 0;
+    zk.world = d->world > 1 ? d->world : 1;
+    if (zk.rank < 0 || zk.rank >= zk.world) throw Error("zkey: bad rank / world");
+    size_t len_h = zk.domain_size(), len_x = zk.n_aux();
+    if (zk.world > 1) {
+      MsmShard sh;
+      sh.rank = zk.rank;
+      sh.world = zk.world;
+      size_t off_x;
+      sh.range(zk.domain_size(), zk.h_first, len_h);
+      sh.range(zk.n_aux(), off_x, len_x);
+      zk.l_first = off_x;
+      zk.a_first = zk.b_g1_first = zk.b_g2_first = 1 + l + off_x;
+    }
+    const size_t len_q = zk.world > 1 ? len_x : m;  // a / b queries: whole (heads included) or the aux slice
+    bases(COCG_G1, d->a_query, zk.a_first, len_q, 1, &zk.a_query, "a_query");
+    bases(COCG_G1, d->b_g1_query, zk.b_g1_first, len_q, 2, &zk.b_g1_query, "b_g1_query");
+    bases(COCG_G2, d->b_g2_query, zk.b_g2_first, len_q, 3, &zk.b_g2_query, "b_g2_query");
+    bases(COCG_G1, d->h_query, zk.h_first, len_h, 4, &zk.h_query, "h_query");
+    bases(COCG_G1, d->l_query, zk.l_first, len_x, 5, &zk.l_query, "l_query");
     check(c, cocg_csr_upload_form(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, d->coeff_form, &zk.csr_a), "csr_a");
     check(c, cocg_csr_upload_form(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, d->coeff_form, &zk.csr_b), "csr_b");
     zk.a_head.resize(l + 1);
     zk.b_g1_head.resize(l + 1);
     zk.b_g2_head.resize(l + 1);
-    {
+    {  // the first 1 + l points of the coefficient queries, host copies (from the array, or a tiny generated prefix)
       std::vector<uint64_t> buf((l + 1) * 4 * lq);
-      auto heads = [&](uint64_t handle, size_t limbs, std::vector<Point>& dst, const char* what) {
-        check(c, cocg_bases_download(c, handle, 0, l + 1, buf.data()), what);
+      auto heads = [&](int group, const void* pts, int salt, size_t limbs, std::vector<Point>& dst, const char* what) {
+        if (pts) {
+          memcpy(buf.data(), pts, (l + 1) * limbs * 8);
+        } else {
+          uint64_t hh = 0;
+          bases(group, nullptr, 0, l + 1, salt, &hh, what);
+          check(c, cocg_bases_download(c, hh, 0, l + 1, buf.data()), what);
+          cocg_bases_free(c, hh);
+        }
         for (size_t i = 0; i <= l; i++) dst[i] = load_point(buf.data() + i * limbs, limbs);
       };
-      heads(zk.a_query, 2 * lq, zk.a_head, "a_query head");
-      heads(zk.b_g1_query, 2 * lq, zk.b_g1_head, "b_g1_query head");
-      heads(zk.b_g2_query, 4 * lq, zk.b_g2_head, "b_g2_query head");
+      heads(COCG_G1, d->a_query, 1, 2 * lq, zk.a_head, "a_query head");
+      heads(COCG_G1, d->b_g1_query, 2, 2 * lq, zk.b_g1_head, "b_g1_query head");
+      heads(COCG_G2, d->b_g2_query, 3, 4 * lq, zk.b_g2_head, "b_g2_query head");
     }
     // vk points: given, or three G1 / two G2 synthetic points
     uint64_t vk1[3][12], vk2[2][24];
     if (!d->alpha_g1 || !d->beta_g1 || !d->delta_g1 || !d->beta_g2 || !d->delta_g2) {
       uint64_t h1 = 0, h2 = 0;
-      bases(COCG_G1, nullptr, 3, 6, &h1, "vk g1");
-      bases(COCG_G2, nullptr, 2, 7, &h2, "vk g2");
+      bases(COCG_G1, nullptr, 0, 3, 6, &h1, "vk g1");
+      bases(COCG_G2, nullptr, 0, 2, 7, &h2, "vk g2");
       std::vector<uint64_t> b1(3 * 2 * lq), b2(2 * 4 * lq);
       check(c, cocg_bases_download(c, h1, 0, 3, b1.data()), "vk g1");
       check(c, cocg_bases_download(c, h2, 0, 2, b2.data()), "vk g2");
@@ -216,6 +240,7 @@ extern "C" int cohost_plain_prove(cohost_plain_session* s, const void* public_in
 extern "C" int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds /* 3 x 32 */, int rank, int world, cohost_rep3_session** out) {
   if (!z || !out || !seeds) return fail("cohost_rep3_session_create: null argument");
   if (world < 1 || rank < 0 || rank >= world) return fail("cohost_rep3_session_create: bad rank/world");
+  if (z->zk.world != 1 && (z->zk.world != world || z->zk.rank != rank)) return fail("cohost_rep3_session_create: the zkey holds another rank's shard");
   return guarded([&] {
     std::unique_ptr<cohost_rep3_session> s(new cohost_rep3_session());
     s->zkey = z;
@@ -594,6 +619,7 @@ extern "C" int cohost_zkey_query_download(cohost_zkey* z, int which, size_t off,
   if (!z || !out) return fail("cohost_zkey_query_download: null argument");
   const uint64_t h[5] = {z->zk.a_query, z->zk.b_g1_query, z->zk.b_g2_query, z->zk.h_query, z->zk.l_query};
   if (which < 0 || which > 4) return fail("cohost_zkey_query_download: unknown query");
+  if (z->zk.world != 1) return fail("cohost_zkey_query_download: only this rank's shard of the queries is resident");
   if (cocg_bases_download(z->zk.owner, h[which], off, n, out)) return fail(cocg_last_error(z->zk.owner));
   return 0;
 }

@@ -174,12 +174,14 @@ class CoGroth16 {
     // ---- all secret-scalar MSMs first (msm_public_points at groth16.rs:248, 251-255 and inside calculate_coeff :221-225)
     MsmPartials m;
     size_t off, len;
+    if (zkey.world != 1 && (zkey.world != shard.world || zkey.rank != shard.rank)) throw Error("the zkey holds another rank's shard of the queries");
     shard.range(std::min(h.len(), zkey.domain_size()), off, len);
-    m.h_acc = driver.msm_public_points(1, hd.h_query, off, len, h, off);
+    m.h_acc = driver.msm_public_points(1, hd.h_query, off - zkey.h_first, len, h, off);
     shard.range(n_aux, off, len);
     {  // the four queries multiplied by aux_assignment share one digit sort per share component
-      std::vector<PointShare> r = driver.msm_public_points_multi({1, 1, 1, 2}, {hd.l_query, hd.a_query, hd.b_g1_query, hd.b_g2_query},
-                                                                 {off, 1 + l + off, 1 + l + off, 1 + l + off}, len, aux_assignment, off);
+      std::vector<PointShare> r = driver.msm_public_points_multi(
+          {1, 1, 1, 2}, {hd.l_query, hd.a_query, hd.b_g1_query, hd.b_g2_query},
+          {off - zkey.l_first, 1 + l + off - zkey.a_first, 1 + l + off - zkey.b_g1_first, 1 + l + off - zkey.b_g2_first}, len, aux_assignment, off);
       m.l_acc = r[0];
       m.a_acc = r[1];
       m.b1_acc = r[2];

@@ -77,6 +77,10 @@ struct ZKey {
   size_t num_inputs() const { return n_public + 1; }  // matrices.num_instance_variables
   size_t n_aux() const { return n_vars - n_public - 1; }
   uint64_t a_query = 0, b_g1_query = 0, b_g2_query = 0, h_query = 0, l_query = 0;  // handles in `owner`
+  // Multi-GPU: a rank may hold only the slice of each query it accumulates (index-range sharding); `*_first` is
+  // the index, in the full query, of the resident table's entry 0 (0 when the whole query is resident).
+  int rank = 0, world = 1;
+  size_t a_first = 0, b_g1_first = 0, b_g2_first = 0, h_first = 0, l_first = 0;
   uint64_t csr_a = 0, csr_b = 0;
   // the first 1 + l points of each coefficient query stay on the host as well (calculate_coeff groth16.rs:219-231)
   std::vector<Point> a_head, b_g1_head, b_g2_head;  // packed affine

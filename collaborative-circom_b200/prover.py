@@ -35,7 +35,7 @@ class ZKeyDesc(ctypes.Structure):
                 ("a_rowptr", vp), ("a_col", vp), ("a_coeff", vp), ("a_nnz", sz),
                 ("b_rowptr", vp), ("b_col", vp), ("b_coeff", vp), ("b_nnz", sz),
                 ("a_query", vp), ("b_g1_query", vp), ("b_g2_query", vp), ("h_query", vp), ("l_query", vp),
-                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp), ("coeff_form", ci)]
+                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp), ("rank", ci), ("world", ci), ("coeff_form", ci)]
 
 
 class ZKeyInfo(ctypes.Structure):
@@ -111,8 +111,10 @@ class Groth16ZKey:
 
     def __init__(self, curve: int, n_public: int, n_vars: int, pow_: int, num_constraints: int, a_csr, b_csr,
                  a_query=None, b_g1_query=None, b_g2_query=None, h_query=None, l_query=None, alpha_g1=None, beta_g1=None,
-                 delta_g1=None, beta_g2=None, delta_g2=None, device: int = 0, synthetic_seed: bytes | None = None):
-        """Query / vk arrays left as None are generated in HBM from `synthetic_seed` (32 bytes)."""
+                 delta_g1=None, beta_g2=None, delta_g2=None, device: int = 0, synthetic_seed: bytes | None = None, rank: int = 0,
+                 world: int = 1):
+        """Query / vk arrays left as None are generated in HBM from `synthetic_seed` (32 bytes).  world > 1: only rank's
+        index-range shard of every query becomes resident (host arrays are still passed whole)."""
         L = load_host()
         self.curve, self.lq = curve, (4 if curve == _lib.BN254 else 6)
         self.n_public, self.n_vars, self.pow, self.num_constraints = n_public, n_vars, pow_, num_constraints
@@ -126,6 +128,7 @@ class Groth16ZKey:
 
         d = ZKeyDesc()
         d.curve, d.device, d.n_public, d.n_vars, d.pow, d.num_constraints = curve, device, n_public, n_vars, pow_, num_constraints
+        d.rank, d.world = rank, world
         d.a_rowptr, d.a_col, d.a_coeff, d.a_nnz = P(a_csr[0], np.uint32), P(a_csr[1], np.uint32), P(a_csr[2]), len(a_csr[1])
         d.b_rowptr, d.b_col, d.b_coeff, d.b_nnz = P(b_csr[0], np.uint32), P(b_csr[1], np.uint32), P(b_csr[2]), len(b_csr[1])
         assert len(a_csr[0]) == num_constraints + 1 and len(b_csr[0]) == num_constraints + 1

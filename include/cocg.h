@@ -124,6 +124,8 @@ COCG_API int cocg_bases_free(cocg_ctx* ctx, uint64_t handle);
 /* Synthetic bases generated in HBM: P0 + i*Q for two points derived from `seed` (HOST pointer, 32 bytes) -- valid, distinct
  * curve points for the 2^20..2^22 benchmark configurations, for which no zkey ships (csrc/gen.cu). */
 COCG_API int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const void* seed, uint64_t* handle);
+/* The slice [first, first + n) of the same sequence: a rank of a multi-GPU run generates only the shard it accumulates. */
+COCG_API int cocg_bases_generate_range(cocg_ctx* ctx, int group, size_t first, size_t n, const void* seed, uint64_t* handle);
 /* Copy n packed affine points starting at `off` back to the HOST. */
 COCG_API int cocg_bases_download(cocg_ctx* ctx, uint64_t handle, size_t off, size_t n, void* out);
 /* Non-owning alias of another context's bases on the same device: the three REP3 drivers of one process borrow the

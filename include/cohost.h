@@ -44,6 +44,7 @@ typedef struct cohost_zkey_desc {
   /* NULL, or 32 bytes: every query / vk pointer above that is NULL is filled with synthetic curve points generated in HBM
    * (cocg_bases_generate) -- the shape-faithful 2^20-constraint benchmark key, for which no zkey ships. */
   const void* synthetic_seed;
+  int rank, world;           /* world > 1: only this rank's index-range shard of every query becomes resident */
   int coeff_form;            /* COCG_FORM_MONT (0, default) | COCG_FORM_R2 (as stored in a zkey) | COCG_FORM_CANONICAL */
 } cohost_zkey_desc;
 
