@@ -87,6 +87,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (msm_accumulate_kernel, weighted 4 G1 : 1 G2
+    like the launches of one share component) from the committed `ncu --set full` capture summary, single-GPU shape only."""
+    p = os.path.join(ROOT, "profiles", "r01_msm_accumulate_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    if t.get("g2_bytes_per_launch") is None:
+        return t["g1_bytes_per_launch"]  # only the G1 instantiation was captured
+    return (4 * t["g1_bytes_per_launch"] + t["g2_bytes_per_launch"]) / 5
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -306,7 +318,7 @@ def run_own(args):
                     "note": "witness shares in pinned host memory uploaded every step, proofs read back; both legs also move the two mul_vec "
                             "rounds (n x 32 B per party per round) over PCIe because the MPC network stays on the host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(world),
                          "kernel": "msm_accumulate_kernel (+ msm_heavy_kernel), per share-component launch, timed in situ with the three "
                                    "parties' streams running concurrently", "peak_source": peak_src,
                          "note": "MSM is bound by 32-bit integer multiply-add issue, not HBM (DESIGN.md)"},

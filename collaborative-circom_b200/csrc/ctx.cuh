@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <array>
+#include <deque>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,7 +54,7 @@ struct cocg_ctx {
   // per-kernel-class device timing (cocg_profile_*): event pairs recorded on the launching stream
   bool profile = false;
   struct ProfPair { cudaEvent_t a, b; int cls; };
-  std::vector<ProfPair> prof_pending;
+  std::deque<ProfPair> prof_pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
   double prof_ms[COCG_PROF_CLASSES] = {};
   uint64_t prof_count[COCG_PROF_CLASSES] = {};
@@ -86,6 +87,18 @@ struct ProfScope {
   cudaEvent_t stop = nullptr;
   ProfScope(cocg_ctx* ctx, int cls) : c(ctx) {
     if (!c->profile) return;
+    // recycle finished pairs instead of creating events on the hot path (cudaEventCreate costs ~10 us)
+    while (c->prof_free.empty() && !c->prof_pending.empty()) {
+      if (cudaEventQuery(c->prof_pending.front().b) != cudaSuccess) {
+        (void)cudaGetLastError();  // cudaErrorNotReady is not an error; do not leave it for the next launch check
+        break;
+      }
+      auto pr = c->prof_pending.front();
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, pr.a, pr.b) == cudaSuccess) { c->prof_ms[pr.cls] += ms; c->prof_count[pr.cls]++; }
+      c->prof_free.push_back({pr.a, pr.b});
+      c->prof_pending.pop_front();
+    }
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->prof_free.empty()) { ev = c->prof_free.back(); c->prof_free.pop_back(); }
     else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return;
