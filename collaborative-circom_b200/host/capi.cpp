@@ -661,3 +661,11 @@ extern "C" int cohost_wtns_load_file(cohost_zkey* z, const char* path, void* out
     check(c, cocg_free(c, d), "cocg_free");
   });
 }
+
+// Host wall-clock per phase of the last proof, seconds: out[party][4] = witness map | MSMs | wait for the all-gather | assembly.
+extern "C" int cohost_rep3_phase_times(cohost_rep3_session* s, double* out) {
+  if (!s || !out) return fail("cohost_rep3_phase_times: null argument");
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 4; k++) out[4 * i + k] = s->prover[i]->phase_s[k];
+  return 0;
+}

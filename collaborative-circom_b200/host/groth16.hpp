@@ -11,6 +11,7 @@
 //   * the five secret-scalar MSMs are issued before the first opening (they depend on h and the witness only), so a
 //     multi-GPU caller can combine all partial sums with ONE all-gather per proof (`MsmCombine`).
 #pragma once
+#include <chrono>
 #include <functional>
 
 #include "driver.hpp"
@@ -102,6 +103,10 @@ class CoGroth16 {
   MsmCombine combine;
   FieldShareVec last_h;  // kept for parity tests (released by the next prove)
   FieldShare last_r, last_s;
+  // host wall-clock of the last prove per phase, seconds (the reference logs "Proof generation took {} ms", co-circom.rs:503-506;
+  // here split so that multi-GPU scaling can be read): witness map | MSMs incl. their syncs | wait for the all-gather | assembly
+  double phase_s[4] = {0, 0, 0, 0};
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
   // bases/CSR handles of `zkey` valid in driver.ctx (aliases made by the session)
   struct Handles {
@@ -112,7 +117,10 @@ class CoGroth16 {
   Groth16Proof prove(const ZKey& zkey, const Handles& hd, const DevVec& public_inputs, const std::vector<Fr>& public_inputs_host,
                      const FieldShareVec& private_witness) {
     driver.release(last_h);
+    const double t0 = now();
     FieldShareVec h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
+    check(driver.ctx, cocg_sync(driver.ctx), "cocg_sync");
+    phase_s[0] = now() - t0;
     FieldShare r = driver.rand();
     FieldShare s = driver.rand();
     last_r = r;
@@ -169,6 +177,7 @@ class CoGroth16 {
 
   Groth16Proof create_proof_with_assignment(const ZKey& zkey, const Handles& hd, const FieldShare& r, const FieldShare& s, const FieldShareVec& h,
                                             const std::vector<Fr>& public_inputs_host, const FieldShareVec& aux_assignment) {
+    const double t_start = now();
     std::vector<Fr> input_assignment(public_inputs_host.begin() + 1, public_inputs_host.end());
     const size_t l = zkey.n_public, n_aux = zkey.n_aux();
     // ---- all secret-scalar MSMs first (msm_public_points at groth16.rs:248, 251-255 and inside calculate_coeff :221-225)
@@ -187,7 +196,11 @@ class CoGroth16 {
       m.b1_acc = r[2];
       m.b2_acc = r[3];
     }
+    const double t_msm = now();
+    phase_s[1] = t_msm - t_start;
     if (combine) combine(party_id(), m);
+    const double t_comb = now();
+    phase_s[2] = t_comb - t_msm;
 
     Point delta_g1 = driver.from_affine(1, zkey.delta_g1);
     FieldShare rs = driver.mul(r, s);
@@ -217,6 +230,7 @@ class CoGroth16 {
     proof.pi_a = driver.to_affine(1, g_a_opened);
     proof.pi_b = driver.to_affine(2, opened.second);
     proof.pi_c = driver.to_affine(1, opened.first);
+    phase_s[3] = now() - t_comb;
     return proof;
   }
 

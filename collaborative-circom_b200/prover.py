@@ -23,7 +23,7 @@ HOST_SYMBOLS = [
     "cohost_rep3_prove_end", "cohost_rep3_launch_count", "cohost_rep3_prove_begin_device", "cohost_rep3_profile_enable",
     "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range", "cohost_shamir_session_create",
     "cohost_shamir_session_destroy", "cohost_shamir_prove", "cohost_zkey_load", "cohost_zkey_load_file", "cohost_zkey_get_info",
-    "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file",
+    "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file", "cohost_rep3_phase_times",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -88,6 +88,7 @@ def load_host():
     L.cohost_zkey_matrix_download.argtypes = [vp, ci, vp, vp, vp, ctypes.POINTER(sz)]
     L.cohost_zkey_vk_download.argtypes = [vp, vp]
     L.cohost_wtns_load_file.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(sz)]
+    L.cohost_rep3_phase_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.cohost_shamir_session_create.argtypes = [vp, ci, ci, vp, pvp]
     L.cohost_shamir_session_destroy.argtypes = [vp]
     L.cohost_shamir_session_destroy.restype = None
@@ -327,6 +328,12 @@ class Rep3Session:
 
     def launch_count(self) -> int:
         return int(load_host().cohost_rep3_launch_count(self.h))
+
+    def phase_times(self) -> np.ndarray:
+        """(3, 4) seconds of the last proof per party: witness map | MSMs | all-gather wait | assembly."""
+        out = (ctypes.c_double * 12)()
+        _ck(load_host().cohost_rep3_phase_times(self.h, out))
+        return np.array(out).reshape(3, 4)
 
     def close(self):
         if self.h:

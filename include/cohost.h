@@ -107,6 +107,8 @@ COHOST_API int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gat
 /* proofs_out: 3 x (A | B | C); h_a / h_b: NULL or 3 HOST buffers of 2^pow Fr receiving each party's share of h. */
 COHOST_API int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, void* const* h_a, void* const* h_b);
 COHOST_API uint64_t cohost_rep3_launch_count(cohost_rep3_session* s);
+/* Host wall-clock per phase of the last proof, seconds: out[party * 4 + k], k = witness map | MSMs | all-gather wait | assembly. */
+COHOST_API int cohost_rep3_phase_times(cohost_rep3_session* s, double* out);
 /* num_parties CoGroth16<ShamirProtocol> provers (mpc-core/src/protocols/shamir.rs), threshold t with 2t + 1 <= num_parties, on
  * one thread each over an in-process network; seeds: num_parties x 32 bytes.  wit[i]: party i's HOST share vector; proofs_out:
  * num_parties x (A | B | C); rs_out: NULL or num_parties x (share of r | share of s) for tests. */
