@@ -92,6 +92,13 @@ class Context:
         self._ck(self.L.cocg_vec_op(self.h, op, a.ptr, b.ptr if b else None, out.ptr, a.n))
         return out
 
+    def vec_axpy(self, a: np.ndarray, x: DeviceVec, y: DeviceVec | None = None, out: DeviceVec | None = None) -> DeviceVec:
+        """out = a * x (+ y), a: one Montgomery Fr (4 limbs)."""
+        out = out or DeviceVec(self, x.n)
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        self._ck(self.L.cocg_vec_axpy(self.h, a.ctypes.data, x.ptr, y.ptr if y else None, out.ptr, x.n))
+        return out
+
     def rep3_mul_local(self, aa, ab, ba, bb, mask=None, out=None) -> DeviceVec:
         out = out or DeviceVec(self, aa.n)
         self._ck(self.L.cocg_rep3_mul_local(self.h, aa.ptr, ab.ptr, ba.ptr, bb.ptr, mask.ptr if mask else None, out.ptr, aa.n))
