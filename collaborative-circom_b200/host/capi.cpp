@@ -9,6 +9,7 @@
 #include "groth16.hpp"
 #include "shamir.hpp"
 #include "formats.hpp"
+#include "plonk.hpp"
 
 using namespace cohost;
 
@@ -668,4 +669,113 @@ extern "C" int cohost_rep3_phase_times(cohost_rep3_session* s, double* out) {
   for (int i = 0; i < 3; i++)
     for (int k = 0; k < 4; k++) out[4 * i + k] = s->prover[i]->phase_s[k];
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Plonk, round 1
+struct cohost_plonk_zkey {
+  PlonkZKey zk;
+  size_t lq = 4;
+};
+
+extern "C" int cohost_plonk_zkey_load_file(const char* path, int device, cohost_plonk_zkey** out) {
+  if (!path || !out) return fail("cohost_plonk_zkey_load_file: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    std::vector<uint8_t> buf = read_file(path);
+    PlonkZKeyFile f(buf.data(), buf.size());
+    std::unique_ptr<cohost_plonk_zkey> z(new cohost_plonk_zkey());
+    PlonkZKey& zk = z->zk;
+    zk.curve = f.curve;
+    zk.device = device;
+    z->lq = f.curve == COCG_BN254 ? 4 : 6;
+    zk.n_vars = f.n_vars; zk.n_public = f.n_public; zk.domain_size = f.domain_size; zk.pow = f.pow;
+    zk.n_additions = f.n_additions; zk.n_constraints = f.n_constraints;
+    zk.additions.resize(f.n_additions);
+    for (size_t i = 0; i < f.n_additions; i++) {
+      const uint8_t* e = f.additions + i * 72;
+      zk.additions[i].s1 = BinFile::u32(e);
+      zk.additions[i].s2 = BinFile::u32(e + 4);
+      memcpy(zk.additions[i].f1.l, e + 8, 32);   // already Montgomery limbs (montgomery_bigint_from_reader)
+      memcpy(zk.additions[i].f2.l, e + 40, 32);
+    }
+    auto rd_map = [&](const uint8_t* p, std::vector<uint32_t>& m) {
+      m.resize(f.n_constraints);
+      memcpy(m.data(), p, f.n_constraints * 4);
+    };
+    rd_map(f.map_a, zk.map_a);
+    rd_map(f.map_b, zk.map_b);
+    rd_map(f.map_c, zk.map_c);
+    if (cocg_create(&zk.owner, device, f.curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
+    check(zk.owner, cocg_bases_upload(zk.owner, COCG_G1, f.p_tau, f.domain_size + 6, 2 * f.n8q, 1, &zk.p_tau), "p_tau");
+    *out = z.release();
+  });
+}
+extern "C" void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z) {
+  if (!z) return;
+  if (z->zk.owner) cocg_destroy(z->zk.owner);
+  delete z;
+}
+// info[6] = curve, n_vars, n_public, domain_size, n_additions, n_constraints
+extern "C" int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info) {
+  if (!z || !info) return fail("cohost_plonk_zkey_get_info: null argument");
+  const PlonkZKey& k = z->zk;
+  const size_t v[6] = {(size_t)k.curve, k.n_vars, k.n_public, k.domain_size, k.n_additions, k.n_constraints};
+  memcpy(info, v, sizeof(v));
+  return 0;
+}
+// Round1::round1 with PlainDriver.  public_inputs: n_public + 1 Fr; witness: n_vars - n_additions - n_public - 1 Fr;
+// deterministic != 0 uses the reference's KAT blinders b_i = i (round1.rs:101-108).  commits_out: [a]_1 | [b]_1 | [c]_1 affine.
+extern "C" int cohost_plonk_round1_plain(cohost_plonk_zkey* z, const void* public_inputs, const void* witness, int deterministic, void* commits_out) {
+  if (!z || !public_inputs || !witness || !commits_out) return fail("cohost_plonk_round1_plain: null argument");
+  return guarded([&] {
+    PlainDriver d(z->zk.curve, z->zk.device);
+    uint64_t h = 0;
+    check(d.ctx, cocg_bases_share(d.ctx, z->zk.owner, z->zk.p_tau, &h), "share p_tau");
+    CoPlonkRound1<PlainDriver> r1(d);
+    Round1Proof p = r1.round1(z->zk, h, (const Fr*)public_inputs, (const Fr*)witness, nullptr, deterministic != 0);
+    uint64_t* o = (uint64_t*)commits_out;
+    memcpy(o, p.commit_a.l, 2 * z->lq * 8);
+    memcpy(o + 2 * z->lq, p.commit_b.l, 2 * z->lq * 8);
+    memcpy(o + 4 * z->lq, p.commit_c.l, 2 * z->lq * 8);
+  });
+}
+// Same with three Rep3Protocol drivers on three threads.  wit_a[i] / wit_b[i]: party i's HOST share components;
+// commits_out: 3 parties x ([a]_1 | [b]_1 | [c]_1).
+extern "C" int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                        const uint8_t* seeds, int deterministic, void* commits_out) {
+  if (!z || !public_inputs || !wit_a || !wit_b || !seeds || !commits_out) return fail("cohost_plonk_round1_rep3: null argument");
+  return guarded([&] {
+    Rep3TestNetwork net;
+    std::unique_ptr<Rep3Protocol> drv[3];
+    for (int i = 0; i < 3; i++) drv[i].reset(new Rep3Protocol(z->zk.curve, z->zk.device, net.party(i), seeds + 32 * i));
+    for (int i = 0; i < 3; i++) drv[i]->finish_setup();
+    std::thread th[3];
+    std::string errs[3];
+    Round1Proof proofs[3];
+    for (int i = 0; i < 3; i++) {
+      const void* a = wit_a[i];
+      const void* b = wit_b[i];
+      th[i] = std::thread([&, i, a, b] {
+        try {
+          uint64_t h = 0;
+          check(drv[i]->ctx, cocg_bases_share(drv[i]->ctx, z->zk.owner, z->zk.p_tau, &h), "share p_tau");
+          CoPlonkRound1<Rep3Protocol> r1(*drv[i]);
+          proofs[i] = r1.round1(z->zk, h, (const Fr*)public_inputs, (const Fr*)a, (const Fr*)b, deterministic != 0);
+        } catch (const std::exception& e) {
+          errs[i] = e.what();
+          net.close_all();
+        }
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int i = 0; i < 3; i++)
+      if (!errs[i].empty()) throw Error("party " + std::to_string(i) + ": " + errs[i]);
+    const size_t lq = z->lq;
+    for (int i = 0; i < 3; i++) {
+      uint64_t* o = (uint64_t*)commits_out + (size_t)i * 6 * lq;
+      memcpy(o, proofs[i].commit_a.l, 2 * lq * 8);
+      memcpy(o + 2 * lq, proofs[i].commit_b.l, 2 * lq * 8);
+      memcpy(o + 4 * lq, proofs[i].commit_c.l, 2 * lq * 8);
+    }
+  });
 }

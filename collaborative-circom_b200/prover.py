@@ -23,7 +23,8 @@ HOST_SYMBOLS = [
     "cohost_rep3_prove_end", "cohost_rep3_launch_count", "cohost_rep3_prove_begin_device", "cohost_rep3_profile_enable",
     "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range", "cohost_shamir_session_create",
     "cohost_shamir_session_destroy", "cohost_shamir_prove", "cohost_zkey_load", "cohost_zkey_load_file", "cohost_zkey_get_info",
-    "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file", "cohost_rep3_phase_times",
+    "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file", "cohost_rep3_phase_times", "cohost_plonk_zkey_load_file", "cohost_plonk_zkey_destroy",
+    "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -88,6 +89,12 @@ def load_host():
     L.cohost_zkey_matrix_download.argtypes = [vp, ci, vp, vp, vp, ctypes.POINTER(sz)]
     L.cohost_zkey_vk_download.argtypes = [vp, vp]
     L.cohost_wtns_load_file.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(sz)]
+    L.cohost_plonk_zkey_load_file.argtypes = [ctypes.c_char_p, ci, pvp]
+    L.cohost_plonk_zkey_destroy.argtypes = [vp]
+    L.cohost_plonk_zkey_destroy.restype = None
+    L.cohost_plonk_zkey_get_info.argtypes = [vp, ctypes.POINTER(sz)]
+    L.cohost_plonk_round1_plain.argtypes = [vp, vp, vp, ci, vp]
+    L.cohost_plonk_round1_rep3.argtypes = [vp, vp, pvp, pvp, vp, ci, vp]
     L.cohost_rep3_phase_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.cohost_shamir_session_create.argtypes = [vp, ci, ci, vp, pvp]
     L.cohost_shamir_session_destroy.argtypes = [vp]
@@ -368,4 +375,39 @@ class ShamirSession:
     def close(self):
         if self.h:
             load_host().cohost_shamir_session_destroy(self.h)
+            self.h = None
+
+
+class PlonkZKey:
+    """What round 1 of the Plonk prover consumes from a snarkjs Plonk zkey (p_tau resident in HBM)."""
+
+    def __init__(self, path: str, device: int = 0):
+        h = vp()
+        _ck(load_host().cohost_plonk_zkey_load_file(path.encode(), device, ctypes.byref(h)))
+        self.h = h
+        info = (sz * 6)()
+        _ck(load_host().cohost_plonk_zkey_get_info(h, info))
+        self.curve, self.n_vars, self.n_public, self.domain_size, self.n_additions, self.n_constraints = (int(x) for x in info)
+        self.lq = 4 if self.curve == _lib.BN254 else 6
+
+    def round1_plain(self, public_inputs, witness, deterministic=True) -> np.ndarray:
+        pub, wit = _c(public_inputs), _c(witness)
+        assert pub.size == 4 * (self.n_public + 1) and wit.size == 4 * (self.n_vars - self.n_additions - self.n_public - 1)
+        out = np.zeros((3, 2 * self.lq), dtype=np.uint64)
+        _ck(load_host().cohost_plonk_round1_plain(self.h, pub.ctypes.data, wit.ctypes.data, 1 if deterministic else 0, out.ctypes.data))
+        return out
+
+    def round1_rep3(self, public_inputs, wit_a, wit_b, seeds: bytes = bytes(range(96)), deterministic=True) -> np.ndarray:
+        pub = _c(public_inputs)
+        wa, wb = [_c(x) for x in wit_a], [_c(x) for x in wit_b]
+        A = (vp * 3)(*[x.ctypes.data for x in wa])
+        B = (vp * 3)(*[x.ctypes.data for x in wb])
+        sd = np.frombuffer(seeds, dtype=np.uint8).copy()
+        out = np.zeros((3, 3, 2 * self.lq), dtype=np.uint64)
+        _ck(load_host().cohost_plonk_round1_rep3(self.h, pub.ctypes.data, A, B, sd.ctypes.data, 1 if deterministic else 0, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            load_host().cohost_plonk_zkey_destroy(self.h)
             self.h = None

@@ -26,6 +26,7 @@ typedef struct cohost_zkey cohost_zkey;
 typedef struct cohost_plain_session cohost_plain_session;
 typedef struct cohost_rep3_session cohost_rep3_session;
 typedef struct cohost_shamir_session cohost_shamir_session;
+typedef struct cohost_plonk_zkey cohost_plonk_zkey;
 
 /* A parsed Groth16 proving key (circom-types/src/groth16/zkey.rs:47-71), HOST pointers; copied to HBM once. */
 typedef struct cohost_zkey_desc {
@@ -115,6 +116,16 @@ COHOST_API int cohost_rep3_phase_times(cohost_rep3_session* s, double* out);
 COHOST_API int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out);
 COHOST_API void cohost_shamir_session_destroy(cohost_shamir_session* s);
 COHOST_API int cohost_shamir_prove(cohost_shamir_session* s, const void* public_inputs, const void* const* wit, void* proofs_out, void* rs_out);
+/* Plonk, round 1 of CoPlonk::prove (co-plonk/src/round1.rs): the zkey reader for what the round consumes (header, additions, wire
+ * maps, p_tau: circom-types/src/plonk/zkey.rs:160-330) and the wire commitments [a]_1 | [b]_1 | [c]_1 (packed affine) with the plain
+ * driver or three REP3 parties.  deterministic != 0: the reference's KAT blinders b_i = i (round1.rs:101-108).
+ * info[6] = curve, n_vars, n_public, domain_size, n_additions, n_constraints. */
+COHOST_API int cohost_plonk_zkey_load_file(const char* path, int device, cohost_plonk_zkey** out);
+COHOST_API void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z);
+COHOST_API int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info);
+COHOST_API int cohost_plonk_round1_plain(cohost_plonk_zkey* z, const void* public_inputs, const void* witness, int deterministic, void* commits_out);
+COHOST_API int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                        const uint8_t* seeds, int deterministic, void* commits_out);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 
