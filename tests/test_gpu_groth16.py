@@ -247,3 +247,53 @@ def test_shamir_prove_matches_plain_oracle(cocg, curve, circ, n, t):
         assert got[0] == groth16.prove_plain(zk, wt, r_val, s_val)
     sess.close()
     dz.close()
+
+
+def test_witness_map_full_size_matches_c_oracle(cocg):
+    """BASELINE config 3 size (n = 2^20, synthetic shape-faithful R1CS): witness_map_from_matrices on the GPU (plain driver) against the
+    C oracle's restatement of the same steps (SpMV, mul, 3 x [iNTT, coset scale, NTT], sub) -- bit-exact h, all 2^20 elements."""
+    from oracle import ntt as ontt
+    c = BN254
+    log_n = 20
+    n = 1 << log_n
+    rng = np.random.default_rng(2024)
+
+    def rand_fr(m):
+        a = rng.integers(0, 2**64, size=(m, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        return a
+
+    n_public, n_vars, rows = 1, n, n - 2
+
+    def mat():
+        rowptr = (2 * np.arange(rows + 1)).astype(np.uint32)
+        col = ((np.repeat(np.arange(rows, dtype=np.int64), 2) + rng.integers(-64, 64, size=2 * rows)) % n_vars).astype(np.uint32)
+        return rowptr, col, rand_fr(2 * rows)
+
+    A, B = mat(), mat()
+    from importlib import import_module
+    prover = import_module("collaborative-circom_b200.prover")
+    zk = prover.Groth16ZKey(cocg.BN254, n_public, n_vars, log_n, rows, A, B, synthetic_seed=bytes(range(32)))
+    sess = prover.PlainSession(zk)
+    pub, wit = rand_fr(n_public + 1), rand_fr(n_vars - n_public - 1)
+    one = cref.fr_to_mont(c, [1])
+    _, h = sess.prove(pub, wit, one, one, want_h=True)
+    # C oracle
+    z = np.concatenate([pub, wit])
+    a = np.zeros((n, 4), dtype=np.uint64)
+    b = np.zeros((n, 4), dtype=np.uint64)
+    a[:rows] = cref.spmv(c, A[0], A[1], A[2], z)
+    b[:rows] = cref.spmv(c, B[0], B[1], B[2], z)
+    a[rows:rows + n_public + 1] = pub                     # clone_from_slice of the public inputs (groth16.rs:169-171)
+    omega, g = ontt.groth16_roots(c, log_n)
+    om, omi, gm = cref.fr_to_mont(c, [omega]), cref.fr_to_mont(c, [pow(omega, -1, c.r)]), cref.fr_to_mont(c, [g])
+
+    def coset(v):
+        return cref.ntt(c, cref.distribute_powers(c, cref.ntt(c, v, omi, inverse=True), gm, one), om)
+
+    cc = cref.fr_vec_op(c, cref.OP_MUL, a, b)
+    ab = cref.fr_vec_op(c, cref.OP_MUL, coset(a), coset(b))
+    want = cref.fr_vec_op(c, cref.OP_SUB, ab, coset(cc))
+    assert np.array_equal(h, want)
+    sess.close()
+    zk.close()
