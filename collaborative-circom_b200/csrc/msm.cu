@@ -88,7 +88,8 @@ extern "C" int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_h
 
 namespace {
 struct MsmOps {
-  int (*accumulate)(cocg_ctx*, const BasesEntry&, size_t, const MsmSorted&, void*);
+  int (*buckets)(cocg_ctx*, const BasesEntry&, size_t, const MsmSorted&);
+  int (*reduce)(cocg_ctx*, const MsmSorted&, void*);
   void (*finish)(const void*, void*);
   size_t xyzz_bytes, jac_bytes;
 };
@@ -96,10 +97,12 @@ MsmOps msm_ops(int curve, int group) {
   const size_t cb = curve == COCG_BN254 ? 32 : 48;
   MsmOps o;
   if (curve == COCG_BN254) {
-    o.accumulate = group == COCG_G1 ? msm_accumulate_bn254_g1 : msm_accumulate_bn254_g2;
+    o.buckets = group == COCG_G1 ? msm_buckets_bn254_g1 : msm_buckets_bn254_g2;
+    o.reduce = group == COCG_G1 ? msm_reduce_bn254_g1 : msm_reduce_bn254_g2;
     o.finish = group == COCG_G1 ? msm_finish_bn254_g1 : msm_finish_bn254_g2;
   } else {
-    o.accumulate = group == COCG_G1 ? msm_accumulate_bls381_g1 : msm_accumulate_bls381_g2;
+    o.buckets = group == COCG_G1 ? msm_buckets_bls381_g1 : msm_buckets_bls381_g2;
+    o.reduce = group == COCG_G1 ? msm_reduce_bls381_g1 : msm_reduce_bls381_g2;
     o.finish = group == COCG_G1 ? msm_finish_bls381_g1 : msm_finish_bls381_g2;
   }
   o.xyzz_bytes = 4 * cb * group;
@@ -147,7 +150,9 @@ extern "C" int cocg_msm_multi(cocg_ctx* ctx, const uint64_t* bases, const size_t
       else COCG_TRY(msm_sort_impl<Bls381FrP>(ctx, scalars[j], n, c, scalars_mont, S));
       for (int q = q0; q < nq; q++) {
         if (be[q]->c != c) continue;
-        COCG_TRY(msm_ops(ctx->curve, be[q]->group).accumulate(ctx, *be[q], offs[q], S, (char*)d_res + ((size_t)q * k + j) * kResultSlot));
+        MsmOps o = msm_ops(ctx->curve, be[q]->group);
+        COCG_TRY(o.buckets(ctx, *be[q], offs[q], S));
+        COCG_TRY(o.reduce(ctx, S, (char*)d_res + ((size_t)q * k + j) * kResultSlot));
       }
     }
     for (int q = q0; q < nq; q++)

@@ -462,32 +462,42 @@ int msm_sort_impl(cocg_ctx* ctx, const void* scalars, size_t n, int c, int mont,
   return 0;
 }
 
-// accumulate + reduce one query against a finished sort; the XYZZ result is written to d_result (device)
+// One query against a finished sort, in two halves that live in separate translation units (the group law over Fq2 makes each
+// of them minutes of ptxas time): bucket accumulation into the context's bucket scratch, then the bucket reduction whose XYZZ
+// result is written to d_result (device).
 template <class F>
-int msm_accumulate_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, void* d_result) {
+int msm_buckets_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S) {
   using X = XYZZ<F>;
   if (be.c != S.c) return fail(ctx, "cocg_msm: the table's window width differs from the sort's");
   const uint32_t nb = S.nb;
-  const uint32_t logL = (uint32_t)(S.c - 1) / 2, logH = (uint32_t)(S.c - 1) - logL;
-  const uint32_t nmarg = (1u << logH) + (1u << logL) * kColSeg;
-  X *buckets, *marg, *hpartial;
+  X *buckets, *hpartial;
   void* p;
   COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
-  COCG_TRY(scratch_get(ctx, 8, ((size_t)nmarg + nmarg / 32 + 2) * sizeof(X), &p)); marg = (X*)p;  // partial marginals | weighted warp sums
   COCG_TRY(scratch_get(ctx, 12, 2 * S.max_heavy * sizeof(X), &p)); hpartial = (X*)p;
   const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
   cudaStream_t st = ctx->stream;
-  {
-    ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
-    COCG_CUDA(ctx, cudaMemsetAsync(S.heavy, 0, 16, st));
-    msm_accumulate_kernel<F><<<(nb + 127) / 128, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list, S.chunk_owner,
-                                                                S.heavy);
-    COCG_LAUNCH_CHECK(ctx);
-    msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.heavy_list, S.chunk_owner, S.heavy, hpartial);
-    COCG_LAUNCH_CHECK(ctx);
-    msm_heavy_fold_kernel<F><<<kNumSMs, 128, 0, st>>>(S.heavy_list, S.heavy, hpartial, buckets);
-    COCG_LAUNCH_CHECK(ctx);
-  }
+  ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
+  COCG_CUDA(ctx, cudaMemsetAsync(S.heavy, 0, 16, st));
+  msm_accumulate_kernel<F><<<(nb + 127) / 128, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list, S.chunk_owner,
+                                                              S.heavy);
+  COCG_LAUNCH_CHECK(ctx);
+  msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.heavy_list, S.chunk_owner, S.heavy, hpartial);
+  COCG_LAUNCH_CHECK(ctx);
+  msm_heavy_fold_kernel<F><<<kNumSMs, 128, 0, st>>>(S.heavy_list, S.heavy, hpartial, buckets);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template <class F>
+int msm_reduce_impl(cocg_ctx* ctx, const MsmSorted& S, void* d_result) {
+  using X = XYZZ<F>;
+  const uint32_t nb = S.nb;
+  const uint32_t logL = (uint32_t)(S.c - 1) / 2, logH = (uint32_t)(S.c - 1) - logL;
+  const uint32_t nmarg = (1u << logH) + (1u << logL) * kColSeg;
+  X *buckets, *marg;
+  void* p;
+  COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;  // filled by msm_buckets_impl
+  COCG_TRY(scratch_get(ctx, 8, ((size_t)nmarg + nmarg / 32 + 2) * sizeof(X), &p)); marg = (X*)p;  // partial marginals | weighted warp sums
+  cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
   msm_marginals_kernel<F><<<(nmarg * 32 + 127) / 128, 128, 0, st>>>(buckets, logH, logL, marg);
   COCG_LAUNCH_CHECK(ctx);
@@ -509,7 +519,8 @@ void msm_finish_impl(const void* h_xyzz, void* out_jac) {
 
 // per-(curve, group) entry points, one translation unit each (msm_<curve>_<group>.cu)
 #define COCG_MSM_DECL(NAME)                                                                                     \
-  int msm_accumulate_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, void* d_result); \
+  int msm_buckets_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S);                   \
+  int msm_reduce_##NAME(cocg_ctx* ctx, const MsmSorted& S, void* d_result);                                      \
   void msm_finish_##NAME(const void* h_xyzz, void* out_jac);                                                      \
   int msm_precompute_##NAME(cocg_ctx* ctx, BasesEntry& be);
 COCG_MSM_DECL(bn254_g1)
