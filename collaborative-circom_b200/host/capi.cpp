@@ -3,6 +3,7 @@
 // Rep3TestNetwork, exactly how /root/reference/tests/tests/circom/e2e_tests/mod.rs:55-70 and
 // tests/benches/poseidon_hash2.rs:197-222 run it) on top of libcocg.so.  Declared in include/cohost.h.
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 
 #include "../../include/cohost.h"
@@ -248,6 +249,10 @@ extern "C" int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds /
     s->rank = rank;
     s->world = world;
     s->net.reset(new Rep3TestNetwork());
+    {  // COHOST_MPC_EXCHANGE=device: the three co-located parties pass share vectors in HBM (default: pinned host staging)
+      const char* ex = getenv("COHOST_MPC_EXCHANGE");
+      s->net->device_exchange = ex && std::string(ex) == "device";
+    }
     for (int i = 0; i < 3; i++) s->drv[i].reset(new Rep3Protocol(z->zk.curve, z->device, s->net->party(i), seeds + 32 * i));
     for (int i = 0; i < 3; i++) {
       s->drv[i]->finish_setup();
@@ -778,4 +783,13 @@ extern "C" int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public
       memcpy(o + 4 * lq, proofs[i].commit_c.l, 2 * lq * 8);
     }
   });
+}
+
+// How the three co-located parties of a session move share vectors in the mul_vec rounds: 0 = staged through pinned host memory
+// (default; what a party that has to reach a NIC does), 1 = handed over in HBM (all parties share the session's GPU).
+extern "C" int cohost_rep3_set_mpc_exchange(cohost_rep3_session* s, int device) {
+  if (!s) return fail("cohost_rep3_set_mpc_exchange: null session");
+  if (s->running) return fail("cohost_rep3_set_mpc_exchange: a proof is in flight");
+  s->net->device_exchange = device != 0;
+  return 0;
 }

@@ -290,6 +290,20 @@ class Rep3Protocol : public DeviceDriver {
     } else {
       check(ctx, cocg_rep3_mul_local_prf(ctx, a.a.p, a.b.p, b.a.p, b.b.p, seed1, seed2, ctr++, o.a.p, n), "cocg_rep3_mul_local_prf");
     }
+    if (net->device_exchange()) {  // co-located parties on one GPU: hand a copy over in HBM, the receiver adopts it as its `b`
+      DevVec out_copy = alloc(n);
+      check(ctx, cocg_d2d(ctx, out_copy.p, o.a.p, n * 32), "cocg_d2d");
+      check(ctx, cocg_sync(ctx), "cocg_sync");
+      Message s;
+      s.bytes = n * 32;
+      s.device = out_copy.p;
+      net->send_next(std::move(s));
+      Message m = net->recv_prev();
+      if (m.bytes != n * 32 || !m.device) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
+      release(o.b);
+      o.b = DevVec{m.device, n};
+      return o;
+    }
     std::shared_ptr<void> buf = pinned(n * 32);
     check(ctx, cocg_d2h(ctx, buf.get(), o.a.p, n * 32), "cocg_d2h");
     net->send_next(Message{buf, n * 32});

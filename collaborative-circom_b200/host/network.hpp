@@ -20,6 +20,7 @@ namespace cohost {
 struct Message {
   std::shared_ptr<void> data;  // host memory (pinned for share vectors)
   size_t bytes = 0;
+  void* device = nullptr;      // device-exchange mode: an HBM buffer whose ownership moves to the receiver (data is null)
 };
 
 class Channel {  // unbounded MPSC byte channel (std::sync::mpsc in the reference's test network)
@@ -61,6 +62,10 @@ class Rep3Network {
   virtual int get_id() const = 0;
   virtual void send(int target, Message m) = 0;
   virtual Message recv(int from) = 0;
+  // true when all parties of this network live in one process on ONE GPU and the caller opted in: share vectors may then be
+  // handed over as HBM buffers instead of being staged through pinned host memory (the default, which is what a party that has
+  // to reach a NIC does)
+  virtual bool device_exchange() const { return false; }
   void send_next(Message m) { send((get_id() + 1) % 3, std::move(m)); }
   Message recv_prev() { return recv((get_id() + 2) % 3); }
   // small values: copied into a heap buffer
@@ -83,6 +88,7 @@ class PartyTestNetwork : public Rep3Network {
   int get_id() const override { return id_; }
   void send(int target, Message m) override;
   Message recv(int from) override;
+  bool device_exchange() const override;
 
  private:
   Rep3TestNetwork* net_;
@@ -96,6 +102,7 @@ class Rep3TestNetwork {
   }
   PartyTestNetwork* party(int i) { return parties_[i].get(); }
   Channel& chan(int from, int to) { return ch_[from][to]; }
+  bool device_exchange = false;
   void close_all() {
     for (auto& row : ch_)
       for (auto& c : row) c.close();
@@ -108,5 +115,6 @@ class Rep3TestNetwork {
 
 inline void PartyTestNetwork::send(int target, Message m) { net_->chan(id_, target).send(std::move(m)); }
 inline Message PartyTestNetwork::recv(int from) { return net_->chan(from, id_).recv(); }
+inline bool PartyTestNetwork::device_exchange() const { return net_->device_exchange; }
 
 }  // namespace cohost

@@ -24,7 +24,7 @@ HOST_SYMBOLS = [
     "cohost_rep3_profile_read", "cohost_rep3_profile_reset", "cohost_msm_shard_range", "cohost_shamir_session_create",
     "cohost_shamir_session_destroy", "cohost_shamir_prove", "cohost_zkey_load", "cohost_zkey_load_file", "cohost_zkey_get_info",
     "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file", "cohost_rep3_phase_times", "cohost_plonk_zkey_load_file", "cohost_plonk_zkey_destroy",
-    "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3",
+    "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3", "cohost_rep3_set_mpc_exchange",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -95,6 +95,7 @@ def load_host():
     L.cohost_plonk_zkey_get_info.argtypes = [vp, ctypes.POINTER(sz)]
     L.cohost_plonk_round1_plain.argtypes = [vp, vp, vp, ci, vp]
     L.cohost_plonk_round1_rep3.argtypes = [vp, vp, pvp, pvp, vp, ci, vp]
+    L.cohost_rep3_set_mpc_exchange.argtypes = [vp, ci]
     L.cohost_rep3_phase_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.cohost_shamir_session_create.argtypes = [vp, ci, ci, vp, pvp]
     L.cohost_shamir_session_destroy.argtypes = [vp]
@@ -335,6 +336,11 @@ class Rep3Session:
 
     def launch_count(self) -> int:
         return int(load_host().cohost_rep3_launch_count(self.h))
+
+    def set_mpc_exchange(self, mode: str):
+        """'host': mul_vec payloads staged through pinned host memory (default); 'device': handed over in HBM (co-located parties)."""
+        assert mode in ("host", "device")
+        _ck(load_host().cohost_rep3_set_mpc_exchange(self.h, 1 if mode == "device" else 0))
 
     def phase_times(self) -> np.ndarray:
         """(3, 4) seconds of the last proof per party: witness map | MSMs | all-gather wait | assembly."""

@@ -108,6 +108,9 @@ COHOST_API int cohost_rep3_prove_combine(cohost_rep3_session* s, const void* gat
 /* proofs_out: 3 x (A | B | C); h_a / h_b: NULL or 3 HOST buffers of 2^pow Fr receiving each party's share of h. */
 COHOST_API int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, void* const* h_a, void* const* h_b);
 COHOST_API uint64_t cohost_rep3_launch_count(cohost_rep3_session* s);
+/* mul_vec payloads between the three co-located parties: device = 0 staged through pinned host memory (default: what a party that
+ * must reach a NIC does; also selected by COHOST_MPC_EXCHANGE=host), device = 1 handed over in HBM (the parties share one GPU). */
+COHOST_API int cohost_rep3_set_mpc_exchange(cohost_rep3_session* s, int device);
 /* Host wall-clock per phase of the last proof, seconds: out[party * 4 + k], k = witness map | MSMs | all-gather wait | assembly. */
 COHOST_API int cohost_rep3_phase_times(cohost_rep3_session* s, double* out);
 /* num_parties CoGroth16<ShamirProtocol> provers (mpc-core/src/protocols/shamir.rs), threshold t with 2t + 1 <= num_parties, on

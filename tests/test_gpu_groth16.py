@@ -297,3 +297,27 @@ def test_witness_map_full_size_matches_c_oracle(cocg):
     assert np.array_equal(h, want)
     sess.close()
     zk.close()
+
+
+def test_rep3_device_exchange_equals_host_exchange(cocg):
+    """The mul_vec payloads of the three co-located parties handed over in HBM (cohost_rep3_set_mpc_exchange) instead of being staged
+    through pinned host memory: same proof, same h shares."""
+    zk, wt, vk, public = load_fixture("bn254", "poseidon")
+    c = zk.curve
+    prover, dz = device_zkey(cocg, zk)
+    pub, shares, r, s, rnd = _rep3_inputs(zk, wt, 77)
+    f = lambda vals: cref.fr_to_mont(c, vals)
+    wa, wb = [f(sh[0]) for sh in shares], [f(sh[1]) for sh in shares]
+    limbs = _rnd_to_limbs(c, rnd)
+    sess = prover.Rep3Session(dz)
+    want, ha, hb = sess.prove(f(pub), wa, wb, limbs, want_h=True)
+    sess.set_mpc_exchange("device")
+    for _ in range(2):
+        got, ga, gb = sess.prove(f(pub), wa, wb, limbs, want_h=True)
+        assert np.array_equal(got, want)
+        assert all(np.array_equal(x, y) for x, y in zip(ha + hb, ga + gb))
+    sess.set_mpc_exchange("host")
+    assert np.array_equal(sess.prove(f(pub), wa, wb, limbs), want)
+    assert groth16.verify(vk, *proof_points(c, want[0]), public)
+    sess.close()
+    dz.close()
