@@ -65,6 +65,12 @@ COCG_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc
 COCG_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 COCG_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 COCG_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+COCG_D void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {  // one IMAD.WIDE.U32 instead of a mul.lo / mul.hi pair
+  uint64_t r;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+  lo = (uint32_t)r;
+  hi = (uint32_t)(r >> 32);
+}
 COCG_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 COCG_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 COCG_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -261,10 +267,8 @@ COCG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
   // row 0: disjoint (lo,hi) pairs, no chain needed
 #pragma unroll
   for (int j = 0; j < N; j += 2) {
-    e[j] = ptx::mul_lo(a.l[j], b.l[0]);
-    e[j + 1] = ptx::mul_hi(a.l[j], b.l[0]);
-    o[j] = ptx::mul_lo(a.l[j + 1], b.l[0]);
-    o[j + 1] = ptx::mul_hi(a.l[j + 1], b.l[0]);
+    ptx::mul_wide(e[j], e[j + 1], a.l[j], b.l[0]);
+    ptx::mul_wide(o[j], o[j + 1], a.l[j + 1], b.l[0]);
   }
   e[N] = 0; e[N + 1] = 0; o[N] = 0; o[N + 1] = 0;
   {

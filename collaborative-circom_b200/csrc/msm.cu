@@ -88,8 +88,8 @@ extern "C" int cocg_bases_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_h
 
 namespace {
 struct MsmOps {
-  int (*buckets)(cocg_ctx*, const BasesEntry&, size_t, const MsmSorted&);
-  int (*reduce)(cocg_ctx*, const MsmSorted&, void*);
+  int (*buckets)(cocg_ctx*, const BasesEntry&, size_t, const MsmSorted&, int);
+  int (*reduce)(cocg_ctx*, int, const ReduceSets&, void*);
   void (*finish)(const void*, void*);
   size_t xyzz_bytes, jac_bytes;
 };
@@ -109,7 +109,6 @@ MsmOps msm_ops(int curve, int group) {
   o.jac_bytes = 3 * cb * group;
   return o;
 }
-constexpr size_t kResultSlot = 512;  // bytes reserved per XYZZ result (G2 over BLS12-381 needs 384)
 }  // namespace
 
 extern "C" int cocg_msm_multi(cocg_ctx* ctx, const uint64_t* bases, const size_t* offs, int nq, size_t n, const void* const* scalars, int k,
@@ -139,22 +138,40 @@ extern "C" int cocg_msm_multi(cocg_ctx* ctx, const uint64_t* bases, const size_t
   }
   void* d_res;
   COCG_TRY(scratch_get(ctx, 9, (size_t)nq * k * kResultSlot, &d_res));
-  // queries are grouped by window width so that each group shares one digit sort per component
+  // Queries are grouped by window width so that each group shares one digit sort per component.  Every (query, component)
+  // accumulates into its own bucket set; the sets of one curve group are reduced together, kMaxSets per launch (msm_impl.cuh).
   bool done[16] = {};
   for (int q0 = 0; q0 < nq; q0++) {
     if (done[q0]) continue;
     const int c = be[q0]->c;
+    const size_t nb = (size_t)1 << (c - 1);
+    ReduceSets pend[3] = {};  // indexed by group (COCG_G1 = 1, COCG_G2 = 2)
+    for (int g = COCG_G1; g <= COCG_G2; g++) {  // size the bucket arenas before the first set is written (growth does not preserve contents)
+      size_t cnt = 0;
+      for (int q = q0; q < nq; q++) cnt += (be[q]->c == c && be[q]->group == g) ? (size_t)k : 0;
+      if (cnt > (size_t)kMaxSets) cnt = kMaxSets;
+      void* p;
+      if (cnt) COCG_TRY(scratch_get(ctx, msm_bucket_slot(g), cnt * nb * msm_ops(ctx->curve, g).xyzz_bytes, &p));
+    }
     for (int j = 0; j < k; j++) {
       MsmSorted S;
       if (ctx->curve == COCG_BN254) COCG_TRY(msm_sort_impl<Bn254FrP>(ctx, scalars[j], n, c, scalars_mont, S));
       else COCG_TRY(msm_sort_impl<Bls381FrP>(ctx, scalars[j], n, c, scalars_mont, S));
       for (int q = q0; q < nq; q++) {
         if (be[q]->c != c) continue;
-        MsmOps o = msm_ops(ctx->curve, be[q]->group);
-        COCG_TRY(o.buckets(ctx, *be[q], offs[q], S));
-        COCG_TRY(o.reduce(ctx, S, (char*)d_res + ((size_t)q * k + j) * kResultSlot));
+        const int g = be[q]->group;
+        MsmOps o = msm_ops(ctx->curve, g);
+        ReduceSets& P = pend[g];
+        COCG_TRY(o.buckets(ctx, *be[q], offs[q], S, (int)P.n));
+        P.slot[P.n++] = (uint32_t)(q * k + j);
+        if (P.n == (uint32_t)kMaxSets) {
+          COCG_TRY(o.reduce(ctx, c, P, d_res));
+          P.n = 0;
+        }
       }
     }
+    for (int g = COCG_G1; g <= COCG_G2; g++)
+      if (pend[g].n) COCG_TRY(msm_ops(ctx->curve, g).reduce(ctx, c, pend[g], d_res));
     for (int q = q0; q < nq; q++)
       if (be[q]->c == c) done[q] = true;
   }

@@ -254,23 +254,40 @@ __device__ __forceinline__ T warp_shfl_down(const T& v, int delta) {
 template <class F>
 __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const void* table, size_t tstride, const uint32_t* sorted, uint32_t beg, uint32_t end,
                                                uint32_t step) {
+  // The gather address of entry e + step is known one addition ahead: prefetching its cache line(s) into L1 hides the DRAM latency
+  // of the random table access behind the current addition without holding a second point in registers.
+  auto entry_index = [&](uint32_t v) { return (size_t)((v >> kIdxBits) & 63u) * tstride + (v & ((1u << kIdxBits) - 1)); };
+  if (beg >= end) return;
+  uint32_t v = sorted[beg];
   for (uint32_t e = beg; e < end; e += step) {
-    uint32_t v = sorted[e];
-    size_t idx = (size_t)((v >> kIdxBits) & 63u) * tstride + (v & ((1u << kIdxBits) - 1));
+    const size_t idx = entry_index(v);
+    uint32_t vn = 0;
+    if (e + step < end) {
+      vn = sorted[e + step];
+      const char* nxt = reinterpret_cast<const char*>(table) + entry_index(vn) * sizeof(Affine<F>);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+      if (128 % sizeof(Affine<F>) != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + sizeof(Affine<F>) - 16));  // may straddle two lines
+    }
     Affine<F> p = load_affine<F>(table, idx);
     if (v >> 31) p.y = f_neg(p.y);
     xyzz_madd(acc, p);
+    v = vn;
   }
 }
 
 // ------------------------------------------------------------------ 4. bucket accumulation
+static inline int msm_bucket_slot(int group) { return group == COCG_G1 ? 7 : 14; }  // scratch arena of the group's bucket sets
+// Blocks of 128 threads, registers left to ptxas (104 for Fq, 188 for Fq2 = 2 blocks per SM).  Measured alternatives on B200
+// (BN254 G2, 2^20 terms, ms): 7.6 as is; 64-thread blocks (5 per SM) 8.08; capped at 168 registers (3 blocks per SM, 156 B of
+// spills) 8.23.  G1 capped at 96 registers (5 blocks per SM): 2.12, unchanged.
+constexpr int kAccumulateThreads = 128;
 // One thread per bucket, buckets taken in descending size order so that the lanes of a warp finish together (ncu: 31.7 of 32
 // lanes active, fmaheavy pipe 90 % busy at 2^19 buckets of ~26 points).
 struct HeavyRec {
   uint32_t bucket, first_chunk, nchunks;
 };
 template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(kAccumulateThreads) msm_accumulate_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
                                                               const uint32_t* __restrict__ start, const uint32_t* __restrict__ order, uint32_t nbuckets,
                                                               XYZZ<F>* __restrict__ buckets, HeavyRec* __restrict__ heavy_list,
                                                               uint32_t* __restrict__ chunk_owner,
@@ -347,14 +364,26 @@ __device__ __forceinline__ XYZZ<F> xyzz_mul_small(const XYZZ<F>& p, uint32_t k) 
 // row sums R_hi = sum_lo B[hi][lo] and column sums C_lo = sum_hi B[hi][lo].  One warp per row; columns (twice as long when
 // H = 2L) are cut into kColSeg segments of one warp each, so that all warps run the same number of additions.
 // out[row], then out[H + col * kColSeg + seg].
+// The reductions of up to kMaxSets bucket sets (the queries and share components of one cocg_msm_multi call) run as ONE launch
+// of each kernel, set index = blockIdx.y: a single 2^19-bucket set gives only ~3.5 warps per scheduler and the weigh / final
+// kernels are pure latency chains, so batching sets is free parallelism.
 constexpr uint32_t kColSeg = 2;
+constexpr int kMaxSets = 8;
+constexpr size_t kResultSlot = 512;  // bytes reserved per XYZZ result (G2 over BLS12-381 needs 384)
+struct ReduceSets {
+  uint32_t n;
+  uint32_t slot[kMaxSets];  // result slot (kResultSlot bytes each) of every set
+};
+static inline uint32_t marg_stride(uint32_t nmarg) { return nmarg + (nmarg + 31) / 32 + 2; }  // partial marginals | weighted warp sums
 template <class F>
 __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
-                                                             XYZZ<F>* __restrict__ out) {
+                                                             XYZZ<F>* __restrict__ out, uint32_t mstride) {
   const uint32_t H = 1u << logH, L = 1u << logL;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= H + L * kColSeg) return;
+  buckets += (size_t)blockIdx.y << (logH + logL);
+  out += (size_t)blockIdx.y * mstride;
   XYZZ<F> acc = xyzz_inf<F>();
   if (warp < H) {
     const XYZZ<F>* r = buckets + ((size_t)warp << logL);
@@ -373,8 +402,11 @@ __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __res
 }
 // weights: one THREAD per partial marginal (all lanes busy, unlike a multiply on the reducing lane), then a warp tree
 template <class F>
-__global__ void __launch_bounds__(128) msm_weigh_kernel(const XYZZ<F>* __restrict__ marg, uint32_t logH, uint32_t logL, XYZZ<F>* __restrict__ partial) {
+__global__ void __launch_bounds__(128) msm_weigh_kernel(const XYZZ<F>* __restrict__ marg, uint32_t logH, uint32_t logL, XYZZ<F>* __restrict__ partial,
+                                                         uint32_t mstride) {
   const uint32_t H = 1u << logH, nmarg = H + (1u << logL) * kColSeg;
+  marg += (size_t)blockIdx.y * mstride;
+  partial += (size_t)blockIdx.y * mstride;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
   XYZZ<F> acc = xyzz_inf<F>();
@@ -383,12 +415,15 @@ __global__ void __launch_bounds__(128) msm_weigh_kernel(const XYZZ<F>* __restric
     XYZZ<F> other = warp_shfl_down(acc, delta);
     if (lane < (uint32_t)delta) xyzz_add(acc, other);
   }
-  if (lane == 0) partial[i >> 5] = acc;
+  if (lane == 0 && i < ((nmarg + 31) & ~31u)) partial[i >> 5] = acc;  // warps past the last marginal own no slot (the next set's region follows)
 }
-// one warp: plain sum of m points
+// one warp per set: plain sum of m points into the set's result slot
 template <class F>
-__global__ void __launch_bounds__(32) msm_final_kernel(const XYZZ<F>* __restrict__ in, uint32_t m, XYZZ<F>* __restrict__ out) {
+__global__ void __launch_bounds__(32) msm_final_kernel(const XYZZ<F>* __restrict__ in, uint32_t m, uint32_t mstride, char* __restrict__ results,
+                                                        ReduceSets sets) {
   const uint32_t lane = threadIdx.x;
+  in += (size_t)blockIdx.x * mstride;
+  XYZZ<F>* out = reinterpret_cast<XYZZ<F>*>(results + (size_t)sets.slot[blockIdx.x] * kResultSlot);
   XYZZ<F> acc = xyzz_inf<F>();
   for (uint32_t i = lane; i < m; i += 32) xyzz_add(acc, in[i]);
   for (int delta = 16; delta >= 1; delta >>= 1) {
@@ -466,20 +501,22 @@ int msm_sort_impl(cocg_ctx* ctx, const void* scalars, size_t n, int c, int mont,
 // of them minutes of ptxas time): bucket accumulation into the context's bucket scratch, then the bucket reduction whose XYZZ
 // result is written to d_result (device).
 template <class F>
-int msm_buckets_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S) {
+int msm_buckets_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, int set) {
   using X = XYZZ<F>;
   if (be.c != S.c) return fail(ctx, "cocg_msm: the table's window width differs from the sort's");
   const uint32_t nb = S.nb;
   X *buckets, *hpartial;
   void* p;
-  COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;
+  // bucket sets of one group live side by side (slot sized by cocg_msm_multi before the first set is written)
+  COCG_TRY(scratch_get(ctx, msm_bucket_slot(be.group), (size_t)(set + 1) * nb * sizeof(X), &p)); buckets = (X*)p + (size_t)set * nb;
   COCG_TRY(scratch_get(ctx, 12, 2 * S.max_heavy * sizeof(X), &p)); hpartial = (X*)p;
   const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
   cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
   COCG_CUDA(ctx, cudaMemsetAsync(S.heavy, 0, 16, st));
-  msm_accumulate_kernel<F><<<(nb + 127) / 128, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list, S.chunk_owner,
-                                                              S.heavy);
+  constexpr int kThreads = kAccumulateThreads;
+  msm_accumulate_kernel<F><<<(nb + kThreads - 1) / kThreads, kThreads, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list,
+                                                                                  S.chunk_owner, S.heavy);
   COCG_LAUNCH_CHECK(ctx);
   msm_heavy_chunks_kernel<F><<<kNumSMs * 4, 128, 0, st>>>(table, be.n, S.sorted, S.start, S.heavy_list, S.chunk_owner, S.heavy, hpartial);
   COCG_LAUNCH_CHECK(ctx);
@@ -487,24 +524,27 @@ int msm_buckets_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmS
   COCG_LAUNCH_CHECK(ctx);
   return 0;
 }
+// Reduces bucket sets 0 .. sets.n-1 of `group` (all built with window width c); set s goes to d_results + sets.slot[s] * kResultSlot.
 template <class F>
-int msm_reduce_impl(cocg_ctx* ctx, const MsmSorted& S, void* d_result) {
+int msm_reduce_impl(cocg_ctx* ctx, int group, int c, const ReduceSets& sets, void* d_results) {
   using X = XYZZ<F>;
-  const uint32_t nb = S.nb;
-  const uint32_t logL = (uint32_t)(S.c - 1) / 2, logH = (uint32_t)(S.c - 1) - logL;
+  if (sets.n == 0) return 0;
+  const uint32_t nb = 1u << (c - 1);
+  const uint32_t logL = (uint32_t)(c - 1) / 2, logH = (uint32_t)(c - 1) - logL;
   const uint32_t nmarg = (1u << logH) + (1u << logL) * kColSeg;
+  const uint32_t mstride = marg_stride(nmarg);
   X *buckets, *marg;
   void* p;
-  COCG_TRY(scratch_get(ctx, 7, (size_t)nb * sizeof(X), &p)); buckets = (X*)p;  // filled by msm_buckets_impl
-  COCG_TRY(scratch_get(ctx, 8, ((size_t)nmarg + nmarg / 32 + 2) * sizeof(X), &p)); marg = (X*)p;  // partial marginals | weighted warp sums
+  COCG_TRY(scratch_get(ctx, msm_bucket_slot(group), (size_t)sets.n * nb * sizeof(X), &p)); buckets = (X*)p;  // filled by msm_buckets_impl
+  COCG_TRY(scratch_get(ctx, 8, (size_t)sets.n * mstride * sizeof(X), &p)); marg = (X*)p;
   cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
-  msm_marginals_kernel<F><<<(nmarg * 32 + 127) / 128, 128, 0, st>>>(buckets, logH, logL, marg);
+  msm_marginals_kernel<F><<<dim3((nmarg * 32 + 127) / 128, sets.n), 128, 0, st>>>(buckets, logH, logL, marg, mstride);
   COCG_LAUNCH_CHECK(ctx);
   const uint32_t nwarps = (nmarg + 31) / 32;
-  msm_weigh_kernel<F><<<(nmarg + 127) / 128, 128, 0, st>>>(marg, logH, logL, marg + nmarg);
+  msm_weigh_kernel<F><<<dim3((nmarg + 127) / 128, sets.n), 128, 0, st>>>(marg, logH, logL, marg + nmarg, mstride);
   COCG_LAUNCH_CHECK(ctx);
-  msm_final_kernel<F><<<1, 32, 0, st>>>(marg + nmarg, nwarps, reinterpret_cast<X*>(d_result));
+  msm_final_kernel<F><<<sets.n, 32, 0, st>>>(marg + nmarg, nwarps, mstride, (char*)d_results, sets);
   COCG_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -519,8 +559,8 @@ void msm_finish_impl(const void* h_xyzz, void* out_jac) {
 
 // per-(curve, group) entry points, one translation unit each (msm_<curve>_<group>.cu)
 #define COCG_MSM_DECL(NAME)                                                                                     \
-  int msm_buckets_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S);                   \
-  int msm_reduce_##NAME(cocg_ctx* ctx, const MsmSorted& S, void* d_result);                                      \
+  int msm_buckets_##NAME(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmSorted& S, int set);          \
+  int msm_reduce_##NAME(cocg_ctx* ctx, int c, const ReduceSets& sets, void* d_results);                          \
   void msm_finish_##NAME(const void* h_xyzz, void* out_jac);                                                      \
   int msm_precompute_##NAME(cocg_ctx* ctx, BasesEntry& be);
 COCG_MSM_DECL(bn254_g1)

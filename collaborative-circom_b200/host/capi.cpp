@@ -11,6 +11,7 @@
 #include "shamir.hpp"
 #include "formats.hpp"
 #include "plonk.hpp"
+#include "serialize.hpp"
 
 using namespace cohost;
 
@@ -792,4 +793,189 @@ extern "C" int cohost_rep3_set_mpc_exchange(cohost_rep3_session* s, int device) 
   if (s->running) return fail("cohost_rep3_set_mpc_exchange: a proof is in flight");
   s->net->device_exchange = device != 0;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ output formats (serialize.hpp)
+namespace {
+int copy_out(const void* src, size_t n, void* out, size_t cap, size_t* len, const char* what) {
+  if (len) *len = n;
+  if (!out) return 0;  // size query
+  if (cap < n) return fail(std::string(what) + ": output buffer too small");
+  memcpy(out, src, n);
+  return 0;
+}
+}  // namespace
+
+// proof: A | B | C packed affine Montgomery (as written by cohost_*_prove).  out == NULL: only *len is set.  No terminating NUL.
+extern "C" int cohost_proof_to_json(int curve, const void* proof, char* out, size_t cap, size_t* len) {
+  if (!proof) return fail("cohost_proof_to_json: null argument");
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_proof_to_json: unknown curve");
+  int rc = 0;
+  int g = guarded([&] {
+    std::string s = proof_to_json(curve, (const uint64_t*)proof);
+    rc = copy_out(s.data(), s.size(), out, cap, len, "cohost_proof_to_json");
+  });
+  return g ? g : rc;
+}
+// pub: count Montgomery Fr, pub[0] = the constant 1 (skipped in the output like the reference's writer)
+extern "C" int cohost_public_inputs_to_json(int curve, const void* pub, size_t count, char* out, size_t cap, size_t* len) {
+  if (!pub && count) return fail("cohost_public_inputs_to_json: null argument");
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_public_inputs_to_json: unknown curve");
+  int rc = 0;
+  int g = guarded([&] {
+    std::string s = public_inputs_to_json(curve, (const uint64_t*)pub, count);
+    rc = copy_out(s.data(), s.size(), out, cap, len, "cohost_public_inputs_to_json");
+  });
+  return g ? g : rc;
+}
+// SharedWitness file image of one party.  comps: k = 2 (REP3: a, b) or 1 (Shamir) HOST vectors of n Montgomery Fr.
+extern "C" int cohost_shared_witness_encode(int curve, const void* pub, size_t n_pub, const void* const* comps, int k, size_t n, void* out,
+                                            size_t cap, size_t* len) {
+  if ((!pub && n_pub) || !comps || (k != 1 && k != 2)) return fail("cohost_shared_witness_encode: bad argument");
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_shared_witness_encode: unknown curve");
+  const size_t need = 8 + 8 + 32 * n_pub + 8 + (size_t)k * (8 + 32 * n);
+  if (len) *len = need;
+  if (!out) return 0;
+  if (cap < need) return fail("cohost_shared_witness_encode: output buffer too small");
+  for (int j = 0; j < k; j++)
+    if (n && !comps[j]) return fail("cohost_shared_witness_encode: null share component");
+  return guarded([&] {
+    const uint64_t* c[2] = {(const uint64_t*)comps[0], k == 2 ? (const uint64_t*)comps[1] : nullptr};
+    std::vector<uint8_t> o = shared_witness_encode(curve, (const uint64_t*)pub, n_pub, c, k, n);
+    memcpy(out, o.data(), o.size());
+  });
+}
+// Two-step decode: with pub == NULL only the element counts are returned; then the caller passes buffers of that size.
+extern "C" int cohost_shared_witness_decode(int curve, const void* data, size_t len, int k, size_t* n_pub, size_t* n, void* pub,
+                                            void* const* comps) {
+  if (!data || (k != 1 && k != 2) || !n_pub || !n) return fail("cohost_shared_witness_decode: bad argument");
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_shared_witness_decode: unknown curve");
+  return guarded([&] {
+    SharedWitnessData w = shared_witness_decode(curve, (const uint8_t*)data, len, k);
+    *n_pub = w.public_inputs.size();
+    *n = w.comps[0].size();
+    if (!pub && !comps) return;
+    if (pub && *n_pub) memcpy(pub, w.public_inputs.data(), *n_pub * 32);
+    if (comps)
+      for (int j = 0; j < k; j++)
+        if (comps[j] && *n) memcpy(comps[j], w.comps[j].data(), *n * 32);
+  });
+}
+// SharedWitness::share_rep3 (co-circom-snarks/src/lib.rs:149-173) on the GPU: a, b <- PRF streams of seed[0..32) / seed[32..64),
+// c = x - a - b; party 0 = (a, c), party 1 = (b, a), party 2 = (c, b)  (rep3::utils::share_field_elements, mpc-core/src/protocols/rep3.rs:124-150;
+// the reference draws a and b from the caller's RNG, so the shares themselves are not reproducible across implementations).
+// witness: n Montgomery Fr on the HOST (values[num_pub_inputs..]); out_a / out_b: 3 HOST vectors each.
+extern "C" int cohost_split_witness_rep3(int curve, int device, const void* witness, size_t n, const uint8_t* seed, void* const* out_a,
+                                         void* const* out_b) {
+  if ((!witness && n) || !seed || !out_a || !out_b) return fail("cohost_split_witness_rep3: null argument");
+  return guarded([&] {
+    DeviceDriver d(curve, device);
+    cocg_ctx* c = d.ctx;
+    if (n == 0) return;
+    DevVec x = d.alloc(n), a = d.alloc(n), b = d.alloc(n);
+    check(c, cocg_h2d(c, x.p, witness, n * 32), "cocg_h2d");
+    check(c, cocg_prf_fill(c, seed, 0, a.p, n), "cocg_prf_fill");
+    check(c, cocg_prf_fill(c, seed + 32, 0, b.p, n), "cocg_prf_fill");
+    check(c, cocg_vec_op(c, COCG_OP_SUB, x.p, a.p, x.p, n), "cocg_vec_op");
+    check(c, cocg_vec_op(c, COCG_OP_SUB, x.p, b.p, x.p, n), "cocg_vec_op");  // x is now c
+    const void* src_a[3] = {a.p, b.p, x.p};
+    const void* src_b[3] = {x.p, a.p, b.p};
+    for (int i = 0; i < 3; i++) {
+      check(c, cocg_d2h(c, out_a[i], src_a[i], n * 32), "cocg_d2h");
+      check(c, cocg_d2h(c, out_b[i], src_b[i], n * 32), "cocg_d2h");
+    }
+    d.release(x); d.release(a); d.release(b);
+  });
+}
+
+// info[6] = curve, n_wires, n_pub_out, n_pub_in, n_constraints, num_inputs (= 1 + n_pub_out + n_pub_in, r1cs.rs:201).  No GPU needed.
+extern "C" int cohost_r1cs_info(const char* path, size_t* info) {
+  if (!path || !info) return fail("cohost_r1cs_info: null argument");
+  return guarded([&] {
+    std::vector<uint8_t> buf = read_file(path);
+    R1csHeader h(buf.data(), buf.size());
+    info[0] = (size_t)h.curve; info[1] = h.n_wires; info[2] = h.n_pub_out; info[3] = h.n_pub_in; info[4] = h.n_constraints; info[5] = h.num_inputs();
+  });
+}
+
+// `co-circom split-witness` (co-circom/src/bin/co-circom.rs:160-256): witness.wtns + circuit.r1cs -> <out_dir>/<witness file name>.<i>.shared,
+// one SharedWitness file per party.  protocol 0 = REP3 (threshold 1, 3 parties), 1 = Shamir(threshold, num_parties): share i is the value of
+// x + sum_k c_k (i + 1)^k, k = 1..threshold (shamir/shamir_core.rs:8-33).  The random shares / coefficients come from the GPU PRF keyed by
+// seed[32 * j ..) (REP3: 2 streams, Shamir: `threshold` streams; seed holds 32 * max(2, threshold) bytes).
+extern "C" int cohost_split_witness_files(const char* witness_path, const char* r1cs_path, int protocol, int curve, int threshold, int num_parties,
+                                          const uint8_t* seed, const char* out_dir, int device) {
+  if (!witness_path || !r1cs_path || !seed || !out_dir) return fail("cohost_split_witness_files: null argument");
+  if (protocol == 0 && threshold != 1) return fail("REP3 only allows the threshold to be 1");
+  if (protocol == 0 && num_parties != 3) return fail("REP3 only allows the number of parties to be 3");
+  if (protocol != 0 && protocol != 1) return fail("cohost_split_witness_files: unknown protocol");
+  if (protocol == 1 && (threshold < 1 || num_parties <= threshold)) return fail("Shamir needs 1 <= threshold < num_parties");
+  return guarded([&] {
+    std::vector<uint8_t> wbuf = read_file(witness_path), rbuf = read_file(r1cs_path);
+    WitnessFile w(wbuf.data(), wbuf.size());
+    R1csHeader r(rbuf.data(), rbuf.size());
+    if (w.curve != curve || r.curve != curve) throw Error("split-witness: the files are over a different curve");
+    if (r.num_inputs() > w.n) throw Error("split-witness: fewer witness values than public inputs");
+    const size_t n_pub = r.num_inputs(), n = w.n - n_pub;
+    DeviceDriver d(curve, device);
+    cocg_ctx* c = d.ctx;
+    DevVec all = d.alloc(w.n);
+    check(c, cocg_h2d(c, all.p, w.values, w.n * 32), "cocg_h2d");
+    check(c, cocg_vec_op(c, COCG_OP_TO_MONT, all.p, nullptr, all.p, w.n), "cocg_vec_op");
+    std::vector<uint64_t> pub(4 * n_pub);
+    check(c, cocg_d2h(c, pub.data(), all.p, n_pub * 32), "cocg_d2h");
+    void* x = all.at(n_pub);
+    const int parties = protocol == 0 ? 3 : num_parties, k = protocol == 0 ? 2 : 1;
+    std::vector<std::vector<uint64_t>> comp_a(parties, std::vector<uint64_t>(4 * n)), comp_b(k == 2 ? parties : 0, std::vector<uint64_t>(4 * n));
+    if (n) {
+      if (protocol == 0) {
+        DevVec a = d.alloc(n), b = d.alloc(n), cc = d.alloc(n);
+        check(c, cocg_prf_fill(c, seed, 0, a.p, n), "cocg_prf_fill");
+        check(c, cocg_prf_fill(c, seed + 32, 0, b.p, n), "cocg_prf_fill");
+        check(c, cocg_vec_op(c, COCG_OP_SUB, x, a.p, cc.p, n), "cocg_vec_op");
+        check(c, cocg_vec_op(c, COCG_OP_SUB, cc.p, b.p, cc.p, n), "cocg_vec_op");
+        const void* sa[3] = {a.p, b.p, cc.p};   // share_field_elements rep3.rs:124-150: (a, c), (b, a), (c, b)
+        const void* sb[3] = {cc.p, a.p, b.p};
+        for (int i = 0; i < 3; i++) {
+          check(c, cocg_d2h(c, comp_a[i].data(), sa[i], n * 32), "cocg_d2h");
+          check(c, cocg_d2h(c, comp_b[i].data(), sb[i], n * 32), "cocg_d2h");
+        }
+        d.release(a); d.release(b); d.release(cc);
+      } else {
+        std::vector<DevVec> coeff(threshold);
+        for (int j = 0; j < threshold; j++) {
+          coeff[j] = d.alloc(n);
+          check(c, cocg_prf_fill(c, seed + 32 * j, 0, coeff[j].p, n), "cocg_prf_fill");
+        }
+        DevVec acc = d.alloc(n);
+        for (int i = 0; i < parties; i++) {
+          Fr xi = d.fr.zero(), one = d.fr.one(), pw;
+          for (int t = 0; t <= i; t++) xi = d.fr.add(xi, one);  // i + 1 in Montgomery form
+          pw = xi;
+          const void* cur = x;
+          for (int j = 0; j < threshold; j++) {  // acc = x + sum_j coeff_j * (i+1)^(j+1)
+            check(c, cocg_vec_axpy(c, pw.l, coeff[j].p, cur, acc.p, n), "cocg_vec_axpy");
+            cur = acc.p;
+            pw = d.fr.mul(pw, xi);
+          }
+          check(c, cocg_d2h(c, comp_a[i].data(), acc.p, n * 32), "cocg_d2h");
+        }
+        d.release(acc);
+        for (auto& v : coeff) d.release(v);
+      }
+    }
+    d.release(all);
+    std::string base = witness_path;
+    size_t slash = base.find_last_of('/');
+    if (slash != std::string::npos) base = base.substr(slash + 1);
+    for (int i = 0; i < parties; i++) {
+      const uint64_t* comps[2] = {comp_a[i].data(), k == 2 ? comp_b[i].data() : nullptr};
+      std::vector<uint8_t> img = shared_witness_encode(curve, pub.data(), n_pub, comps, k, n);
+      std::string path = std::string(out_dir) + "/" + base + "." + std::to_string(i) + ".shared";
+      FILE* f = fopen(path.c_str(), "wb");
+      if (!f) throw Error("cannot create " + path);
+      size_t wr = fwrite(img.data(), 1, img.size(), f);
+      fclose(f);
+      if (wr != img.size()) throw Error("short write on " + path);
+    }
+  });
 }

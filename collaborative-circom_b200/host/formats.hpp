@@ -156,6 +156,28 @@ struct Groth16ZKeyFile {
   }
 };
 
+// .r1cs header (circom-types/src/r1cs.rs:100-215): only what split-witness needs -- num_inputs = 1 + n_pub_out + n_pub_in (r1cs.rs:201).
+struct R1csHeader {
+  int curve = 0;
+  size_t n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_prv_in = 0, n_constraints = 0;
+  size_t num_inputs() const { return 1 + n_pub_out + n_pub_in; }
+  R1csHeader(const uint8_t* data, size_t len) {
+    BinFile bf(data, len, "r1cs");
+    auto h = bf.take(1);
+    const uint8_t* p = h.first;
+    if (h.second < 4) throw Error("r1cs: truncated header");
+    const uint32_t n8 = BinFile::u32(p);
+    if (n8 != 32 || h.second < 4 + 32 + 4 * 4 + 8 + 4) throw Error("r1cs: wrong scalar field");
+    if (memcmp(p + 4, kBn254R, 32) == 0) curve = COCG_BN254;
+    else if (memcmp(p + 4, kBls381R, 32) == 0) curve = COCG_BLS12_381;
+    else throw Error("r1cs: wrong scalar field");
+    p += 36;
+    n_wires = BinFile::u32(p); n_pub_out = BinFile::u32(p + 4); n_pub_in = BinFile::u32(p + 8); n_prv_in = BinFile::u32(p + 12);
+    n_constraints = BinFile::u32(p + 24);
+    if (num_inputs() > n_wires) throw Error("r1cs: more inputs than wires");
+  }
+};
+
 // .wtns: returns the canonical little-endian values (32 bytes each); the caller moves them to Montgomery form on the GPU
 struct WitnessFile {
   int curve = 0;

@@ -25,6 +25,8 @@ HOST_SYMBOLS = [
     "cohost_shamir_session_destroy", "cohost_shamir_prove", "cohost_zkey_load", "cohost_zkey_load_file", "cohost_zkey_get_info",
     "cohost_zkey_query_download", "cohost_zkey_matrix_download", "cohost_zkey_vk_download", "cohost_wtns_load_file", "cohost_rep3_phase_times", "cohost_plonk_zkey_load_file", "cohost_plonk_zkey_destroy",
     "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3", "cohost_rep3_set_mpc_exchange",
+    "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
+    "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -102,6 +104,13 @@ def load_host():
     L.cohost_shamir_session_destroy.restype = None
     L.cohost_shamir_prove.argtypes = [vp, vp, pvp, vp, vp]
     L.cohost_msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
+    L.cohost_proof_to_json.argtypes = [ci, vp, vp, sz, ctypes.POINTER(sz)]
+    L.cohost_public_inputs_to_json.argtypes = [ci, vp, sz, vp, sz, ctypes.POINTER(sz)]
+    L.cohost_shared_witness_encode.argtypes = [ci, vp, sz, pvp, ci, sz, vp, sz, ctypes.POINTER(sz)]
+    L.cohost_shared_witness_decode.argtypes = [ci, vp, sz, ci, ctypes.POINTER(sz), ctypes.POINTER(sz), vp, pvp]
+    L.cohost_split_witness_rep3.argtypes = [ci, ci, vp, sz, vp, pvp, pvp]
+    L.cohost_r1cs_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(sz)]
+    L.cohost_split_witness_files.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ci, ci, ci, vp, ctypes.c_char_p, ci]
     _host = L
     return L
 
@@ -113,6 +122,85 @@ def _ck(rc):
 
 def _c(a, dtype=np.uint64):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _sized(call):
+    """Two-step writer protocol of include/cohost.h: query the length, then fill a buffer of that size."""
+    n = sz(0)
+    _ck(call(None, 0, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(max(n.value, 1))
+    _ck(call(buf, n.value, ctypes.byref(n)))
+    return buf.raw[:n.value]
+
+
+def proof_to_json(curve: int, proof) -> str:
+    """snarkjs / serde_json text of a proof block (A | B | C packed affine Montgomery) as `co-circom generate-proof` writes it."""
+    L = load_host()
+    p = _c(proof)
+    return _sized(lambda out, cap, n: L.cohost_proof_to_json(curve, p.ctypes.data, out, cap, n)).decode()
+
+
+def public_inputs_to_json(curve: int, pub) -> str:
+    """JSON array of decimal strings of pub[1:] (pub[0] is the constant 1), Montgomery Fr in."""
+    L = load_host()
+    p = _c(pub).reshape(-1, 4)
+    return _sized(lambda out, cap, n: L.cohost_public_inputs_to_json(curve, p.ctypes.data, p.shape[0], out, cap, n)).decode()
+
+
+def shared_witness_encode(curve: int, pub, comps) -> bytes:
+    """SharedWitness file image (bincode + ark-serialize); comps = [a, b] for REP3, [a] for Shamir; Montgomery Fr in."""
+    L = load_host()
+    p = _c(pub).reshape(-1, 4)
+    cs = [_c(c).reshape(-1, 4) for c in comps]
+    arr = (vp * len(cs))(*[c.ctypes.data for c in cs])
+    return _sized(lambda out, cap, n: L.cohost_shared_witness_encode(curve, p.ctypes.data, p.shape[0], arr, len(cs), cs[0].shape[0], out, cap, n))
+
+
+def shared_witness_decode(curve: int, data: bytes, k: int):
+    """-> (public_inputs, [components]) as Montgomery Fr arrays."""
+    L = load_host()
+    npub, n = sz(0), sz(0)
+    buf = ctypes.create_string_buffer(data, len(data))
+    _ck(L.cohost_shared_witness_decode(curve, buf, len(data), k, ctypes.byref(npub), ctypes.byref(n), None, None))
+    pub = np.zeros((npub.value, 4), dtype=np.uint64)
+    comps = [np.zeros((n.value, 4), dtype=np.uint64) for _ in range(k)]
+    arr = (vp * k)(*[c.ctypes.data for c in comps])
+    _ck(L.cohost_shared_witness_decode(curve, buf, len(data), k, ctypes.byref(npub), ctypes.byref(n), pub.ctypes.data, arr))
+    return pub, comps
+
+
+def split_witness_rep3(curve: int, witness, seed: bytes, device: int = 0):
+    """SharedWitness::share_rep3 on the GPU: three (a, b) pairs of Montgomery Fr arrays; seed = 64 bytes."""
+    L = load_host()
+    assert len(seed) == 64
+    w = _c(witness).reshape(-1, 4)
+    n = w.shape[0]
+    oa = [np.zeros((n, 4), dtype=np.uint64) for _ in range(3)]
+    ob = [np.zeros((n, 4), dtype=np.uint64) for _ in range(3)]
+    A = (vp * 3)(*[o.ctypes.data for o in oa])
+    B = (vp * 3)(*[o.ctypes.data for o in ob])
+    sb = ctypes.create_string_buffer(seed, 64)
+    _ck(L.cohost_split_witness_rep3(curve, device, w.ctypes.data, n, sb, A, B))
+    return list(zip(oa, ob))
+
+
+def r1cs_info(path: str) -> dict:
+    info = (sz * 6)()
+    _ck(load_host().cohost_r1cs_info(path.encode(), info))
+    return dict(zip(("curve", "n_wires", "n_pub_out", "n_pub_in", "n_constraints", "num_inputs"), [int(x) for x in info]))
+
+
+def split_witness_files(witness: str, r1cs: str, protocol: str, curve: int, out_dir: str, threshold: int = 1, num_parties: int = 3,
+                        seed: bytes | None = None, device: int = 0):
+    """`co-circom split-witness`: writes <out_dir>/<witness name>.<i>.shared; seed defaults to os.urandom."""
+    proto = {"REP3": 0, "SHAMIR": 1}[protocol.upper()]
+    need = 32 * max(2, threshold)
+    seed = os.urandom(need) if seed is None else seed
+    assert len(seed) >= need
+    sb = ctypes.create_string_buffer(seed, len(seed))
+    _ck(load_host().cohost_split_witness_files(witness.encode(), r1cs.encode(), proto, curve, threshold, num_parties, sb, out_dir.encode(), device))
+    n = 3 if proto == 0 else num_parties
+    return [os.path.join(out_dir, f"{os.path.basename(witness)}.{i}.shared") for i in range(n)]
 
 
 class Groth16ZKey:

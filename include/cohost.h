@@ -129,6 +129,29 @@ COHOST_API int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info);
 COHOST_API int cohost_plonk_round1_plain(cohost_plonk_zkey* z, const void* public_inputs, const void* witness, int deterministic, void* commits_out);
 COHOST_API int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
                                         const uint8_t* seeds, int deterministic, void* commits_out);
+/* Output-side formats of the path, byte-compatible with what `co-circom generate-proof` / `split-witness` write.
+ * Writers fill `out` (capacity `cap`) and set *len; out == NULL only queries the length.  Strings carry no terminating NUL.
+ *  - cohost_proof_to_json: serde_json of Groth16Proof (circom-types/src/groth16/proof.rs:7-29, traits.rs:186-233); `proof` is the
+ *    A | B | C packed affine Montgomery block the prove calls return.
+ *  - cohost_public_inputs_to_json: decimal strings of pub[1..count) (co-circom/src/bin/co-circom.rs:611-629).
+ *  - cohost_shared_witness_{encode,decode}: the bincode + ark-serialize image of SharedWitness (co-circom-snarks/src/lib.rs:24-41,
+ *    serde_compat.rs:5-24); k = 2 components for REP3 (a, b), 1 for Shamir.  decode with pub == NULL and comps == NULL returns the counts.
+ *  - cohost_split_witness_rep3: SharedWitness::share_rep3 (co-circom-snarks/src/lib.rs:149-173) with the random shares drawn by the
+ *    GPU PRF from seed[64]; witness / outputs are HOST vectors of n Montgomery Fr (needs a GPU). */
+COHOST_API int cohost_proof_to_json(int curve, const void* proof, char* out, size_t cap, size_t* len);
+COHOST_API int cohost_public_inputs_to_json(int curve, const void* pub, size_t count, char* out, size_t cap, size_t* len);
+COHOST_API int cohost_shared_witness_encode(int curve, const void* pub, size_t n_pub, const void* const* comps, int k, size_t n, void* out,
+                                            size_t cap, size_t* len);
+COHOST_API int cohost_shared_witness_decode(int curve, const void* data, size_t len, int k, size_t* n_pub, size_t* n, void* pub,
+                                            void* const* comps);
+COHOST_API int cohost_split_witness_rep3(int curve, int device, const void* witness, size_t n, const uint8_t* seed, void* const* out_a,
+                                         void* const* out_b);
+/* .r1cs header: info[6] = curve, n_wires, n_pub_out, n_pub_in, n_constraints, num_inputs (circom-types/src/r1cs.rs:100-215).  No GPU. */
+COHOST_API int cohost_r1cs_info(const char* path, size_t* info);
+/* `co-circom split-witness` (co-circom/src/bin/co-circom.rs:160-256): writes <out_dir>/<witness file name>.<i>.shared for every party.
+ * protocol 0 = REP3 (threshold 1, 3 parties), 1 = Shamir; the random part comes from the GPU PRF keyed by seed (32 * max(2, threshold) bytes). */
+COHOST_API int cohost_split_witness_files(const char* witness_path, const char* r1cs_path, int protocol, int curve, int threshold, int num_parties,
+                                          const uint8_t* seed, const char* out_dir, int device);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 

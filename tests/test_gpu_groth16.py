@@ -116,7 +116,7 @@ def _rnd_to_limbs(c, rnd):
     }
 
 
-@pytest.mark.parametrize("curve,circ", [("bn254", "multiplier2"), ("bn254", "poseidon"), ("bls12_381", "multiplier2")])
+@pytest.mark.parametrize("curve,circ", [("bn254", "multiplier2"), ("bn254", "poseidon"), ("bls12_381", "multiplier2"), ("bls12_381", "poseidon")])
 def test_rep3_prove_matches_oracle(cocg, curve, circ):
     zk, wt, vk, public = load_fixture(curve, circ)
     c = zk.curve

@@ -363,6 +363,51 @@ def test_msm_multi_shares_one_sort(cocg, bn):
         bn.bases_free(h)
 
 
+def test_msm_multi_batched_reduction_flushes(cocg, bn):
+    """The bucket reductions of one cocg_msm_multi call are batched, 8 bucket sets per launch (msm_impl.cuh kMaxSets): 5 G1
+    queries x 3 components = 15 sets (one flush in the middle, sets of later components landing in recycled arenas), a G2 query
+    beside them, and a query of a different size (other window width, separate sort group) -- every result vs the oracle."""
+    c = BN254
+    n = 700
+    g1 = [make_bases(c, 1, n + 3, seed=40 + i) for i in range(5)]
+    small = make_bases(c, 1, 40, seed=46)       # window width differs from the n = 703 tables
+    g2 = make_bases(c, 2, n + 3, seed=47)
+    hs = [bn.bases_upload(1, p) for p in g1[:3]] + [bn.bases_upload(1, small), bn.bases_upload(2, g2)] + [bn.bases_upload(1, p) for p in g1[3:]]
+    offs = [0, 1, 2, 0, 3, 3, 0]
+    sc = [rand_fr(40, 90 + j) for j in range(3)]
+    outs = bn.msm_multi(hs, offs, [bn.upload(s) for s in sc], n=40)   # n bounded by the small query
+    cases = [(g1[0], 1), (g1[1], 1), (g1[2], 1), (small, 1), (g2, 2), (g1[3], 1), (g1[4], 1)]
+    for out, (pts, group), off in zip(outs, cases, offs):
+        for j, s in enumerate(sc):
+            assert same_point(c, group, out[j], cref.msm(c, group, pts[off:off + 40], s))
+    bn.bases_free(hs[3])
+    hs6 = hs[:3] + hs[4:]
+    offs6 = [0, 1, 2, 3, 3, 0]
+    sc = [rand_fr(n, 95 + j) for j in range(3)]
+    outs = bn.msm_multi(hs6, offs6, [bn.upload(s) for s in sc], n=n)
+    cases = [(g1[0], 1), (g1[1], 1), (g1[2], 1), (g2, 2), (g1[3], 1), (g1[4], 1)]
+    for out, (pts, group), off in zip(outs, cases, offs6):
+        for j, s in enumerate(sc):
+            assert same_point(c, group, out[j], cref.msm(c, group, pts[off:off + n], s))
+    for h in hs6:
+        bn.bases_free(h)
+    # tiny window plans (tables of <= 200 bases: c <= 8, fewer partial marginals than one block of the weighting kernel) with
+    # adjacent bucket sets, repeated: a set's reduction must not touch its neighbour's scratch
+    for nb_pts in (9, 40, 200):
+        small_cases = [(make_bases(c, 1, nb_pts, seed=60 + i), 1) for i in range(3)] + [(make_bases(c, 2, nb_pts, seed=63), 2)]
+        hsm = [bn.bases_upload(g, p) for p, g in small_cases]
+        sc = [rand_fr(nb_pts, 120 + j) for j in range(4)]
+        want = [[cref.msm(c, group, pts, s) for s in sc] for pts, group in small_cases]
+        dsc = [bn.upload(s) for s in sc]
+        for _ in range(5):
+            outs = bn.msm_multi(hsm, [0, 0, 0, 0], dsc, n=nb_pts)
+            for out, w, (pts, group) in zip(outs, want, small_cases):
+                for k in range(4):
+                    assert same_point(c, group, out[k], w[k])
+        for h in hsm:
+            bn.bases_free(h)
+
+
 def test_bls12_381_full_size_properties(cocg, bls):
     """BLS12-381 at the size of BASELINE config 5's shards (2^20 terms per GPU at 2^22 over 4+ GPUs): MSM linearity on generated
     bases, a prefix against the oracle, and an NTT round trip at 2^22."""

@@ -1,0 +1,129 @@
+"""CPU-only: the product's output-side formats (collaborative-circom_b200/host/serialize.hpp through the C ABI of include/cohost.h)
+against the reference's own fixtures.
+
+  circom-types/src/groth16/proof.rs:31-99      the snarkjs circom.proof files (BN254 and BLS12-381): our writer, fed the fixture's
+                                               points, must reproduce the fixture's JSON value exactly (keys, order, decimal strings)
+  co-circom/src/bin/co-circom.rs:611-629       public.json: decimal strings of the public inputs without the leading 1
+  co-circom-snarks/src/lib.rs:24-41,           SharedWitness files: bincode + ark-serialize layout, checked byte-for-byte against an
+  serde_compat.rs:5-24                         independent Python restatement and by decode(encode(x)) == x; error paths
+"""
+import json
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import cref, formats
+from oracle.curves import BN254, BLS12_381
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+CURVES = {"bn254": BN254, "bls12_381": BLS12_381}
+
+
+def _cid(cocg, c):
+    return cocg.BN254 if c is BN254 else cocg.BLS12_381
+
+
+@pytest.mark.parametrize("curve,circ", [("bn254", "multiplier2"), ("bn254", "poseidon"), ("bls12_381", "multiplier2"), ("bls12_381", "poseidon")])
+def test_proof_json_reproduces_the_snarkjs_fixture(cocg, curve, circ):
+    c = CURVES[curve]
+    text = open(os.path.join(G, "groth16", curve, circ, "circom.proof")).read()
+    _, A, B, C = formats.proof_from_json(text)
+    block = np.concatenate([cref.g_to_mont(c, [A], 1).ravel(), cref.g_to_mont(c, [B], 2).ravel(), cref.g_to_mont(c, [C], 1).ravel()])
+    ours = cocg.proof_to_json(_cid(cocg, c), block)
+    assert " " not in ours and "\n" not in ours                     # serde_json::to_writer: compact
+    want, got = json.loads(text), json.loads(ours)
+    assert list(got.keys()) == ["pi_a", "pi_b", "pi_c", "protocol", "curve"]  # struct field order of Groth16Proof
+    assert got == want
+    assert formats.proof_from_json(ours)[1:] == (A, B, C)
+
+
+def test_proof_json_infinity_and_errors(cocg):
+    c = BN254
+    g2 = cref.g_to_mont(c, [c.gen(2)], 2).ravel()
+    block = np.concatenate([np.zeros(8, dtype=np.uint64), g2, cref.g_to_mont(c, [c.gen(1)], 1).ravel()])
+    got = json.loads(cocg.proof_to_json(cocg.BN254, block))
+    assert got["pi_a"] == ["0", "1", "0"]                           # g1_to_strings_projective, traits.rs:186-193
+    assert got["pi_c"] == ["1", "2", "1"]
+    block[8:24] = 0
+    with pytest.raises(cocg.CocgError, match="infinity"):           # serialize_g2 unwraps xy(): no encoding exists
+        cocg.proof_to_json(cocg.BN254, block)
+    with pytest.raises(cocg.CocgError, match="curve"):
+        cocg.proof_to_json(7, block)
+
+
+@pytest.mark.parametrize("curve,circ", [("bn254", "multiplier2"), ("bn254", "poseidon"), ("bls12_381", "poseidon")])
+def test_public_inputs_json_matches_fixture(cocg, curve, circ):
+    c = CURVES[curve]
+    d = os.path.join(G, "groth16", curve, circ)
+    want = json.load(open(os.path.join(d, "public.json")))
+    _, wt = formats.parse_wtns(open(os.path.join(d, "witness.wtns"), "rb").read())
+    pub = cref.fr_to_mont(c, wt[:1 + len(want)])
+    ours = cocg.public_inputs_to_json(_cid(cocg, c), pub)
+    assert json.loads(ours) == want and " " not in ours
+    assert cocg.public_inputs_to_json(_cid(cocg, c), pub[:1]) == "[]"
+    zero = cref.fr_to_mont(c, [1, 0, c.r - 1])
+    assert json.loads(cocg.public_inputs_to_json(_cid(cocg, c), zero)) == ["0", str(c.r - 1)]
+
+
+def _ark_vec(vals):
+    return struct.pack("<Q", len(vals)) + b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+def _bincode_shared_witness(pub, comps):
+    """Independent restatement: bincode(serialize_bytes) = u64 length + bytes; ark compressed Vec<F> = u64 count + LE elements."""
+    p = _ark_vec(pub)
+    w = b"".join(_ark_vec(c) for c in comps)
+    return struct.pack("<Q", len(p)) + p + struct.pack("<Q", len(w)) + w
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bls12_381"])
+@pytest.mark.parametrize("k", [2, 1])
+def test_shared_witness_file_layout_and_round_trip(cocg, curve, k):
+    c = CURVES[curve]
+    rng = random.Random(5 + k)
+    for n_pub, n in ((2, 7), (1, 0), (3, 300)):
+        pub = [1] + [rng.randrange(c.r) for _ in range(n_pub - 1)]
+        comps = [[rng.randrange(c.r) for _ in range(n)] for _ in range(k)]
+        if n:
+            comps[0][0], comps[-1][-1] = 0, c.r - 1
+        mp, mc = cref.fr_to_mont(c, pub), [cref.fr_to_mont(c, x) if n else np.zeros((0, 4), dtype=np.uint64) for x in comps]
+        img = cocg.shared_witness_encode(_cid(cocg, c), mp, mc)
+        assert img == _bincode_shared_witness(pub, comps)
+        dp, dc = cocg.shared_witness_decode(_cid(cocg, c), img, k)
+        assert np.array_equal(dp, mp)
+        for a, b in zip(dc, mc):
+            assert np.array_equal(a, b)
+
+
+def test_shared_witness_decode_rejects_bad_files(cocg):
+    c = BN254
+    pub, comps = [1, 5], [[3, 4], [6, 7]]
+    good = _bincode_shared_witness(pub, comps)
+    with pytest.raises(cocg.CocgError, match="truncated"):
+        cocg.shared_witness_decode(cocg.BN254, good[:-5], 2)
+    with pytest.raises(cocg.CocgError, match="trailing|wrong protocol"):       # a REP3 file read as a Shamir share
+        cocg.shared_witness_decode(cocg.BN254, good, 1)
+    bad = _bincode_shared_witness(pub, [[c.r, 4], [6, 7]])                      # element == modulus: Validate::Yes rejects
+    with pytest.raises(cocg.CocgError, match="canonical"):
+        cocg.shared_witness_decode(cocg.BN254, bad, 2)
+    ragged = _bincode_shared_witness(pub, [[3, 4], [6]])
+    with pytest.raises(cocg.CocgError, match="length"):
+        cocg.shared_witness_decode(cocg.BN254, ragged, 2)
+    huge = struct.pack("<Q", 1 << 60) + good[8:]
+    with pytest.raises(cocg.CocgError, match="truncated"):
+        cocg.shared_witness_decode(cocg.BN254, huge, 2)
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bls12_381"])
+def test_r1cs_header_matches_reference_kat(cocg, curve):
+    """circom-types/src/r1cs.rs:280-330: multiplier2 has num_inputs 2 (n_pub_out 1, n_pub_in 0), 4 wires, 1 constraint."""
+    info = cocg.r1cs_info(os.path.join(G, "groth16", curve, "multiplier2", "circuit.r1cs"))
+    assert info == {"curve": _cid(cocg, CURVES[curve]), "n_wires": 4, "n_pub_out": 1, "n_pub_in": 0, "n_constraints": 1, "num_inputs": 2}
+    zk = formats.parse_groth16_zkey(open(os.path.join(G, "groth16", curve, "poseidon", "circuit.zkey"), "rb").read(), check_points=False)
+    info = cocg.r1cs_info(os.path.join(G, "groth16", curve, "poseidon", "circuit.r1cs"))
+    assert (info["n_wires"], info["num_inputs"]) == (zk.n_vars, zk.n_public + 1)
+    with pytest.raises(cocg.CocgError, match="r1cs"):
+        cocg.r1cs_info(os.path.join(G, "groth16", curve, "multiplier2", "witness.wtns"))

@@ -25,7 +25,7 @@ def copy_fixtures():
             src = os.path.join(REF, "test_vectors", "Groth16", curve, circ)
             dst = os.path.join(OUT, "groth16", curve, circ)
             os.makedirs(dst, exist_ok=True)
-            for f in ("circuit.zkey", "witness.wtns", "circom.proof", "public.json", "verification_key.json"):
+            for f in ("circuit.zkey", "witness.wtns", "circom.proof", "public.json", "verification_key.json", "circuit.r1cs"):
                 shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
                 os.chmod(os.path.join(dst, f), 0o644)
 

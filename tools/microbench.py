@@ -52,6 +52,14 @@ def main():
             ctx.bases_free(h)
             for v in sc:
                 v.free()
+        # the Groth16 aux shape: 3 G1 queries + 1 G2 query x 2 share components, one call (shared sorts, batched reductions)
+        hs = [ctx.bases_generate(1, n, bytes([10 + i] * 32)) for i in range(3)] + [ctx.bases_generate(2, n, bytes([13] * 32))]
+        sc = [ctx.upload(rand_fr(n, 9)), ctx.upload(rand_fr(n, 10))]
+        res[f"msm_multi_3g1_1g2_2^{logn}_k2"] = prof(ctx, lambda: ctx.msm_multi(hs, [0, 0, 0, 0], sc))
+        for h in hs:
+            ctx.bases_free(h)
+        for v in sc:
+            v.free()
         # NTT: root of unity is irrelevant for timing; use any element
         vs = [ctx.upload(rand_fr(n, 3 + i)) for i in range(2)]
         om = np.array([[R1 & (2**64 - 1), (R1 >> 64) & (2**64 - 1), (R1 >> 128) & (2**64 - 1), R1 >> 192]], dtype=np.uint64)
