@@ -325,6 +325,27 @@ def run_own(args):
         sess1.close()
         zk1.close()
 
+    # The same accumulate kernel timed ALONE (one context, one stream, no other party competing for the SMs): the in-situ scope times
+    # above include the time slices the GPU gives to the other two parties' kernels.  One G1 query of this rank's shard size, k = 1.
+    alone = None
+    if world == 1:
+        bits = 254 if args.curve == "bn254" else 255
+        per_alone = n_aux
+        h_alone = ctx.bases_generate(1, per_alone, bytes([77] * 32))
+        ctx.msm(h_alone, [dev[0]], n=per_alone)
+        ctx.profile(True)
+        ctx.profile_reset()
+        for _ in range(5):
+            ctx.msm(h_alone, [dev[0]], n=per_alone)
+        ctx.sync()
+        pa = ctx.profile_read()
+        ctx.profile(False)
+        ctx.bases_free(h_alone)
+        lg = (per_alone + per_alone // 2).bit_length() - 1
+        c_bits = min(max(lg, 4), 20)
+        nwin = (bits + c_bits) // c_bits
+        alone = {"ms": pa["msm_accumulate"][0] / max(pa["msm_accumulate"][1], 1), "terms": per_alone, "window_bits": c_bits, "windows": nwin}
+
     value = args.steps / (ms / 1e3)
     e2e = args.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak()
@@ -365,6 +386,21 @@ def run_own(args):
             "host_phases_ms": {"witness_map": round(float(phases[0]), 2), "msm": round(float(phases[1]), 2),
                                "all_gather_wait": round(float(phases[2]), 2), "assembly": round(float(phases[3]), 2)},
         }
+        if alone:
+            # issue roofline of the same kernel: 10 Fq multiplications (8M + 2S) per table point added; ceiling = 148 SMs x 32
+            # IMAD.WIDE/clk x sm_max_mhz / 144 multiply-pipe instructions per 8-limb Montgomery product (SASS count)
+            fq_mul = alone["terms"] * alone["windows"] * 10 / (alone["ms"] * 1e-3) / 1e9
+            ceiling, ceiling_src = 148 * 32 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 144 / 1e9, "IMAD.WIDE issue ceiling (148 SMs x 32/clk / 144 per product)"
+            cpath = os.path.join(ROOT, "profiles", "r01_fp_mul_ceiling.json")
+            if os.path.exists(cpath):  # measured: a pure chain of the same Montgomery product on every SM
+                ceiling = float(json.load(open(cpath))["G_mul_per_s"]["bn254_fq" if args.curve == "bn254" else "bls381_fq"])
+                ceiling_src = "measured fp_mul chain, profiles/r01_fp_mul_ceiling.json"
+            out["roofline"].update({
+                "achieved_alone": alone["terms"] * 96 / (alone["ms"] * 1e-3) / 1e9, "frac_alone": alone["terms"] * 96 / (alone["ms"] * 1e-3) / 1e9 / peak,
+                "alone_ms": alone["ms"],
+                "issue": {"unit": "G Fq-mul/s", "achieved": fq_mul, "peak": ceiling, "frac": fq_mul / ceiling,
+                          "note": f"G1 accumulate alone: {alone['terms']} terms x {alone['windows']} windows (c = {alone['window_bits']}) x 10 "
+                                  f"Montgomery products; peak = {ceiling_src}"}})
         if world == 1 and not args.no_cpu_baseline:
             t, cores = cpu_party_time(log_n)
             out["cpu_baseline"] = {"value": 1.0 / (3.0 * t), "unit": "proofs/s", "cores": cores, "kind": "port",
