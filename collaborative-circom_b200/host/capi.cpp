@@ -12,6 +12,7 @@
 #include "formats.hpp"
 #include "plonk.hpp"
 #include "serialize.hpp"
+#include "verify_json.hpp"
 
 using namespace cohost;
 
@@ -978,4 +979,25 @@ extern "C" int cohost_split_witness_files(const char* witness_path, const char* 
       if (wr != img.size()) throw Error("short write on " + path);
     }
   });
+}
+
+// ------------------------------------------------------------------------------------------------ Groth16 verification (pairing.hpp)
+// *ok = 1 accepted, 0 rejected by the pairing check.  A non-zero return is a malformed input (bad counts, a point off the curve or
+// outside the subgroup, unparsable JSON) -- where the reference fails while deserialising, before Groth16::verify runs.  No GPU needed.
+// vk: alpha_g1 | beta_g2 | gamma_g2 | delta_g2 packed affine Montgomery; ic: n_ic G1 points; proof: A | B | C; pub: n_ic - 1 Montgomery Fr.
+extern "C" int cohost_groth16_verify(int curve, const void* vk, const void* ic, size_t n_ic, const void* proof, const void* pub, int* ok) {
+  if (!vk || !ic || !proof || !ok || (n_ic > 1 && !pub)) return fail("cohost_groth16_verify: null argument");
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_groth16_verify: unknown curve");
+  return guarded([&] {
+    const size_t lq = curve == COCG_BN254 ? 4 : 6;
+    const uint64_t* v = (const uint64_t*)vk;
+    VerifyInput in{v, v + 2 * lq, v + 6 * lq, v + 10 * lq, (const uint64_t*)ic, n_ic, (const uint64_t*)proof, (const uint64_t*)pub};
+    *ok = groth16_verify(curve, in) ? 1 : 0;
+  });
+}
+// `co-circom verify groth16 --vk verification_key.json --proof proof.json --public-input public.json` (co-circom.rs:640-720)
+extern "C" int cohost_groth16_verify_json(const char* vk_json, size_t vk_len, const char* proof_json, size_t proof_len, const char* public_json,
+                                          size_t public_len, int* ok) {
+  if (!vk_json || !proof_json || !public_json || !ok) return fail("cohost_groth16_verify_json: null argument");
+  return guarded([&] { *ok = groth16_verify_json(vk_json, vk_len, proof_json, proof_len, public_json, public_len) ? 1 : 0; });
 }

@@ -27,6 +27,7 @@ HOST_SYMBOLS = [
     "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3", "cohost_rep3_set_mpc_exchange",
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
+    "cohost_groth16_verify", "cohost_groth16_verify_json",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -110,6 +111,8 @@ def load_host():
     L.cohost_shared_witness_decode.argtypes = [ci, vp, sz, ci, ctypes.POINTER(sz), ctypes.POINTER(sz), vp, pvp]
     L.cohost_split_witness_rep3.argtypes = [ci, ci, vp, sz, vp, pvp, pvp]
     L.cohost_r1cs_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(sz)]
+    L.cohost_groth16_verify.argtypes = [ci, vp, vp, sz, vp, vp, ctypes.POINTER(ci)]
+    L.cohost_groth16_verify_json.argtypes = [ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.POINTER(ci)]
     L.cohost_split_witness_files.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ci, ci, ci, vp, ctypes.c_char_p, ci]
     _host = L
     return L
@@ -182,6 +185,23 @@ def split_witness_rep3(curve: int, witness, seed: bytes, device: int = 0):
     sb = ctypes.create_string_buffer(seed, 64)
     _ck(L.cohost_split_witness_rep3(curve, device, w.ctypes.data, n, sb, A, B))
     return list(zip(oa, ob))
+
+
+def groth16_verify_json(vk_json: str, proof_json: str, public_json: str) -> bool:
+    """`co-circom verify groth16`: True = accepted, False = rejected by the pairing check; CocgError for malformed input."""
+    ok = ci(0)
+    a, b, c = vk_json.encode(), proof_json.encode(), public_json.encode()
+    _ck(load_host().cohost_groth16_verify_json(a, len(a), b, len(b), c, len(c), ctypes.byref(ok)))
+    return bool(ok.value)
+
+
+def groth16_verify(curve: int, vk, ic, proof, pub) -> bool:
+    """Binary form: vk = alpha_g1 | beta_g2 | gamma_g2 | delta_g2, ic = (n_ic, 2 lq), proof = A | B | C, pub = (n_ic - 1, 4), all Montgomery."""
+    ok = ci(0)
+    v, i, p, u = _c(vk), _c(ic), _c(proof), _c(pub)
+    lq = 4 if curve == _lib.BN254 else 6
+    _ck(load_host().cohost_groth16_verify(curve, v.ctypes.data, i.ctypes.data, i.size // (2 * lq), p.ctypes.data, u.ctypes.data, ctypes.byref(ok)))
+    return bool(ok.value)
 
 
 def r1cs_info(path: str) -> dict:

@@ -152,6 +152,13 @@ COHOST_API int cohost_r1cs_info(const char* path, size_t* info);
  * protocol 0 = REP3 (threshold 1, 3 parties), 1 = Shamir; the random part comes from the GPU PRF keyed by seed (32 * max(2, threshold) bytes). */
 COHOST_API int cohost_split_witness_files(const char* witness_path, const char* r1cs_path, int protocol, int curve, int threshold, int num_parties,
                                           const uint8_t* seed, const char* out_dir, int device);
+/* Groth16 verification on the host (pairing over BN254 / BLS12-381; no GPU needed): the check the reference runs after every proof
+ * (co-groth16/src/verifier.rs:23-43) and behind `co-circom verify` (co-circom/src/bin/co-circom.rs:640-720).  *ok = 1 accepted, 0 rejected;
+ * a non-zero return means malformed input (counts, a point off the curve or outside the subgroup, unparsable JSON).
+ * vk: alpha_g1 | beta_g2 | gamma_g2 | delta_g2 packed affine Montgomery; ic: n_ic G1 points; proof: A | B | C; pub: n_ic - 1 Montgomery Fr. */
+COHOST_API int cohost_groth16_verify(int curve, const void* vk, const void* ic, size_t n_ic, const void* proof, const void* pub, int* ok);
+COHOST_API int cohost_groth16_verify_json(const char* vk_json, size_t vk_len, const char* proof_json, size_t proof_len, const char* public_json,
+                                          size_t public_len, int* ok);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 

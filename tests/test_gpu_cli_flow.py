@@ -52,6 +52,13 @@ def test_split_witness_then_generate_proof(cocg, tmp_path, curve, circ):
     vk = formats.vk_from_json(open(os.path.join(d, "verification_key.json")).read())
     assert groth16.verify(vk, A, B, C, public)
     assert not groth16.verify(vk, A, B, C, [(public[0] + 1) % c.r] + public[1:])
+    # and `co-circom verify` (the product's own host pairing) reaches the same verdicts
+    cli.main(["verify", "groth16", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", pub_out, "--curve", cname])
+    bad_pub = str(tmp_path / "bad_public.json")
+    json.dump([str((public[0] + 1) % c.r)] + [str(v) for v in public[1:]], open(bad_pub, "w"))
+    with pytest.raises(SystemExit) as e:
+        cli.main(["verify", "groth16", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", bad_pub, "--curve", cname])
+    assert e.value.code == 1
 
 
 def test_split_witness_shamir_files_reconstruct(cocg, tmp_path):

@@ -6,6 +6,8 @@ sub-commands and flag names as /root/reference/co-circom/co-circom/src/lib.rs:10
                   -> DIR/<W>.<i>.shared                                   (co-circom.rs:160-256)
   generate-proof  groth16 --witness S0.shared [S1.shared S2.shared] --zkey K.zkey --protocol REP3 --curve ... --out proof.json
                   [--public-input public.json]                              (co-circom.rs:455-636)
+  verify          groth16 --proof proof.json --vk verification_key.json --public-input public.json --curve ...
+                  exit code 0 = accepted, 1 = rejected                      (co-circom.rs:640-720; host pairing, no GPU)
 
 Differences, by design: the reference runs ONE party per process and joins them over QUIC (mpc-net, out of scope); here
 `generate-proof` takes the three parties' share files and runs them as three threads of one process on one B200, joined by the
@@ -62,6 +64,20 @@ def generate_proof(a):
     zk.close()
 
 
+def verify(a):
+    if a.proof_system != "groth16":
+        sys.exit("only groth16 is built")
+    vk, proof, pub = (open(p).read() for p in (a.vk, a.proof, a.public_input))
+    import json
+    if json.loads(vk).get("curve") != {"BN254": "bn128", "BLS12-381": "bls12381"}[a.curve]:
+        sys.exit("the verification key is over a different curve")
+    if cocg.groth16_verify_json(vk, proof, pub):
+        print("Proof verified successfully")
+        return
+    print("Proof verification failed")
+    sys.exit(1)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="co-circom")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -84,6 +100,13 @@ def main(argv=None):
     gp.add_argument("--public-input")
     gp.add_argument("-t", "--threshold", type=int, default=1)
     gp.set_defaults(fn=generate_proof)
+    vf = sub.add_parser("verify")
+    vf.add_argument("proof_system", choices=["groth16", "plonk"])
+    vf.add_argument("--proof", required=True)
+    vf.add_argument("--vk", required=True)
+    vf.add_argument("--public-input", required=True)
+    vf.add_argument("--curve", required=True, choices=list(CURVES))
+    vf.set_defaults(fn=verify)
     a = ap.parse_args(argv)
     try:
         a.fn(a)
