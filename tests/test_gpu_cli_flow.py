@@ -94,6 +94,23 @@ def test_split_witness_shamir_files_reconstruct(cocg, tmp_path):
     assert interpolate([0, 1]) != want
 
 
+def test_shamir_files_to_verified_proof(cocg, tmp_path):
+    """SHAMIR (3, 1): split-witness -> generate-proof -> verify, all through the CLI; and the oracle's verifier agrees."""
+    d = os.path.join(G, "groth16", "bn254", "poseidon")
+    cli = _cli()
+    cli.main(["split-witness", "--witness", os.path.join(d, "witness.wtns"), "--r1cs", os.path.join(d, "circuit.r1cs"), "--protocol", "SHAMIR",
+              "--curve", "BN254", "--out-dir", str(tmp_path), "-t", "1", "-n", "3"])
+    shares = [str(tmp_path / f"witness.wtns.{i}.shared") for i in range(3)]
+    out, pub_out = str(tmp_path / "proof.json"), str(tmp_path / "public.json")
+    cli.main(["generate-proof", "groth16", "--witness", *shares, "--zkey", os.path.join(d, "circuit.zkey"), "--protocol", "SHAMIR", "-t", "1",
+              "--curve", "BN254", "--out", out, "--public-input", pub_out])
+    cli.main(["verify", "groth16", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", pub_out, "--curve", "BN254"])
+    _, A, B, C = formats.proof_from_json(open(out).read())
+    vk = formats.vk_from_json(open(os.path.join(d, "verification_key.json")).read())
+    assert groth16.verify(vk, A, B, C, [int(x) for x in json.load(open(pub_out))])
+    assert json.load(open(pub_out)) == json.load(open(os.path.join(d, "public.json")))
+
+
 def test_cli_rejects_bad_arguments(cocg, tmp_path):
     cli = _cli()
     d = os.path.join(G, "groth16", "bn254", "multiplier2")

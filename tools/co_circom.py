@@ -4,8 +4,8 @@ sub-commands and flag names as /root/reference/co-circom/co-circom/src/lib.rs:10
 
   split-witness   --witness W.wtns --r1cs C.r1cs --protocol REP3|SHAMIR --curve BN254|BLS12-381 --out-dir DIR [-t T] [-n N]
                   -> DIR/<W>.<i>.shared                                   (co-circom.rs:160-256)
-  generate-proof  groth16 --witness S0.shared [S1.shared S2.shared] --zkey K.zkey --protocol REP3 --curve ... --out proof.json
-                  [--public-input public.json]                              (co-circom.rs:455-636)
+  generate-proof  groth16 --witness S0.shared S1.shared S2.shared [...] --zkey K.zkey --protocol REP3|SHAMIR [-t T] --curve ...
+                  --out proof.json [--public-input public.json]             (co-circom.rs:455-636)
   verify          groth16 --proof proof.json --vk verification_key.json --public-input public.json --curve ...
                   exit code 0 = accepted, 1 = rejected                      (co-circom.rs:640-720; host pairing, no GPU)
 
@@ -35,22 +35,27 @@ def split_witness(a):
 def generate_proof(a):
     if a.proof_system != "groth16":
         sys.exit("only groth16 is built (CoPlonk: round 1 only, see DESIGN.md)")
-    if a.protocol != "REP3":
-        sys.exit("generate-proof from share files is built for REP3 (Shamir sessions take shares through the C ABI)")
-    if len(a.witness) != 3:
+    rep3 = a.protocol == "REP3"
+    if rep3 and len(a.witness) != 3:
         sys.exit("REP3 needs the three parties' share files (one process plays all three parties)")
+    if not rep3 and len(a.witness) <= 2 * a.threshold:
+        sys.exit("Shamir needs the share files of all n > 2t parties (one process plays all of them)")
     curve = CURVES[a.curve]
     zk = cocg.Groth16ZKey.from_file(a.zkey)
     pubs, wa, wb = [], [], []
     for path in a.witness:
-        pub, (ca, cb) = cocg.shared_witness_decode(curve, open(path, "rb").read(), 2)
+        pub, comps = cocg.shared_witness_decode(curve, open(path, "rb").read(), 2 if rep3 else 1)
         pubs.append(pub)
-        wa.append(ca)
-        wb.append(cb)
-    if any(not (p == pubs[0]).all() for p in pubs[1:]):
+        wa.append(comps[0])
+        wb.append(comps[-1])
+    if any(p.shape != pubs[0].shape or not (p == pubs[0]).all() for p in pubs[1:]):
         sys.exit("the share files disagree on the public inputs")
-    sess = cocg.Rep3Session(zk, seeds=os.urandom(96))
-    proofs = sess.prove(pubs[0], wa, wb)
+    if rep3:
+        sess = cocg.Rep3Session(zk, seeds=os.urandom(96))
+        proofs = sess.prove(pubs[0], wa, wb)
+    else:
+        sess = cocg.ShamirSession(zk, len(a.witness), a.threshold)
+        proofs, _ = sess.prove(pubs[0], wa)
     if any(not (p == proofs[0]).all() for p in proofs[1:]):
         sys.exit("the parties opened different proofs")
     with open(a.out, "w") as f:
