@@ -44,18 +44,32 @@ template <class P> COCG_HD Fp2<P> f_sub(const Fp2<P>& a, const Fp2<P>& b) { retu
 template <class P> COCG_HD Fp2<P> f_dbl(const Fp2<P>& a) { return Fp2<P>{fp_add(a.c0, a.c0), fp_add(a.c1, a.c1)}; }
 template <class P> COCG_HD Fp2<P> f_neg(const Fp2<P>& a) { return Fp2<P>{fp_neg(a.c0), fp_neg(a.c1)}; }
 template <class P>
-COCG_HD Fp2<P> f_mul(const Fp2<P>& a, const Fp2<P>& b) {  // Karatsuba, u^2 = -1
+COCG_HD Fp2<P> f2_mul_body(const Fp2<P>& a, const Fp2<P>& b) {  // Karatsuba, u^2 = -1
   Fp<P> v0 = fp_mul(a.c0, b.c0);
   Fp<P> v1 = fp_mul(a.c1, b.c1);
   Fp<P> s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
   return Fp2<P>{fp_sub(v0, v1), fp_sub(fp_sub(s, v0), v1)};
 }
 template <class P>
-COCG_HD Fp2<P> f_sqr(const Fp2<P>& a) {  // (a0+a1)(a0-a1) + 2 a0 a1 u
+COCG_HD Fp2<P> f2_sqr_body(const Fp2<P>& a) {  // (a0+a1)(a0-a1) + 2 a0 a1 u
   Fp<P> t = fp_mul(a.c0, a.c1);
   Fp<P> r0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
   return Fp2<P>{r0, fp_add(t, t)};
 }
+#if defined(__CUDA_ARCH__)
+// On the device the Fq2 product and square are CALLED, operands and result by value (registers), not inlined: a fully inlined G2
+// mixed addition is ~110 KB of SASS, more than the instruction cache holds (ncu: icc hit rate 80 %, `no_instruction` the second
+// largest stall), while the three base-field products inside one call still interleave.
+template <class P>
+__device__ __noinline__ Fp2<P> f2_mul_call(Fp2<P> a, Fp2<P> b) { return f2_mul_body(a, b); }
+template <class P>
+__device__ __noinline__ Fp2<P> f2_sqr_call(Fp2<P> a) { return f2_sqr_body(a); }
+template <class P> COCG_D Fp2<P> f_mul(const Fp2<P>& a, const Fp2<P>& b) { return f2_mul_call<P>(a, b); }
+template <class P> COCG_D Fp2<P> f_sqr(const Fp2<P>& a) { return f2_sqr_call<P>(a); }
+#else
+template <class P> COCG_HD Fp2<P> f_mul(const Fp2<P>& a, const Fp2<P>& b) { return f2_mul_body(a, b); }
+template <class P> COCG_HD Fp2<P> f_sqr(const Fp2<P>& a) { return f2_sqr_body(a); }
+#endif
 
 template <class P>
 COCG_HD Fp2<P> f_inv(const Fp2<P>& a) {  // conj(a) / (a0^2 + a1^2)
