@@ -281,13 +281,16 @@ static inline int msm_bucket_slot(int group) { return group == COCG_G1 ? 7 : 14;
 // (BN254 G2, 2^20 terms, ms): 7.6 as is; 64-thread blocks (5 per SM) 8.08; capped at 168 registers (3 blocks per SM, 156 B of
 // spills) 8.23.  G1 capped at 96 registers (5 blocks per SM): 2.12, unchanged.
 constexpr int kAccumulateThreads = 128;
+// After the Fq2 product became a call (ec.cuh) the BN254 G2 instantiation is occupancy-limited rather than fetch-limited: capping it at
+// 128 registers (4 blocks per SM, 456 B of L1-resident spills) measured 7.01 -> 6.52 ms at 2^20 terms; 3 blocks 6.67, 5 blocks 6.82.
+template <class F> constexpr int kAccumulateMinBlocks = sizeof(F) == 64 ? 4 : 1;
 // One thread per bucket, buckets taken in descending size order so that the lanes of a warp finish together (ncu: 31.7 of 32
 // lanes active, fmaheavy pipe 90 % busy at 2^19 buckets of ~26 points).
 struct HeavyRec {
   uint32_t bucket, first_chunk, nchunks;
 };
 template <class F>
-__global__ void __launch_bounds__(kAccumulateThreads) msm_accumulate_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(kAccumulateThreads, kAccumulateMinBlocks<F>) msm_accumulate_kernel(const void* __restrict__ table, size_t tstride, const uint32_t* __restrict__ sorted,
                                                               const uint32_t* __restrict__ start, const uint32_t* __restrict__ order, uint32_t nbuckets,
                                                               XYZZ<F>* __restrict__ buckets, HeavyRec* __restrict__ heavy_list,
                                                               uint32_t* __restrict__ chunk_owner,
