@@ -254,6 +254,10 @@ class PlonkZKey:
         self.additions = []       # (signal_id1, signal_id2, factor1, factor2), factors canonical
         self.map_a = self.map_b = self.map_c = None
         self.p_tau = None         # domain_size + 6 G1 points (zkey.rs:222-225)
+        self.k1 = self.k2 = 0
+        self.vk_points = {}       # qm, ql, qr, qo, qc, s1, s2, s3 (G1 affine)
+        self.x_2 = None
+        self.sigma = None         # [(coefficients, 4n extended evaluations)] x 3 when section 12 is present
 
 
 def parse_plonk_zkey(data: bytes) -> PlonkZKey:
@@ -273,6 +277,19 @@ def parse_plonk_zkey(data: bytes) -> PlonkZKey:
         raise ValueError("domain size must be a power of two")
     zk.pow = zk.domain_size.bit_length() - 1
     rri = _mont_inv(c.Rr, c.r)
+    rqi_h = _mont_inv(c.Rq, c.q)
+    # VerifyingKey::new, plonk/zkey.rs:329-355: k1, k2 (Montgomery limbs), Qm Ql Qr Qo Qc S1 S2 S3 in G1, X_2 in G2
+    zk.k1, zk.k2 = (rd.int_le(n8r) * rri) % c.r, (rd.int_le(n8r) * rri) % c.r
+    zk.vk_points = {name: read_g1(rd, c, rqi_h) for name in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")}
+    zk.x_2 = read_g2(rd, c, rqi_h)
+    if 12 in sec:                                      # sigma1..3: n coefficients + 4n extended evaluations each, zkey.rs:186-208, 250-262
+        n = zk.domain_size
+        rd12 = _Rd(sec[12])
+        zk.sigma = []
+        for _ in range(3):
+            coeffs = [(rd12.int_le(n8r) * rri) % c.r for _ in range(n)]
+            evals = [(rd12.int_le(n8r) * rri) % c.r for _ in range(4 * n)]
+            zk.sigma.append((coeffs, evals))
     rd = _Rd(sec[3])                                   # additions_indices, zkey.rs:159-177: factors are Montgomery limbs
     for _ in range(zk.n_additions):
         s1, s2 = rd.u32(), rd.u32()

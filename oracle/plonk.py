@@ -7,6 +7,7 @@ blinding hook (`Round1Challenges::deterministic`, b_i = i, round1.rs:101-108) --
 from __future__ import annotations
 
 from .formats import PlonkZKey
+from .keccak import keccak256
 from .ntt import roots_of_unity, intt
 
 
@@ -30,15 +31,19 @@ def witness_with_additions(zk: PlonkZKey, values):
     return get
 
 
+def wire_buffers(zk: PlonkZKey, values):
+    """buffer_a/b/c (round1.rs:121-166): the wire values per gate, zero-padded to the domain."""
+    get = witness_with_additions(zk, values)
+    return [[get(i) for i in m] + [0] * (zk.domain_size - zk.n_constraints) for m in (zk.map_a, zk.map_b, zk.map_c)]
+
+
 def wire_polynomials(zk: PlonkZKey, values, blinders):
     """compute_wire_polynomials (round1.rs:121-209): coefficients of the blinded a(X), b(X), c(X), length n + 2 each."""
     r = zk.curve.r
-    get = witness_with_additions(zk, values)
     _, roots = roots_of_unity(zk.curve)
     omega = roots[zk.pow]
     out = []
-    for k, m in enumerate((zk.map_a, zk.map_b, zk.map_c)):
-        buf = [get(i) for i in m] + [0] * (zk.domain_size - zk.n_constraints)
+    for k, buf in enumerate(wire_buffers(zk, values)):
         poly = intt(buf, omega, r)
         b_lo, b_hi = blinders[2 * k], blinders[2 * k + 1]      # blind_coefficients with coeff_rev = b[2k..2k+2] (lib.rs:140-158)
         poly[0] = (poly[0] - b_hi) % r
@@ -52,3 +57,82 @@ def round1_commitments(zk: PlonkZKey, values, blinders=tuple(range(11))):
     c = zk.curve
     polys = wire_polynomials(zk, values, blinders)
     return [c.to_affine(c.msm(zk.p_tau[:len(p)], p, 1), 1) for p in polys]
+
+
+# ------------------------------------------------------------------------------------------------ transcript + round 2
+class Keccak256Transcript:
+    """co-plonk/src/types.rs:125-176: big-endian field bytes into Keccak-256; infinity = 2 x byte_len zero bytes."""
+
+    def __init__(self, curve):
+        self.c = curve
+        self.buf = bytearray()
+        self.qlen = (curve.q.bit_length() + 7) // 8
+        self.rlen = (curve.r.bit_length() + 7) // 8
+
+    def add_scalar(self, v):
+        self.buf += int(v % self.c.r).to_bytes(self.rlen, "big")
+
+    def add_point(self, P):
+        if P is None:
+            self.buf += bytes(2 * self.qlen)
+        else:
+            self.buf += int(P[0]).to_bytes(self.qlen, "big") + int(P[1]).to_bytes(self.qlen, "big")
+
+    def get_challenge(self):
+        return int.from_bytes(keccak256(bytes(self.buf)), "big") % self.c.r   # from_be_bytes_mod_order
+
+
+def round2_challenges(zk: PlonkZKey, values, commits):
+    """beta, gamma (round2.rs:251-276; the verifier derives them the same way, plonk.rs:52-76): vk points, public inputs, round-1 commitments."""
+    c = zk.curve
+    t = Keccak256Transcript(c)
+    for name in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3"):
+        t.add_point(zk.vk_points[name])
+    for v in values[1:zk.n_public + 1]:                     # the leading zero is dropped after round 1 (round1.rs:42-46)
+        t.add_scalar(v % c.r)
+    for P in commits:
+        t.add_point(P)
+    beta = t.get_challenge()
+    t = Keccak256Transcript(c)
+    t.add_scalar(beta)
+    return beta, t.get_challenge()
+
+
+def z_polynomial(zk: PlonkZKey, values, beta, gamma, blinders=tuple(range(11))):
+    """compute_z (round2.rs:146-236) with the plain driver: grand product of the permutation argument over the domain, rotated by
+    one, iFFT, blinded with b[6..9]: n + 3 coefficients."""
+    c = zk.curve
+    r, n = c.r, zk.domain_size
+    a, b, cc = wire_buffers(zk, values)
+    _, roots = roots_of_unity(c)
+    omega = roots[zk.pow]
+    num, den = [], []
+    w = 1
+    for i in range(n):
+        betaw = beta * w % r
+        n_i = (a[i] + betaw + gamma) * (b[i] + zk.k1 * betaw + gamma) % r * (cc[i] + zk.k2 * betaw + gamma) % r
+        d_i = (a[i] + beta * zk.sigma[0][1][4 * i] + gamma) * (b[i] + beta * zk.sigma[1][1][4 * i] + gamma) % r \
+            * (cc[i] + beta * zk.sigma[2][1][4 * i] + gamma) % r
+        num.append(n_i)
+        den.append(d_i)
+        w = w * omega % r
+    for i in range(1, n):                                  # array_prod_mul: prefix products
+        num[i] = num[i] * num[i - 1] % r
+        den[i] = den[i] * den[i - 1] % r
+    buf = [x * pow(d, -1, r) % r for x, d in zip(num, den)]
+    buf = buf[-1:] + buf[:-1]                              # rotate_right(1)
+    poly = intt(buf, omega, r)
+    b6, b7, b8 = blinders[6:9]                             # blind_coefficients(poly, b[6..9]): coefficients given in reverse
+    poly[0] = (poly[0] - b8) % r
+    poly[1] = (poly[1] - b7) % r
+    poly[2] = (poly[2] - b6) % r
+    return poly + [b8 % r, b7 % r, b6 % r]
+
+
+def round2_commitment(zk: PlonkZKey, values, blinders=tuple(range(11))):
+    """[z]_1 (round2.rs:277-289) after round 1 with the same blinders; returns (beta, gamma, commit_z affine)."""
+    c = zk.curve
+    commits = round1_commitments(zk, values, blinders)
+    beta, gamma = round2_challenges(zk, values, commits)
+    z = z_polynomial(zk, values, beta, gamma, blinders)
+    return beta, gamma, c.to_affine(c.msm(zk.p_tau[:len(z)], z, 1), 1)

@@ -105,11 +105,39 @@ def plonk_round1():
     return out
 
 
+def plonk_round2():
+    """Bit-exact round-2 material of the reference: commit_z of test_round2_multiplier2 (co-plonk/src/round2.rs:326-355, blinders
+    b_i = i), the transcript KAT (types.rs:190-226) and the verifier's beta / gamma / alpha / xi for the shipped snarkjs proof
+    (plonk.rs:285-330).  Copies the full multiplier2 Plonk zkey (14.7 KB: sigma evaluations and vk points are needed from round 2 on),
+    its snarkjs proof and public inputs."""
+    out = {}
+    text = open(os.path.join(REF, "co-circom/co-plonk/src/round2.rs")).read()
+    i = text.index("fn test_round2_multiplier2()")
+    pts = re.findall(r'from_xy!\(\s*"(\d+)",\s*"(\d+)"\s*\)', text[i:])
+    out["commit_z"] = pts[0]
+    text = open(os.path.join(REF, "co-circom/co-plonk/src/types.rs")).read()
+    i = text.index("fn test_keccak_transcript()")
+    out["transcript"] = {"points": re.findall(r'to_g1_bn254!\(\s*"(\d+)",\s*"(\d+)"\s*\)', text[i:]),
+                         "scalars_and_challenge": re.findall(r'from_str\(\s*"(\d+)",?\s*\)', text[i:])}
+    text = open(os.path.join(REF, "co-circom/co-plonk/src/plonk.rs")).read()
+    i = text.index("fn calculate_verifier_challenges()")
+    vals = re.findall(r'challenges\.(\w+),\s*ark_bn254::Fr::from_str\(\s*"(\d+)"', text[i:])
+    out["verifier_challenges"] = {k: v for k, v in vals}
+    src = os.path.join(REF, "test_vectors", "Plonk", "bn254", "multiplier2")
+    dst = os.path.join(OUT, "plonk", "bn254", "multiplier2")
+    for f in ("circuit.zkey", "circom.proof", "public.json"):
+        shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     copy_fixtures()
     with open(os.path.join(OUT, "plonk_round1_kats.json"), "w") as f:
         json.dump(plonk_round1(), f, indent=1)
+    with open(os.path.join(OUT, "plonk_round2_kats.json"), "w") as f:
+        json.dump(plonk_round2(), f, indent=1)
     with open(os.path.join(OUT, "zkey_kats.json"), "w") as f:
         json.dump(zkey_kats(), f, indent=1)
     with open(os.path.join(OUT, "rep3_mul_vec_bn.json"), "w") as f:
