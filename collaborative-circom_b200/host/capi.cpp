@@ -13,6 +13,7 @@
 #include "plonk.hpp"
 #include "serialize.hpp"
 #include "verify_json.hpp"
+#include "plonk_verify.hpp"
 
 using namespace cohost;
 
@@ -1000,4 +1001,11 @@ extern "C" int cohost_groth16_verify_json(const char* vk_json, size_t vk_len, co
                                           size_t public_len, int* ok) {
   if (!vk_json || !proof_json || !public_json || !ok) return fail("cohost_groth16_verify_json: null argument");
   return guarded([&] { *ok = groth16_verify_json(vk_json, vk_len, proof_json, proof_len, public_json, public_len) ? 1 : 0; });
+}
+
+// `co-circom verify plonk` (co-plonk/src/plonk.rs:123-283).  challenges_out: NULL, or 6 Montgomery Fr = alpha, beta, gamma, xi, v[0], u.
+extern "C" int cohost_plonk_verify_json(const char* vk_json, size_t vk_len, const char* proof_json, size_t proof_len, const char* public_json,
+                                        size_t public_len, void* challenges_out, int* ok) {
+  if (!vk_json || !proof_json || !public_json || !ok) return fail("cohost_plonk_verify_json: null argument");
+  return guarded([&] { *ok = plonk_verify_json(vk_json, vk_len, proof_json, proof_len, public_json, public_len, (uint64_t*)challenges_out) ? 1 : 0; });
 }

@@ -176,6 +176,8 @@ struct Bn254Pairing {
   }
   static E::Fq b1() { static const uint32_t v[8] = BN254_G1_B; E::Fq r; memcpy(r.l, v, sizeof(v)); return r; }
   static E::Fq2 b2() { static const uint32_t c0[8] = BN254_G2_B_C0, c1[8] = BN254_G2_B_C1; return E::load_f2(c0, c1); }
+  static E::G1 g1_generator() { static const uint32_t g[2][8] = BN254_G1_GEN; E::G1 r; memcpy(&r, g, sizeof(r)); return r; }
+  static E::G2 g2_generator() { static const uint32_t g[4][8] = BN254_G2_GEN; E::G2 r; memcpy(&r, g, sizeof(r)); return r; }
 };
 struct Bls381Pairing {
   using E = PairingEngine<cocg::Bls381FqP, 1, false>;
@@ -193,6 +195,8 @@ struct Bls381Pairing {
   }
   static E::Fq b1() { static const uint32_t v[12] = BLS381_G1_B; E::Fq r; memcpy(r.l, v, sizeof(v)); return r; }
   static E::Fq2 b2() { static const uint32_t c0[12] = BLS381_G2_B_C0, c1[12] = BLS381_G2_B_C1; return E::load_f2(c0, c1); }
+  static E::G1 g1_generator() { static const uint32_t g[2][12] = BLS381_G1_GEN; E::G1 r; memcpy(&r, g, sizeof(r)); return r; }
+  static E::G2 g2_generator() { static const uint32_t g[4][12] = BLS381_G2_GEN; E::G2 r; memcpy(&r, g, sizeof(r)); return r; }
 };
 
 // k * p for a canonical little-endian scalar of 8 x 32 bits (double-and-add, XYZZ accumulators)

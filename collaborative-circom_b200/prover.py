@@ -27,7 +27,7 @@ HOST_SYMBOLS = [
     "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3", "cohost_rep3_set_mpc_exchange",
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
-    "cohost_groth16_verify", "cohost_groth16_verify_json",
+    "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -113,6 +113,7 @@ def load_host():
     L.cohost_r1cs_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(sz)]
     L.cohost_groth16_verify.argtypes = [ci, vp, vp, sz, vp, vp, ctypes.POINTER(ci)]
     L.cohost_groth16_verify_json.argtypes = [ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.POINTER(ci)]
+    L.cohost_plonk_verify_json.argtypes = [ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.c_char_p, sz, vp, ctypes.POINTER(ci)]
     L.cohost_split_witness_files.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ci, ci, ci, vp, ctypes.c_char_p, ci]
     _host = L
     return L
@@ -193,6 +194,15 @@ def groth16_verify_json(vk_json: str, proof_json: str, public_json: str) -> bool
     a, b, c = vk_json.encode(), proof_json.encode(), public_json.encode()
     _ck(load_host().cohost_groth16_verify_json(a, len(a), b, len(b), c, len(c), ctypes.byref(ok)))
     return bool(ok.value)
+
+
+def plonk_verify_json(vk_json: str, proof_json: str, public_json: str, want_challenges: bool = False):
+    """`co-circom verify plonk`.  With want_challenges also the Montgomery Fr rows alpha, beta, gamma, xi, v[0], u."""
+    ok = ci(0)
+    a, b, c = vk_json.encode(), proof_json.encode(), public_json.encode()
+    ch = np.zeros((6, 4), dtype=np.uint64)
+    _ck(load_host().cohost_plonk_verify_json(a, len(a), b, len(b), c, len(c), ch.ctypes.data if want_challenges else None, ctypes.byref(ok)))
+    return (bool(ok.value), ch) if want_challenges else bool(ok.value)
 
 
 def groth16_verify(curve: int, vk, ic, proof, pub) -> bool:

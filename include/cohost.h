@@ -159,6 +159,10 @@ COHOST_API int cohost_split_witness_files(const char* witness_path, const char* 
 COHOST_API int cohost_groth16_verify(int curve, const void* vk, const void* ic, size_t n_ic, const void* proof, const void* pub, int* ok);
 COHOST_API int cohost_groth16_verify_json(const char* vk_json, size_t vk_len, const char* proof_json, size_t proof_len, const char* public_json,
                                           size_t public_len, int* ok);
+/* Plonk verification on the host (co-plonk/src/plonk.rs:123-283: Keccak-256 transcript, challenges, r0 / D / E / F, one pairing equation).
+ * challenges_out: NULL, or room for 6 Montgomery Fr = alpha, beta, gamma, xi, v[0], u (the reference's challenge KAT, plonk.rs:285-350). */
+COHOST_API int cohost_plonk_verify_json(const char* vk_json, size_t vk_len, const char* proof_json, size_t proof_len, const char* public_json,
+                                        size_t public_len, void* challenges_out, int* ok);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 

@@ -133,3 +133,53 @@ def test_binary_entry_point_matches_json(cocg, curve, circ):
     assert cocg.groth16_verify(cid, vkb, ic, block, cref.fr_to_mont(c, [(p[0] + 5) % c.r] + p[1:])) is False
     # our own JSON writer round-trips into the verifier
     assert cocg.groth16_verify_json(vk, cocg.proof_to_json(cid, block), cocg.public_inputs_to_json(cid, cref.fr_to_mont(c, [1] + p))) is True
+
+
+# ------------------------------------------------------------------------------------------------ Plonk
+PLONK_CASES = [("bn254", "multiplier2"), ("bn254", "poseidon"), ("bls12_381", "multiplier2"), ("bls12_381", "poseidon")]
+
+
+def _load_plonk(curve, circ):
+    d = os.path.join(G, "plonk", curve, circ)
+    return tuple(open(os.path.join(d, f)).read() for f in ("verification_key.json", "circom.proof", "public.json"))
+
+
+@pytest.mark.parametrize("curve,circ", PLONK_CASES)
+def test_plonk_verifier_accepts_snarkjs_proofs_and_rejects_changes(cocg, curve, circ):
+    """co-plonk/src/lib.rs:255-275 (`Plonk::verify` on the shipped snarkjs proofs), here through the product's host verifier."""
+    c = CURVES[curve]
+    vk, proof, pub = _load_plonk(curve, circ)
+    assert cocg.plonk_verify_json(vk, proof, pub) is True
+    p = json.loads(pub)
+    bad = json.dumps([str((int(p[0]) + 1) % c.r)] + p[1:])
+    assert cocg.plonk_verify_json(vk, proof, bad) is False
+    pj = json.loads(proof)
+    for key in ("eval_a", "eval_zw"):
+        t = dict(pj)
+        t[key] = str((int(pj[key]) + 1) % c.r)
+        assert cocg.plonk_verify_json(vk, json.dumps(t), pub) is False
+    t = dict(pj)
+    t["Wxi"] = pj["Wxiw"]
+    assert cocg.plonk_verify_json(vk, json.dumps(t), pub) is False
+    with pytest.raises(cocg.CocgError, match="number of public inputs"):
+        cocg.plonk_verify_json(vk, proof, json.dumps(p + ["1"]))
+    off = dict(pj)
+    off["Z"] = [pj["Z"][0], str((int(pj["Z"][1]) + 1) % c.q), "1"]
+    with pytest.raises(cocg.CocgError, match="not on the curve"):
+        cocg.plonk_verify_json(vk, json.dumps(off), pub)
+
+
+def test_plonk_verifier_challenges_match_reference_kat(cocg):
+    """co-plonk/src/plonk.rs:285-350: alpha, beta, gamma, xi, v, u for the multiplier2 proof -- pins the product's Keccak-256
+    transcript (C++) literally."""
+    kat = json.load(open(os.path.join(G, "plonk_round2_kats.json")))["verifier_challenges"]
+    vk, proof, pub = _load_plonk("bn254", "multiplier2")
+    ok, ch = cocg.plonk_verify_json(vk, proof, pub, want_challenges=True)
+    assert ok
+    got = cref.fr_from_mont(BN254, ch)
+    assert got[:4] == [int(kat[k]) for k in ("alpha", "beta", "gamma", "xi")]
+    assert got[4] == int(kat["v"][0]) and got[5] == int(kat["u"])
+    # a groth16 key is not a plonk key
+    gvk, gproof, gpub = _load("bn254", "multiplier2")
+    with pytest.raises(cocg.CocgError, match="plonk|missing key"):
+        cocg.plonk_verify_json(gvk, gproof, gpub)

@@ -6,7 +6,7 @@ sub-commands and flag names as /root/reference/co-circom/co-circom/src/lib.rs:10
                   -> DIR/<W>.<i>.shared                                   (co-circom.rs:160-256)
   generate-proof  groth16 --witness S0.shared S1.shared S2.shared [...] --zkey K.zkey --protocol REP3|SHAMIR [-t T] --curve ...
                   --out proof.json [--public-input public.json]             (co-circom.rs:455-636)
-  verify          groth16 --proof proof.json --vk verification_key.json --public-input public.json --curve ...
+  verify          groth16|plonk --proof proof.json --vk verification_key.json --public-input public.json --curve ...
                   exit code 0 = accepted, 1 = rejected                      (co-circom.rs:640-720; host pairing, no GPU)
 
 Differences, by design: the reference runs ONE party per process and joins them over QUIC (mpc-net, out of scope); here
@@ -70,13 +70,12 @@ def generate_proof(a):
 
 
 def verify(a):
-    if a.proof_system != "groth16":
-        sys.exit("only groth16 is built")
     vk, proof, pub = (open(p).read() for p in (a.vk, a.proof, a.public_input))
     import json
     if json.loads(vk).get("curve") != {"BN254": "bn128", "BLS12-381": "bls12381"}[a.curve]:
         sys.exit("the verification key is over a different curve")
-    if cocg.groth16_verify_json(vk, proof, pub):
+    check = cocg.groth16_verify_json if a.proof_system == "groth16" else cocg.plonk_verify_json
+    if check(vk, proof, pub):
         print("Proof verified successfully")
         return
     print("Proof verification failed")

@@ -128,6 +128,18 @@ def plonk_round2():
     for f in ("circuit.zkey", "circom.proof", "public.json"):
         shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
         os.chmod(os.path.join(dst, f), 0o644)
+    # snarkjs Plonk proofs + keys of all four fixtures: the known-answer test of the verifier (co-plonk/src/lib.rs:255-275)
+    for curve in ("bn254", "bls12_381"):
+        for circ in ("multiplier2", "poseidon"):
+            src = os.path.join(REF, "test_vectors", "Plonk", curve, circ)
+            dst = os.path.join(OUT, "plonk", curve, circ)
+            os.makedirs(dst, exist_ok=True)
+            for f in ("circom.proof", "public.json", "verification_key.json"):
+                shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+                os.chmod(os.path.join(dst, f), 0o644)
+    v = re.search(r'challenges\.v\.to_vec\(\),\s*vec!\[(.*?)\]', text[i:], flags=re.S)
+    if v:
+        out["verifier_challenges"]["v"] = re.findall(r'"(\d+)"', v.group(1))
     return out
 
 
