@@ -258,6 +258,8 @@ class PlonkZKey:
         self.vk_points = {}       # qm, ql, qr, qo, qc, s1, s2, s3 (G1 affine)
         self.x_2 = None
         self.sigma = None         # [(coefficients, 4n extended evaluations)] x 3 when section 12 is present
+        self.selectors = None     # qm, ql, qr, qo, qc -> (coefficients, evaluations)
+        self.lagrange = None      # per public input (coefficients, evaluations)
 
 
 def parse_plonk_zkey(data: bytes) -> PlonkZKey:
@@ -282,6 +284,19 @@ def parse_plonk_zkey(data: bytes) -> PlonkZKey:
     zk.k1, zk.k2 = (rd.int_le(n8r) * rri) % c.r, (rd.int_le(n8r) * rri) % c.r
     zk.vk_points = {name: read_g1(rd, c, rqi_h) for name in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")}
     zk.x_2 = read_g2(rd, c, rqi_h)
+    def _poly_evals(section, count):                   # CircomPolynomial: n coefficients + 4n extended evaluations (zkey.rs:186-208)
+        n = zk.domain_size
+        rdp = _Rd(section)
+        out = []
+        for _ in range(count):
+            coeffs = [(rdp.int_le(n8r) * rri) % c.r for _ in range(n)]
+            evals = [(rdp.int_le(n8r) * rri) % c.r for _ in range(4 * n)]
+            out.append((coeffs, evals))
+        return out
+
+    if all(k in sec for k in (7, 8, 9, 10, 11, 13)):   # selector polynomials and the Lagrange polynomials of the public inputs
+        zk.selectors = {name: _poly_evals(sec[sid], 1)[0] for name, sid in (("qm", 7), ("ql", 8), ("qr", 9), ("qo", 10), ("qc", 11))}
+        zk.lagrange = _poly_evals(sec[13], max(zk.n_public, 1) if len(sec[13]) >= 5 * zk.domain_size * n8r * max(zk.n_public, 1) else zk.n_public)
     if 12 in sec:                                      # sigma1..3: n coefficients + 4n extended evaluations each, zkey.rs:186-208, 250-262
         n = zk.domain_size
         rd12 = _Rd(sec[12])

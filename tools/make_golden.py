@@ -137,6 +137,19 @@ def plonk_round2():
             for f in ("circom.proof", "public.json", "verification_key.json"):
                 shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
                 os.chmod(os.path.join(dst, f), 0o644)
+    # rounds 3-5 (round3.rs:553-596, round4.rs:181-247, round5.rs:391-429): [t1..3]_1, the six evaluations, [Wxi]_1, [Wxiw]_1
+    t3 = open(os.path.join(REF, "co-circom/co-plonk/src/round3.rs")).read()
+    out["commit_t"] = re.findall(r'g1_from_xy!\(\s*"(\d+)",\s*"(\d+)"\s*\)', t3[t3.index("fn test_round3_multiplier2"):])[:3]
+    t4 = open(os.path.join(REF, "co-circom/co-plonk/src/round4.rs")).read()
+    out["evals"] = dict(re.findall(r'round5\.proof\.(eval_\w+),\s*ark_bn254::Fr::from_str\(\s*"(\d+)"', t4[t4.index("fn test_round4_multiplier2"):]))
+    t5 = open(os.path.join(REF, "co-circom/co-plonk/src/round5.rs")).read()
+    out["commit_w"] = re.findall(r'g1_from_xy!\(\s*"(\d+)",\s*"(\d+)"\s*\)', t5[t5.index("fn test_round5_multiplier2"):])[:2]
+    src = os.path.join(REF, "test_vectors", "Plonk", "bls12_381", "multiplier2")
+    dst = os.path.join(OUT, "plonk", "bls12_381", "multiplier2")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("circuit.zkey", "witness.wtns"):
+        shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
     v = re.search(r'challenges\.v\.to_vec\(\),\s*vec!\[(.*?)\]', text[i:], flags=re.S)
     if v:
         out["verifier_challenges"]["v"] = re.findall(r'"(\d+)"', v.group(1))
