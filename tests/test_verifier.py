@@ -183,3 +183,35 @@ def test_plonk_verifier_challenges_match_reference_kat(cocg):
     gvk, gproof, gpub = _load("bn254", "multiplier2")
     with pytest.raises(cocg.CocgError, match="plonk|missing key"):
         cocg.plonk_verify_json(gvk, gproof, gpub)
+
+
+def test_json_readers_survive_mutated_inputs(cocg):
+    """The verifiers parse untrusted text: truncations and byte flips of the fixture files must end in a verdict or a CocgError,
+    never in a crash (the C ABI promises 0 / non-zero + cohost_last_error, nothing throws or aborts)."""
+    import random
+    rng = random.Random(2024)
+    g = _load("bn254", "multiplier2")
+    p = _load_plonk("bn254", "multiplier2")
+    outcomes = {"ok": 0, "rejected": 0, "error": 0}
+    for fn, files in ((cocg.groth16_verify_json, g), (cocg.plonk_verify_json, p)):
+        for trial in range(120):
+            docs = list(files)
+            k = rng.randrange(3)
+            text = docs[k]
+            mode = trial % 4
+            if mode == 0:
+                text = text[:rng.randrange(len(text))]
+            elif mode == 1:
+                i = rng.randrange(len(text))
+                text = text[:i] + rng.choice('{}[],:"0123456789x \\') + text[i + 1:]
+            elif mode == 2:
+                i = rng.randrange(len(text))
+                text = text[:i] + text[i + rng.randrange(1, 40):]
+            else:
+                text = text.replace('"1"', rng.choice(['"0"', '"2"', '1', '[]', '{}']), rng.randrange(1, 4))
+            docs[k] = text
+            try:
+                outcomes["ok" if fn(*docs) else "rejected"] += 1
+            except cocg.CocgError:
+                outcomes["error"] += 1
+    assert outcomes["error"] > 50 and sum(outcomes.values()) == 240
