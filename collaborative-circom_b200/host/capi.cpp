@@ -1009,3 +1009,22 @@ extern "C" int cohost_plonk_verify_json(const char* vk_json, size_t vk_len, cons
   if (!vk_json || !proof_json || !public_json || !ok) return fail("cohost_plonk_verify_json: null argument");
   return guarded([&] { *ok = plonk_verify_json(vk_json, vk_len, proof_json, proof_len, public_json, public_len, (uint64_t*)challenges_out) ? 1 : 0; });
 }
+
+// Plonk zkey header without touching a GPU: info[7] = curve, n_vars, n_public, domain_size, n_additions, n_constraints, and a bit mask of
+// the optional parts present (1 = verifying-key tail, 2 = selector sections, 4 = sigma, 8 = Lagrange).  k1k2: 2 Montgomery Fr;
+// vk_g1: Qm Ql Qr Qo Qc S1 S2 S3 packed affine Montgomery; x_2: one G2 point.  Output pointers may be NULL.
+extern "C" int cohost_plonk_zkey_header(const char* path, size_t* info, void* k1k2, void* vk_g1, void* x_2) {
+  if (!path || !info) return fail("cohost_plonk_zkey_header: null argument");
+  return guarded([&] {
+    std::vector<uint8_t> buf = read_file(path);
+    PlonkZKeyFile f(buf.data(), buf.size());
+    info[0] = (size_t)f.curve; info[1] = f.n_vars; info[2] = f.n_public; info[3] = f.domain_size; info[4] = f.n_additions; info[5] = f.n_constraints;
+    bool sels = true;
+    for (int k = 0; k < 5; k++) sels = sels && f.sel[k];
+    info[6] = (f.k1 ? 1 : 0) | (sels ? 2 : 0) | (f.sigma ? 4 : 0) | (f.lagrange ? 8 : 0);
+    if (!f.k1) return;
+    if (k1k2) { memcpy(k1k2, f.k1, 32); memcpy((char*)k1k2 + 32, f.k2, 32); }
+    if (vk_g1) memcpy(vk_g1, f.vk_g1, 8 * 2 * f.n8q);
+    if (x_2) memcpy(x_2, f.x_2, 4 * f.n8q);
+  });
+}

@@ -17,6 +17,9 @@ struct PlonkZKeyFile {
   int curve = 0;
   size_t n_vars = 0, n_public = 0, domain_size = 0, pow = 0, n_additions = 0, n_constraints = 0, n8q = 0;
   const uint8_t *additions = nullptr, *map_a = nullptr, *map_b = nullptr, *map_c = nullptr, *p_tau = nullptr;
+  const uint8_t *k1 = nullptr, *k2 = nullptr, *vk_g1 = nullptr, *x_2 = nullptr;  // header tail; nullptr when the header stops early
+  // selector / sigma / Lagrange sections (n coefficients + 4n extended evaluations per polynomial, Montgomery Fr), when present
+  const uint8_t *sel[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *sigma = nullptr, *lagrange = nullptr;
   PlonkZKeyFile(const uint8_t* data, size_t len) {
     BinFile bf(data, len, "zkey");
     auto s1 = bf.take(1);
@@ -38,6 +41,13 @@ struct PlonkZKeyFile {
     need(20);
     n_vars = BinFile::u32(p); n_public = BinFile::u32(p + 4); domain_size = BinFile::u32(p + 8);
     n_additions = BinFile::u32(p + 12); n_constraints = BinFile::u32(p + 16);
+    p += 20;
+    // VerifyingKey::new (plonk/zkey.rs:329-355): k1, k2 (Montgomery Fr), Qm Ql Qr Qo Qc S1 S2 S3 (G1, Montgomery), X_2 (G2) -- rounds 2-5
+    if ((size_t)(end - p) >= 64 + 8 * 2 * n8q + 4 * n8q) {
+      k1 = p; k2 = p + 32;
+      vk_g1 = p + 64;
+      x_2 = vk_g1 + 8 * 2 * n8q;
+    }
     if (domain_size == 0 || (domain_size & (domain_size - 1))) throw Error("zkey: invalid domain size");  // PlonkProofError::InvalidDomainSize
     while (((size_t)1 << pow) < domain_size) pow++;
     if (n_constraints > domain_size || n_vars < n_additions + n_public + 1) throw Error("zkey: inconsistent header");
@@ -51,6 +61,14 @@ struct PlonkZKeyFile {
     map_b = sec(5, n_constraints * 4, "B map");
     map_c = sec(6, n_constraints * 4, "C map");
     p_tau = sec(14, (domain_size + 6) * 2 * n8q, "p_tau");
+    const size_t poly_bytes = 5 * domain_size * 32;
+    auto opt = [&](uint32_t id, size_t bytes) -> const uint8_t* {
+      auto it = bf.sections.find(id);
+      return it != bf.sections.end() && it->second.second >= bytes ? it->second.first : nullptr;
+    };
+    for (int k = 0; k < 5; k++) sel[k] = opt(7 + k, poly_bytes);               // Qm, Ql, Qr, Qo, Qc  (zkey.rs:236-249)
+    sigma = opt(12, 3 * poly_bytes);
+    lagrange = opt(13, (n_public > 1 ? n_public : 1) * poly_bytes);
   }
 };
 

@@ -27,7 +27,7 @@ HOST_SYMBOLS = [
     "cohost_plonk_zkey_get_info", "cohost_plonk_round1_plain", "cohost_plonk_round1_rep3", "cohost_rep3_set_mpc_exchange",
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
-    "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json",
+    "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -113,6 +113,7 @@ def load_host():
     L.cohost_r1cs_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(sz)]
     L.cohost_groth16_verify.argtypes = [ci, vp, vp, sz, vp, vp, ctypes.POINTER(ci)]
     L.cohost_groth16_verify_json.argtypes = [ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.POINTER(ci)]
+    L.cohost_plonk_zkey_header.argtypes = [ctypes.c_char_p, ctypes.POINTER(sz), vp, vp, vp]
     L.cohost_plonk_verify_json.argtypes = [ctypes.c_char_p, sz, ctypes.c_char_p, sz, ctypes.c_char_p, sz, vp, ctypes.POINTER(ci)]
     L.cohost_split_witness_files.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ci, ci, ci, vp, ctypes.c_char_p, ci]
     _host = L
@@ -212,6 +213,20 @@ def groth16_verify(curve: int, vk, ic, proof, pub) -> bool:
     lq = 4 if curve == _lib.BN254 else 6
     _ck(load_host().cohost_groth16_verify(curve, v.ctypes.data, i.ctypes.data, i.size // (2 * lq), p.ctypes.data, u.ctypes.data, ctypes.byref(ok)))
     return bool(ok.value)
+
+
+def plonk_zkey_header(path: str) -> dict:
+    """Header of a Plonk zkey read by the product's C++ reader (no GPU): counts, k1 / k2, the eight G1 commitments, X_2 (Montgomery)."""
+    info = (sz * 7)()
+    _ck(load_host().cohost_plonk_zkey_header(path.encode(), info, None, None, None))
+    lq = 4 if int(info[0]) == _lib.BN254 else 6
+    k = np.zeros((2, 4), dtype=np.uint64)
+    g1 = np.zeros((8, 2 * lq), dtype=np.uint64)
+    x2 = np.zeros((1, 4 * lq), dtype=np.uint64)
+    _ck(load_host().cohost_plonk_zkey_header(path.encode(), info, k.ctypes.data, g1.ctypes.data, x2.ctypes.data))
+    out = dict(zip(("curve", "n_vars", "n_public", "domain_size", "n_additions", "n_constraints", "parts"), [int(x) for x in info]))
+    out.update(k=k, vk_g1=g1, x_2=x2)
+    return out
 
 
 def r1cs_info(path: str) -> dict:

@@ -163,6 +163,10 @@ COHOST_API int cohost_groth16_verify_json(const char* vk_json, size_t vk_len, co
  * challenges_out: NULL, or room for 6 Montgomery Fr = alpha, beta, gamma, xi, v[0], u (the reference's challenge KAT, plonk.rs:285-350). */
 COHOST_API int cohost_plonk_verify_json(const char* vk_json, size_t vk_len, const char* proof_json, size_t proof_len, const char* public_json,
                                         size_t public_len, void* challenges_out, int* ok);
+/* Plonk zkey header, host only: info[7] = curve, n_vars, n_public, domain_size, n_additions, n_constraints, parts mask (1 = verifying-key
+ * tail, 2 = selector sections, 4 = sigma, 8 = Lagrange); k1k2: 2 Montgomery Fr; vk_g1: Qm Ql Qr Qo Qc S1 S2 S3 packed affine Montgomery;
+ * x_2: G2 (circom-types/src/plonk/zkey.rs:329-420).  Output pointers may be NULL. */
+COHOST_API int cohost_plonk_zkey_header(const char* path, size_t* info, void* k1k2, void* vk_g1, void* x_2);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 

@@ -127,3 +127,24 @@ def test_r1cs_header_matches_reference_kat(cocg, curve):
     assert (info["n_wires"], info["num_inputs"]) == (zk.n_vars, zk.n_public + 1)
     with pytest.raises(cocg.CocgError, match="r1cs"):
         cocg.r1cs_info(os.path.join(G, "groth16", curve, "multiplier2", "witness.wtns"))
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bls12_381"])
+def test_plonk_zkey_header_reader_agrees_with_verification_key_json(cocg, curve):
+    """The product's C++ Plonk zkey reader (host/plonk.hpp, circom-types/src/plonk/zkey.rs:329-420) on the full multiplier2 keys: the
+    verifying-key tail of the header equals the snarkjs verification_key.json; the trimmed round-1 fixture reports no optional parts."""
+    c = CURVES[curve]
+    d = os.path.join(G, "plonk", curve, "multiplier2")
+    h = cocg.plonk_zkey_header(os.path.join(d, "circuit.zkey"))
+    vk = json.load(open(os.path.join(d, "verification_key.json")))
+    assert (h["curve"], h["n_public"], h["domain_size"], h["parts"]) == (_cid(cocg, c), vk["nPublic"], 1 << vk["power"], 15)
+    assert cref.fr_from_mont(c, h["k"]) == [int(vk["k1"]), int(vk["k2"])]
+    got = cref.g_from_mont(c, h["vk_g1"], 1)
+    for P, name in zip(got, ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3")):
+        v = vk[name]
+        assert P == (None if v[2] == "0" else (int(v[0]), int(v[1]))), name
+    x2 = vk["X_2"]
+    assert cref.g_from_mont(c, h["x_2"], 2)[0] == ((int(x2[0][0]), int(x2[0][1])), (int(x2[1][0]), int(x2[1][1])))
+    if curve == "bn254":
+        t = cocg.plonk_zkey_header(os.path.join(d, "circuit.round1.zkey"))
+        assert t["parts"] & 14 == 0 and t["n_constraints"] == h["n_constraints"]
