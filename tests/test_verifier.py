@@ -215,3 +215,27 @@ def test_json_readers_survive_mutated_inputs(cocg):
             except cocg.CocgError:
                 outcomes["error"] += 1
     assert outcomes["error"] > 50 and sum(outcomes.values()) == 240
+
+
+def test_cli_verify_subcommand_on_fixtures(cocg, tmp_path, capsys):
+    """`co-circom verify groth16|plonk --proof --vk --public-input --curve` (co-circom/src/bin/co-circom.rs:640-720) needs no GPU."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import co_circom
+    for system, sub in (("groth16", "groth16"), ("plonk", "plonk")):
+        for curve, cname in (("bn254", "BN254"), ("bls12_381", "BLS12-381")):
+            d = os.path.join(G, sub, curve, "multiplier2")
+            args = ["verify", system, "--proof", os.path.join(d, "circom.proof"), "--vk", os.path.join(d, "verification_key.json"),
+                    "--public-input", os.path.join(d, "public.json"), "--curve", cname]
+            co_circom.main(args)
+            assert "verified successfully" in capsys.readouterr().out
+            bad = tmp_path / f"{system}_{curve}_public.json"
+            pub = json.load(open(os.path.join(d, "public.json")))
+            bad.write_text(json.dumps([str(int(pub[0]) + 1)] + pub[1:]))
+            args[args.index("--public-input") + 1] = str(bad)
+            with pytest.raises(SystemExit) as e:
+                co_circom.main(args)
+            assert e.value.code == 1
+            other = "BLS12-381" if cname == "BN254" else "BN254"
+            with pytest.raises(SystemExit, match="different curve"):
+                co_circom.main(args[:-1] + [other])
