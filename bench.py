@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 BN254_R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 BLS381_R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 SEED = 0xC0C12C0D20240001
+PRF_SEEDS = bytes(range(96))  # the parties' PRF seeds: fixed HERE ONLY so that every run (and every rank) produces the same proofs
 
 
 def limbs_of(v):
@@ -237,7 +238,7 @@ def run_own(args):
     if args.protocol == "shamir":
         return run_own_shamir(args, cocg, torch, curve_id, modulus, local, (n_public, n_vars, rows, A, B), seed_bytes, rng)
     zk = cocg.Groth16ZKey(curve_id, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes, rank=rank, world=world)
-    sess = cocg.Rep3Session(zk, rank=rank, world=world)
+    sess = cocg.Rep3Session(zk, seeds=PRF_SEEDS, rank=rank, world=world)
     # witness: x = x0 + x1 + x2, party i holds (x_i, x_{i-1}) (rep3.rs:57-68); pinned host copies + resident device copies
     xs = []
     for i in range(3):
@@ -306,7 +307,7 @@ def run_own(args):
     replicas = None
     if world > 1:
         zk1 = cocg.Groth16ZKey(curve_id, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes)
-        sess1 = cocg.Rep3Session(zk1)
+        sess1 = cocg.Rep3Session(zk1, seeds=PRF_SEEDS)
         for _ in range(2):
             sess1.prove(pub, host_a, host_b)
         torch.cuda.synchronize()
@@ -420,7 +421,7 @@ def run_own_shamir(args, cocg, torch, curve_id, modulus, local, r1cs, seed_bytes
     log_n = args.log_n
     n_aux = n_vars - n_public - 1
     zk = cocg.Groth16ZKey(curve_id, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes)
-    sess = cocg.ShamirSession(zk, 3, 1)
+    sess = cocg.ShamirSession(zk, 3, 1, seeds=PRF_SEEDS)
     ctx = cocg.Context(curve_id, local)
     v, c = ctx.upload(rand_fr(n_aux, rng)), ctx.upload(rand_fr(n_aux, rng))
     r1 = pow(2, 256, modulus)

@@ -54,6 +54,8 @@ extern "C" int cocg_csr_upload_form(cocg_ctx* ctx, const uint32_t* rowptr, const
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!handle || !rowptr || (nnz && (!col || !coeff))) return fail(ctx, "cocg_csr_upload: null argument");
   if (rowptr[rows] != nnz) return fail(ctx, "cocg_csr_upload: rowptr[rows] != nnz");
+  for (size_t r = 0; r < rows; r++)  // a malformed row pointer would become an out-of-bounds read in spmv_kernel
+    if (rowptr[r] > rowptr[r + 1]) return fail(ctx, "cocg_csr_upload: rowptr is not non-decreasing");
   CsrEntry m;
   m.rows = rows; m.nnz = nnz;
   COCG_CUDA(ctx, cudaMalloc(&m.rowptr, (rows + 1) * 4));

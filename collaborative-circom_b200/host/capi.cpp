@@ -93,6 +93,10 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
     zk.pow = d->pow;
     zk.num_constraints = d->num_constraints;
     if (zk.n_vars < zk.n_public + 1) throw Error("zkey: n_vars < n_public + 1");
+    // spmv_kernel gathers z[col] without a bound: a column index past the assignment must be refused here (the reference panics on
+    // the Rust bounds check, co-groth16/src/groth16.rs:159-166)
+    for (size_t k = 0; k < d->a_nnz; k++) if (d->a_col[k] >= zk.n_vars) throw Error("zkey: column index of matrix A out of range");
+    for (size_t k = 0; k < d->b_nnz; k++) if (d->b_col[k] >= zk.n_vars) throw Error("zkey: column index of matrix B out of range");
     const size_t m = zk.n_vars, l = zk.n_public;
     const size_t g1b = 2 * lq * 8, g2b = 4 * lq * 8;
     cocg_ctx* c = zk.owner;

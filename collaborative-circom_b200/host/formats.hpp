@@ -149,6 +149,9 @@ struct Groth16ZKeyFile {
       const uint8_t* e = m.first + 4 + (size_t)i * 44;
       const uint32_t k = BinFile::u32(e), row = BinFile::u32(e + 4), sig = BinFile::u32(e + 8);
       if (row >= num_constraints) continue;
+      // the reference indexes the witness with this value and panics on the Rust bounds check; here it would become an
+      // out-of-bounds gather on the device (spmv.cu)
+      if (sig >= n_vars) throw Error("zkey: signal index out of range in the coefficient section");
       const uint32_t at = fill[k][row]++;
       col[k][at] = sig;
       memcpy(coeff_raw[k].data() + (size_t)at * 32, e + 12, 32);

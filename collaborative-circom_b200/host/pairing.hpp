@@ -254,13 +254,16 @@ bool groth16_verify_impl(const VerifyInput& in) {
     if (!on_curve(*p, b2)) throw Error("verify: G2 point is not on the curve");
     if (!scalar_mul_affine(*p, CP::order()).is_inf()) throw Error("verify: G2 point is not in the prime-order subgroup");
   }
-  for (const G1* p : {&A, &C})
+  // the reference checks EVERY proof and vk point at parse time (circom-types/src/traits.rs:160-232): alpha and the IC points as well
+  for (const G1* p : {&A, &C, &alpha})
     if (!scalar_mul_affine(*p, CP::order()).is_inf()) throw Error("verify: G1 point is not in the prime-order subgroup");
   // vk_x
+  if (!on_curve(g1(in.ic), b1) || !scalar_mul_affine(g1(in.ic), CP::order()).is_inf()) throw Error("verify: IC point is not on the curve / in the subgroup");
   cocg::XYZZ<Fq> acc = cocg::xyzz_from_affine(g1(in.ic));
   for (size_t i = 1; i < in.n_ic; i++) {
     G1 ic = g1(in.ic + i * 2 * lq);
     if (!on_curve(ic, b1)) throw Error("verify: IC point is not on the curve");
+    if (!scalar_mul_affine(ic, CP::order()).is_inf()) throw Error("verify: IC point is not in the prime-order subgroup");
     cocg::Fp<FrP> s;
     memcpy(s.l, in.pub + (i - 1) * 4, 32);
     s = cocg::fp_from_mont(s);

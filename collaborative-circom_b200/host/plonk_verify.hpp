@@ -155,8 +155,13 @@ struct PlonkVerifier {
     if (vk.n_public != pub.size()) throw Error("Invalid number of public inputs");
     const Fq b1c = CP::b1();
     for (const G1* q : {&p.a, &p.b, &p.c, &p.z, &p.t1, &p.t2, &p.t3, &p.wxi, &p.wxiw, &vk.qm, &vk.ql, &vk.qr, &vk.qo, &vk.qc, &vk.s1, &vk.s2, &vk.s3})
+    {
       if (!on_curve(*q, b1c)) throw Error("verify: G1 point is not on the curve");
+      // is_in_correct_subgroup_assuming_on_curve at deserialisation (circom-types/src/traits.rs:160-232); G1 of BLS12-381 has a cofactor
+      if (!scalar_mul_affine(*q, CP::order()).is_inf()) throw Error("verify: G1 point is not in the prime-order subgroup");
+    }
     if (!on_curve(vk.x2, CP::b2())) throw Error("verify: G2 point is not on the curve");
+    if (!scalar_mul_affine(vk.x2, CP::order()).is_inf()) throw Error("verify: G2 point is not in the prime-order subgroup");
     const Challenges ch = challenges(vk, p, pub);
     // Domains::new: root_of_unity_pow = roots_of_unity[power] (types.rs:59-99)
     Fr omega;

@@ -55,8 +55,12 @@ class JsonReader {
         switch (*p_) {
           case 'n': s.push_back('\n'); break;
           case 't': s.push_back('\t'); break;
+          case 'r': s.push_back('\r'); break;
+          case 'b': s.push_back('\b'); break;
+          case 'f': s.push_back('\f'); break;
+          case '"': case '\\': case '/': s.push_back(*p_); break;
           case 'u': throw Error("json: \\u escapes are not supported");
-          default: s.push_back(*p_);
+          default: throw Error("json: invalid escape");  // serde_json rejects anything else
         }
         p_++;
       } else {
@@ -92,6 +96,8 @@ class JsonReader {
         std::string k = string();
         if (peek() != ':') throw Error("json: expected ':'");
         p_++;
+        for (const auto& kv : v.obj)
+          if (kv.first == k) throw Error("json: duplicate key \"" + k + "\"");  // serde's derived Deserialize: `duplicate field`
         v.obj.emplace_back(std::move(k), value(depth + 1));
         char d = peek();
         p_++;
@@ -143,6 +149,8 @@ struct JsonVerifier {
     Fq x = field_from_decimal<Fq>(v.at(0).text()), y = field_from_decimal<Fq>(v.at(1).text()), z = field_from_decimal<Fq>(v.at(2).text());
     memset(out, 0, 2 * lq * 8);
     if (z.is_zero()) return;
+    // packed (0, 0) means infinity below this layer; with z != 0 it is the off-curve point (0, 0), which the reference rejects
+    if (x.is_zero() && y.is_zero()) throw Error("verify: G1 point is not on the curve");
     if (!(z == Fq::one())) {
       Fq zi = cocg::fp_inv(z), zi2 = cocg::fp_sqr(zi);
       x = cocg::fp_mul(x, zi2);
@@ -156,6 +164,7 @@ struct JsonVerifier {
     Fq2 x = f2(v.at(0)), y = f2(v.at(1)), z = f2(v.at(2));
     memset(out, 0, 4 * lq * 8);
     if (z.is_zero()) return;
+    if (x.is_zero() && y.is_zero()) throw Error("verify: G2 point is not on the curve");
     if (!(z == Fq2::one())) {
       Fq2 zi = cocg::f_inv(z), zi2 = cocg::f_sqr(zi);
       x = cocg::f_mul(x, zi2);

@@ -129,6 +129,13 @@ def _c(a, dtype=np.uint64):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def _need(cond, msg):
+    """Argument validation at the C boundary: the C side reads raw pointers, so a wrong length must raise (never `assert`, which
+    `python -O` removes)."""
+    if not cond:
+        raise CocgError(msg)
+
+
 def _sized(call):
     """Two-step writer protocol of include/cohost.h: query the length, then fill a buffer of that size."""
     n = sz(0)
@@ -177,7 +184,7 @@ def shared_witness_decode(curve: int, data: bytes, k: int):
 def split_witness_rep3(curve: int, witness, seed: bytes, device: int = 0):
     """SharedWitness::share_rep3 on the GPU: three (a, b) pairs of Montgomery Fr arrays; seed = 64 bytes."""
     L = load_host()
-    assert len(seed) == 64
+    _need(len(seed) == 64, "split_witness_rep3: seed must be 64 bytes")
     w = _c(witness).reshape(-1, 4)
     n = w.shape[0]
     oa = [np.zeros((n, 4), dtype=np.uint64) for _ in range(3)]
@@ -241,7 +248,7 @@ def split_witness_files(witness: str, r1cs: str, protocol: str, curve: int, out_
     proto = {"REP3": 0, "SHAMIR": 1}[protocol.upper()]
     need = 32 * max(2, threshold)
     seed = os.urandom(need) if seed is None else seed
-    assert len(seed) >= need
+    _need(len(seed) >= need, f"split_witness_files: seed must be at least {need} bytes")
     sb = ctypes.create_string_buffer(seed, len(seed))
     _ck(load_host().cohost_split_witness_files(witness.encode(), r1cs.encode(), proto, curve, threshold, num_parties, sb, out_dir.encode(), device))
     n = 3 if proto == 0 else num_parties
@@ -273,21 +280,22 @@ class Groth16ZKey:
         d.rank, d.world = rank, world
         d.a_rowptr, d.a_col, d.a_coeff, d.a_nnz = P(a_csr[0], np.uint32), P(a_csr[1], np.uint32), P(a_csr[2]), len(a_csr[1])
         d.b_rowptr, d.b_col, d.b_coeff, d.b_nnz = P(b_csr[0], np.uint32), P(b_csr[1], np.uint32), P(b_csr[2]), len(b_csr[1])
-        assert len(a_csr[0]) == num_constraints + 1 and len(b_csr[0]) == num_constraints + 1
+        _need(len(a_csr[0]) == num_constraints + 1 and len(b_csr[0]) == num_constraints + 1, "zkey: rowptr must hold num_constraints + 1 entries")
+        _need(len(a_csr[1]) * 4 == _c(a_csr[2]).size and len(b_csr[1]) * 4 == _c(b_csr[2]).size, "zkey: one coefficient per column index")
         lq = self.lq
         for name, arr, n, w in (("a_query", a_query, n_vars, 2), ("b_g1_query", b_g1_query, n_vars, 2), ("b_g2_query", b_g2_query, n_vars, 4),
                                 ("h_query", h_query, 1 << pow_, 2), ("l_query", l_query, self.n_aux, 2)):
             if arr is None:
-                assert synthetic_seed is not None, f"{name} missing and no synthetic_seed"
+                _need(synthetic_seed is not None, f"{name} missing and no synthetic_seed")
                 continue
             arr = _c(arr)
-            assert arr.size == n * w * lq, f"{name}: expected {n} points"
+            _need(arr.size == n * w * lq, f"{name}: expected {n} points")
             setattr(d, name, P(arr))
         for name, arr in (("alpha_g1", alpha_g1), ("beta_g1", beta_g1), ("delta_g1", delta_g1), ("beta_g2", beta_g2), ("delta_g2", delta_g2)):
             if arr is not None:
                 setattr(d, name, P(arr))
         if synthetic_seed is not None:
-            assert len(synthetic_seed) == 32
+            _need(len(synthetic_seed) == 32, "synthetic_seed must be 32 bytes")
             d.synthetic_seed = P(np.frombuffer(synthetic_seed, dtype=np.uint8), np.uint8)
         h = vp()
         _ck(L.cohost_zkey_create(ctypes.byref(d), ctypes.byref(h)))
@@ -359,7 +367,8 @@ class PlainSession:
     def prove(self, public_inputs, witness, r=None, s=None, want_h=False):
         zk = self.zkey
         pub, wit = _c(public_inputs), _c(witness)
-        assert pub.size == 4 * (zk.n_public + 1) and wit.size == 4 * zk.n_aux
+        _need(pub.size == 4 * (zk.n_public + 1), f"prove: expected {zk.n_public + 1} public inputs")
+        _need(wit.size == 4 * zk.n_aux, f"prove: expected {zk.n_aux} witness elements")
         proof = np.zeros(8 * zk.lq, dtype=np.uint64)
         hbuf = np.zeros((1 << zk.pow, 4), dtype=np.uint64) if want_h else None
         rr = None if r is None else _c(r)
@@ -378,8 +387,12 @@ class PlainSession:
 class Rep3Session:
     """Three CoGroth16<Rep3Protocol> provers on three threads over an in-process network (one GPU, or one MSM shard of `world`)."""
 
-    def __init__(self, zkey: Groth16ZKey, seeds: bytes = bytes(range(96)), rank: int = 0, world: int = 1):
-        assert len(seeds) == 96
+    def __init__(self, zkey: Groth16ZKey, seeds: bytes | None = None, rank: int = 0, world: int = 1):
+        """seeds: 3 x 32 bytes, the parties' PRF seeds (Rep3Protocol::new draws them from entropy, rep3.rs:343-349).  Every mask and
+        the Groth16 blinders r, s derive from them, so the default is os.urandom; fixed seeds are for tests and the benchmark only.
+        In a multi-GPU run every rank must pass the SAME seeds (the ranks replay the same three parties)."""
+        seeds = os.urandom(96) if seeds is None else seeds
+        _need(len(seeds) == 96, "Rep3Session: seeds must be 3 x 32 bytes")
         self.zkey, self.rank, self.world = zkey, rank, world
         self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
         h = vp()
@@ -395,13 +408,14 @@ class Rep3Session:
         zk = self.zkey
         self._keep = [_c(public_inputs)]
         pub = self._keep[0]
-        assert pub.size == 4 * (zk.n_public + 1)
+        _need(pub.size == 4 * (zk.n_public + 1), f"prove: expected {zk.n_public + 1} public inputs")
+        _need(len(wit_a) == 3 and len(wit_b) == 3, "prove: three share components per side")
 
         def addr(x):
             if isinstance(x, int):
                 return x
             a = _c(x)
-            assert a.size == 4 * zk.n_aux
+            _need(a.size == 4 * zk.n_aux, f"prove: expected {zk.n_aux} witness share elements")
             self._keep.append(a)
             return a.ctypes.data
 
@@ -429,7 +443,7 @@ class Rep3Session:
 
     def combine(self, gathered: np.ndarray):
         g = _c(gathered)
-        assert g.nbytes == self.world * self.partial_bytes()
+        _need(g.nbytes == self.world * self.partial_bytes(), "combine: gathered buffer has the wrong size")
         _ck(load_host().cohost_rep3_prove_combine(self.h, g.ctypes.data))
 
     def end(self, want_h=False):
@@ -472,7 +486,7 @@ class Rep3Session:
 
     def set_mpc_exchange(self, mode: str):
         """'host': mul_vec payloads staged through pinned host memory (default); 'device': handed over in HBM (co-located parties)."""
-        assert mode in ("host", "device")
+        _need(mode in ("host", "device"), "set_mpc_exchange: mode must be host or device")
         _ck(load_host().cohost_rep3_set_mpc_exchange(self.h, 1 if mode == "device" else 0))
 
     def phase_times(self) -> np.ndarray:
@@ -492,8 +506,10 @@ class ShamirSession:
 
     def __init__(self, zkey: Groth16ZKey, num_parties: int = 3, threshold: int = 1, seeds: bytes | None = None):
         self.zkey, self.n, self.t = zkey, num_parties, threshold
-        seeds = seeds or bytes((i * 7 + 1) % 256 for i in range(32 * num_parties))
-        assert len(seeds) == 32 * num_parties
+        # every double-random pair, and through rand() the Groth16 blinders r and s, derive from these seeds: entropy by default
+        # (ShamirProtocol::new seeds its RngType from entropy, shamir.rs:196-245); fixed seeds are for tests and the benchmark only
+        seeds = os.urandom(32 * num_parties) if seeds is None else seeds
+        _need(len(seeds) == 32 * num_parties, "ShamirSession: seeds must be num_parties x 32 bytes")
         self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
         h = vp()
         _ck(load_host().cohost_shamir_session_create(zkey.h, num_parties, threshold, self._seeds.ctypes.data, ctypes.byref(h)))
@@ -504,7 +520,9 @@ class ShamirSession:
         zk = self.zkey
         pub = _c(public_inputs)
         ws = [_c(x) for x in wit]
-        assert len(ws) == self.n and pub.size == 4 * (zk.n_public + 1) and all(x.size == 4 * zk.n_aux for x in ws)
+        _need(len(ws) == self.n, f"prove: expected {self.n} share vectors")
+        _need(pub.size == 4 * (zk.n_public + 1), f"prove: expected {zk.n_public + 1} public inputs")
+        _need(all(x.size == 4 * zk.n_aux for x in ws), f"prove: expected {zk.n_aux} witness share elements per party")
         W = (vp * self.n)(*[x.ctypes.data for x in ws])
         proofs = np.zeros((self.n, 8 * zk.lq), dtype=np.uint64)
         rs = np.zeros((self.n, 2, 4), dtype=np.uint64)
@@ -531,7 +549,7 @@ class PlonkZKey:
 
     def round1_plain(self, public_inputs, witness, deterministic=True) -> np.ndarray:
         pub, wit = _c(public_inputs), _c(witness)
-        assert pub.size == 4 * (self.n_public + 1) and wit.size == 4 * (self.n_vars - self.n_additions - self.n_public - 1)
+        _need(pub.size == 4 * (self.n_public + 1) and wit.size == 4 * (self.n_vars - self.n_additions - self.n_public - 1), "round1: wrong input length")
         out = np.zeros((3, 2 * self.lq), dtype=np.uint64)
         _ck(load_host().cohost_plonk_round1_plain(self.h, pub.ctypes.data, wit.ctypes.data, 1 if deterministic else 0, out.ctypes.data))
         return out

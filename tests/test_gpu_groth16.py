@@ -158,7 +158,7 @@ def test_rep3_prove_sharded_msm_equals_single(cocg):
     single = prover.Rep3Session(dz)
     want = single.prove(f(pub), wa, wb, limbs)
     single.close()
-    ranks = [prover.Rep3Session(dz, rank=k, world=2) for k in range(2)]
+    ranks = [prover.Rep3Session(dz, seeds=bytes(range(96)), rank=k, world=2) for k in range(2)]
     for s_ in ranks:
         s_.begin(f(pub), wa, wb, limbs)
     gathered = np.concatenate([s_.partials() for s_ in ranks])

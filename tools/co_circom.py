@@ -54,7 +54,7 @@ def generate_proof(a):
         sess = cocg.Rep3Session(zk, seeds=os.urandom(96))
         proofs = sess.prove(pubs[0], wa, wb)
     else:
-        sess = cocg.ShamirSession(zk, len(a.witness), a.threshold)
+        sess = cocg.ShamirSession(zk, len(a.witness), a.threshold, seeds=os.urandom(32 * len(a.witness)))
         proofs, _ = sess.prove(pubs[0], wa)
     if any(not (p == proofs[0]).all() for p in proofs[1:]):
         sys.exit("the parties opened different proofs")
