@@ -25,6 +25,7 @@ SYMBOLS = [
     "cocg_d2d", "cocg_host_alloc", "cocg_host_free", "cocg_rep3_mul_local_prf", "cocg_prf_fill", "cocg_prf_field_host",
     "cocg_bases_share", "cocg_csr_share", "cocg_bases_generate", "cocg_bases_download", "cocg_profile_enable",
     "cocg_profile_read", "cocg_profile_reset", "cocg_msm_multi", "cocg_vec_axpy", "cocg_csr_upload_form", "cocg_csr_download", "cocg_bases_generate_range",
+    "cocg_fp_mul_ceiling",
 ]
 
 _lib = None
@@ -83,6 +84,7 @@ def load():
         "cocg_profile_enable": (ci, [vp, ci]),
         "cocg_profile_read": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),
         "cocg_profile_reset": (ci, [vp]),
+        "cocg_fp_mul_ceiling": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double)]),
         "cocg_csr_upload_form": (ci, [vp, vp, vp, vp, sz, sz, ci, ctypes.POINTER(u64)]),
         "cocg_csr_download": (ci, [vp, u64, vp, vp, vp, ctypes.POINTER(sz)]),
         "cocg_vec_axpy": (ci, [vp, vp, vp, vp, vp, sz]),

@@ -162,6 +162,12 @@ class Context:
             out[name] = (ms.value, int(k.value))
         return out
 
+    def fp_mul_ceiling(self, base_field: bool = True) -> float:
+        """10^9 Montgomery products / s of a pure fp_mul chain on every SM, measured now (Fq of the curve, or Fr)."""
+        out = ctypes.c_double()
+        self._ck(self.L.cocg_fp_mul_ceiling(self.h, 1 if base_field else 0, ctypes.byref(out)))
+        return out.value
+
     def bases_free(self, handle: int):
         self._ck(self.L.cocg_bases_free(self.h, handle))
 

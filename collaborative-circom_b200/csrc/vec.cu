@@ -188,6 +188,51 @@ static int prf_fill_impl(cocg_ctx* ctx, const void* seed, uint32_t ctr, void* ou
 
 using namespace cocg;
 
+namespace cocg {
+// A pure chain of Montgomery products on every SM: the multiplier ceiling the MSM / NTT kernels are measured against
+// (bench.py's roofline.issue.peak), so that the bound is measured in the same run as the kernels instead of being read from a file.
+template <class P>
+__global__ void __launch_bounds__(256) fp_mul_chain_kernel(uint32_t* out, int iters) {
+  Fp<P> a, b;
+#pragma unroll
+  for (int k = 0; k < P::N; k++) { a.l[k] = threadIdx.x * 2654435761u + k; b.l[k] = blockIdx.x * 40503u + 7 * k + 1; }
+  a.l[P::N - 1] &= 0x0fffffffu;
+  b.l[P::N - 1] &= 0x0fffffffu;
+  for (int it = 0; it < iters; it++) a = fp_mul(a, b);
+  if (a.l[0] == 0x12345678u && a.l[1] == 0x9abcdef0u) out[0] = a.l[2];
+}
+template <class P>
+static int fp_mul_ceiling_impl(cocg_ctx* ctx, double* out) {
+  void* d;
+  COCG_TRY(scratch_get(ctx, 15, 64, &d));
+  const int blocks = kNumSMs * 8, iters = 1500;
+  cudaEvent_t e0, e1;
+  COCG_CUDA(ctx, cudaEventCreate(&e0));
+  COCG_CUDA(ctx, cudaEventCreate(&e1));
+  fp_mul_chain_kernel<P><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)d, 50);  // warm-up
+  COCG_LAUNCH_CHECK(ctx);
+  COCG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  fp_mul_chain_kernel<P><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)d, iters);
+  COCG_LAUNCH_CHECK(ctx);
+  COCG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  COCG_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0;
+  COCG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *out = (double)blocks * 256 * iters / (ms * 1e-3) / 1e9;
+  return 0;
+}
+}  // namespace cocg
+
+extern "C" int cocg_fp_mul_ceiling(cocg_ctx* ctx, int base_field, double* gmul_per_s) {
+  if (!ctx) return 1;
+  if (!gmul_per_s) return fail(ctx, "cocg_fp_mul_ceiling: null argument");
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->curve == COCG_BN254) return base_field ? fp_mul_ceiling_impl<Bn254FqP>(ctx, gmul_per_s) : fp_mul_ceiling_impl<Bn254FrP>(ctx, gmul_per_s);
+  return base_field ? fp_mul_ceiling_impl<Bls381FqP>(ctx, gmul_per_s) : fp_mul_ceiling_impl<Bls381FrP>(ctx, gmul_per_s);
+}
+
 extern "C" int cocg_rep3_mul_local_prf(cocg_ctx* ctx, const void* aa, const void* ab, const void* ba, const void* bb,
                                        const void* seed_own, const void* seed_prev, uint32_t ctr, void* out, size_t n) {
   if (!ctx) return 1;

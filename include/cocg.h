@@ -62,6 +62,10 @@ enum { COCG_PROF_MSM_SORT = 0, COCG_PROF_MSM_ACCUMULATE = 1, COCG_PROF_MSM_REDUC
 COCG_API int cocg_profile_enable(cocg_ctx* ctx, int on);
 COCG_API int cocg_profile_read(cocg_ctx* ctx, int cls, double* total_ms, uint64_t* scopes);
 COCG_API int cocg_profile_reset(cocg_ctx* ctx);
+/* Measures, on this device and now, the throughput of a pure dependent chain of the library's own Montgomery product on every SM
+ * (base_field = 0: Fr, 1: Fq of the context's curve), in 10^9 products / s: the multiplier-issue ceiling bench.py reports the MSM
+ * and NTT kernels against (a ~5 ms kernel). */
+COCG_API int cocg_fp_mul_ceiling(cocg_ctx* ctx, int base_field, double* gmul_per_s);
 
 /* ---- device memory (so that share vectors can stay resident between MPC network rounds) ------------- */
 COCG_API int cocg_malloc(cocg_ctx* ctx, size_t bytes, void** dptr);
