@@ -530,7 +530,9 @@ def run_own_msm(args):
     for _ in range(min(args.warmup, 2)):
         e2e_fn()
     ms_e2e, _, out2 = timed(e2e_fn, args.steps)
-    assert np.array_equal(out, out2), "host-pointer and device-pointer entry points disagree"
+    # Jacobian representatives depend on the (atomic) order in which a bucket's points were added: compare the affine point
+    aff, aff2 = ctx.ec_op(1, cocg.EC_TO_AFFINE, out[0]), ctx.ec_op(1, cocg.EC_TO_AFFINE, out2[0])
+    assert np.array_equal(aff, aff2), "host-pointer and device-pointer entry points disagree"
     if rank == 0:
         peak, peak_src = measured_peak()
         acc_ms = prof["msm_accumulate"][0] / max(prof["msm_accumulate"][1], 1)
@@ -546,7 +548,7 @@ def run_own_msm(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "MSM/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": n * 32,
                     "d2h_bytes_per_step": 96, "note": "cocg_msm_host: scalars in pinned host memory uploaded every step, result point read back"},
-            "result_sha256": __import__("hashlib").sha256(np.ascontiguousarray(out).tobytes()).hexdigest(),
+            "result_sha256": __import__("hashlib").sha256(np.ascontiguousarray(aff).tobytes()).hexdigest(),
             "roofline": {"bound": "hbm", "achieved": n * 96 / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": n * 96 / (acc_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(1), "peak_source": peak_src,
                          "kernel": "msm_accumulate_kernel, one launch per MSM, timed with CUDA events on its launching stream",

@@ -25,7 +25,8 @@ SYMBOLS = [
     "cocg_d2d", "cocg_host_alloc", "cocg_host_free", "cocg_rep3_mul_local_prf", "cocg_prf_fill", "cocg_prf_field_host",
     "cocg_bases_share", "cocg_csr_share", "cocg_bases_generate", "cocg_bases_download", "cocg_profile_enable",
     "cocg_profile_read", "cocg_profile_reset", "cocg_msm_multi", "cocg_vec_axpy", "cocg_csr_upload_form", "cocg_csr_download", "cocg_bases_generate_range",
-    "cocg_fp_mul_ceiling",
+    "cocg_fp_mul_ceiling", "cocg_vec_gather", "cocg_vec_scan", "cocg_vec_inv", "cocg_poly_eval", "cocg_vec_lincomb", "cocg_vec_fill",
+    "cocg_plonk_z_factors", "cocg_plonk_quotient_l1", "cocg_plonk_quotient_l2", "cocg_plonk_t_finish",
 ]
 
 _lib = None
@@ -85,6 +86,16 @@ def load():
         "cocg_profile_read": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),
         "cocg_profile_reset": (ci, [vp]),
         "cocg_fp_mul_ceiling": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double)]),
+        "cocg_vec_gather": (ci, [vp, vp, sz, vp, vp, sz]),
+        "cocg_vec_scan": (ci, [vp, ci, vp, vp, sz]),
+        "cocg_vec_inv": (ci, [vp, vp, vp, sz, ctypes.POINTER(sz)]),
+        "cocg_poly_eval": (ci, [vp, vp, sz, vp, vp]),
+        "cocg_vec_lincomb": (ci, [vp, ci, pvp, ctypes.POINTER(sz), vp, vp, sz]),
+        "cocg_vec_fill": (ci, [vp, vp, sz, vp]),
+        "cocg_plonk_z_factors": (ci, [vp, vp, sz, ci]),
+        "cocg_plonk_quotient_l1": (ci, [vp, vp]),
+        "cocg_plonk_quotient_l2": (ci, [vp, vp]),
+        "cocg_plonk_t_finish": (ci, [vp, vp, vp, sz, vp, vp, vp]),
         "cocg_csr_upload_form": (ci, [vp, vp, vp, vp, sz, sz, ci, ctypes.POINTER(u64)]),
         "cocg_csr_download": (ci, [vp, u64, vp, vp, vp, ctypes.POINTER(sz)]),
         "cocg_vec_axpy": (ci, [vp, vp, vp, vp, vp, sz]),

@@ -109,6 +109,56 @@ class Context:
         c = np.ascontiguousarray(c, dtype=np.uint64)
         self._ck(self.L.cocg_vec_scale_powers(self.h, x.ptr, x.n, g.ctypes.data, c.ctypes.data))
 
+    # ---------------- CoPlonk vector primitives (csrc/poly.cu, csrc/plonk.cu)
+    def upload_u32(self, arr: np.ndarray) -> int:
+        """uint32 index array -> raw device address (cocg_malloc; free with free_raw)."""
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        p = ctypes.c_void_p()
+        self._ck(self.L.cocg_malloc(self.h, max(arr.nbytes, 4), ctypes.byref(p)))
+        self._ck(self.L.cocg_h2d(self.h, p, arr.ctypes.data, arr.nbytes))
+        return p.value
+
+    def free_raw(self, ptr: int):
+        self._ck(self.L.cocg_free(self.h, ptr))
+
+    def vec_gather(self, src: DeviceVec, idx_ptr: int, n: int) -> DeviceVec:
+        out = DeviceVec(self, n)
+        self._ck(self.L.cocg_vec_gather(self.h, src.ptr, src.n, idx_ptr, out.ptr, n))
+        return out
+
+    def vec_scan(self, op: int, x: DeviceVec, out: DeviceVec | None = None) -> DeviceVec:
+        out = out or DeviceVec(self, x.n)
+        self._ck(self.L.cocg_vec_scan(self.h, op, x.ptr, out.ptr, x.n))
+        return out
+
+    def vec_inv(self, x: DeviceVec, out: DeviceVec | None = None):
+        """-> (1 / x element-wise with 0 -> 0, number of zero inputs)"""
+        out = out or DeviceVec(self, x.n)
+        z = ctypes.c_size_t()
+        self._ck(self.L.cocg_vec_inv(self.h, x.ptr, out.ptr, x.n, ctypes.byref(z)))
+        return out, int(z.value)
+
+    def poly_eval(self, coeffs: DeviceVec, point: np.ndarray, n: int | None = None) -> np.ndarray:
+        point = np.ascontiguousarray(point, dtype=np.uint64)
+        out = np.zeros(4, dtype=np.uint64)
+        self._ck(self.L.cocg_poly_eval(self.h, coeffs.ptr, coeffs.n if n is None else n, point.ctypes.data, out.ctypes.data))
+        return out
+
+    def vec_lincomb(self, vecs, factors: np.ndarray, n: int) -> DeviceVec:
+        vecs = list(vecs)
+        out = DeviceVec(self, n)
+        P = (ctypes.c_void_p * len(vecs))(*[v.ptr for v in vecs])
+        Ls = (ctypes.c_size_t * len(vecs))(*[v.n for v in vecs])
+        f = np.ascontiguousarray(factors, dtype=np.uint64)
+        self._ck(self.L.cocg_vec_lincomb(self.h, len(vecs), P, Ls, f.ctypes.data, out.ptr, n))
+        return out
+
+    def vec_fill(self, n: int, value: np.ndarray) -> DeviceVec:
+        out = DeviceVec(self, n)
+        v = np.ascontiguousarray(value, dtype=np.uint64)
+        self._ck(self.L.cocg_vec_fill(self.h, out.ptr, n, v.ctypes.data))
+        return out
+
     # ---------------- NTT (a4 + a5)
     def ntt(self, vecs, log_n: int, root: np.ndarray, inverse: bool = False, coset_g: np.ndarray | None = None):
         vecs = list(vecs)

@@ -95,6 +95,32 @@ __global__ void __launch_bounds__(128) powers_kernel(void* __restrict__ out, siz
   }
 }
 
+// x[i] *= first * base^i without a table: (base, first) are per-proof challenges in the CoPlonk rounds (division by X - xi), and a
+// cached table per challenge would never be reused.
+template <class P>
+__global__ void __launch_bounds__(128) scale_powers_kernel(void* __restrict__ x, size_t n, Fp<P> base, Fp<P> first) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * kPowRun;
+  if (lo >= n) return;
+  Fp<P> pw = fp_mul(first, fp_pow_u64(base, (uint64_t)lo));
+  size_t hi = lo + kPowRun < n ? lo + kPowRun : n;
+  for (size_t i = lo; i < hi; i++) {
+    store_fp<P>(x, i, fp_mul(load_fp<P>(x, i), pw));
+    pw = fp_mul(pw, base);
+  }
+}
+template <class P>
+static int scale_powers_impl(cocg_ctx* ctx, void* x, size_t n, const void* g, const void* c) {
+  Fp<P> b, f;
+  memcpy(b.l, g, 32);
+  memcpy(f.l, c, 32);
+  size_t threads = (n + kPowRun - 1) / kPowRun;
+  ProfScope prof(ctx, COCG_PROF_VEC);
+  scale_powers_kernel<P><<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(x, n, b, f);
+  COCG_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 template <class P>
 static int powers_table_impl(cocg_ctx* ctx, uint32_t kind, size_t n, const uint32_t* base, const uint32_t* first, void** out) {
   std::array<uint32_t, 18> key;
@@ -283,10 +309,5 @@ extern "C" int cocg_vec_scale_powers(cocg_ctx* ctx, void* x, size_t n, const voi
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n == 0) return 0;
   if (!x || !g || !c) return fail(ctx, "cocg_vec_scale_powers: null operand");
-  void* tab = nullptr;
-  uint32_t gl[8], cl[8];
-  memcpy(gl, g, 32);
-  memcpy(cl, c, 32);
-  COCG_TRY(powers_table(ctx, /*kind=*/1, n, gl, cl, &tab));
-  return cocg_vec_op(ctx, COCG_OP_MUL, x, tab, x, n);
+  return COCG_FR_DISPATCH(ctx, scale_powers_impl, ctx, x, n, g, c);
 }

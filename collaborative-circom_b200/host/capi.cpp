@@ -683,11 +683,39 @@ extern "C" int cohost_rep3_phase_times(cohost_rep3_session* s, double* out) {
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ Plonk, round 1
+// ------------------------------------------------------------------------------------------------ Plonk
 struct cohost_plonk_zkey {
   PlonkZKey zk;
   size_t lq = 4;
 };
+
+namespace {
+void* plonk_dev_alloc(PlonkZKey& zk, size_t bytes) {
+  void* p = nullptr;
+  check(zk.owner, cocg_malloc(zk.owner, bytes, &p), "cocg_malloc");
+  zk.owned.push_back(p);
+  return p;
+}
+void* plonk_dev_upload(PlonkZKey& zk, const void* host, size_t bytes) {
+  void* p = plonk_dev_alloc(zk, bytes);
+  check(zk.owner, cocg_h2d(zk.owner, p, host, bytes), "cocg_h2d");
+  return p;
+}
+void plonk_upload_maps(PlonkZKey& zk) {
+  const std::vector<uint32_t>* maps[3] = {&zk.map_a, &zk.map_b, &zk.map_c};
+  for (int k = 0; k < 3; k++) {
+    std::vector<uint32_t> padded(zk.domain_size, 0xffffffffu);  // gates past n_constraints read zero (round1.rs:150-166)
+    std::copy(maps[k]->begin(), maps[k]->end(), padded.begin());
+    zk.d_map[k] = (uint32_t*)plonk_dev_upload(zk, padded.data(), padded.size() * 4);
+  }
+}
+void plonk_proof_pack(const PlonkProof& p, size_t lq, uint64_t* o) {
+  const Point* pts[9] = {&p.a, &p.b, &p.c, &p.z, &p.t1, &p.t2, &p.t3, &p.wxi, &p.wxiw};
+  for (int i = 0; i < 9; i++) memcpy(o + (size_t)i * 2 * lq, pts[i]->l, 2 * lq * 8);
+  const Fr* ev[6] = {&p.eval_a, &p.eval_b, &p.eval_c, &p.eval_s1, &p.eval_s2, &p.eval_zw};
+  for (int i = 0; i < 6; i++) memcpy(o + 18 * lq + (size_t)i * 4, ev[i]->l, 32);
+}
+}  // namespace
 
 extern "C" int cohost_plonk_zkey_load_file(const char* path, int device, cohost_plonk_zkey** out) {
   if (!path || !out) return fail("cohost_plonk_zkey_load_file: null argument");
@@ -719,12 +747,93 @@ extern "C" int cohost_plonk_zkey_load_file(const char* path, int device, cohost_
     rd_map(f.map_c, zk.map_c);
     if (cocg_create(&zk.owner, device, f.curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
     check(zk.owner, cocg_bases_upload(zk.owner, COCG_G1, f.p_tau, f.domain_size + 6, 2 * f.n8q, 1, &zk.p_tau), "p_tau");
+    plonk_upload_maps(zk);
+    // rounds 2-5: selector / sigma / Lagrange polynomials (n coefficients | 4n evaluations each, Montgomery) and the vk tail
+    if (f.k1 && f.sigma && f.lagrange && f.sel[0] && f.sel[1] && f.sel[2] && f.sel[3] && f.sel[4]) {
+      const size_t n = f.domain_size;
+      memcpy(zk.k1.l, f.k1, 32);
+      memcpy(zk.k2.l, f.k2, 32);
+      for (int i = 0; i < 8; i++) memcpy(zk.vk_g1[i].l, f.vk_g1 + (size_t)i * 2 * f.n8q, 2 * f.n8q);
+      for (int k = 0; k < 5; k++) {
+        char* d = (char*)plonk_dev_upload(zk, f.sel[k], 5 * n * 32);
+        zk.sel_coef[k] = d;
+        zk.sel_eval[k] = d + n * 32;
+      }
+      for (int k = 0; k < 3; k++) {
+        char* d = (char*)plonk_dev_upload(zk, f.sigma + (size_t)k * 5 * n * 32, 5 * n * 32);
+        zk.sig_coef[k] = d;
+        zk.sig_eval[k] = d + n * 32;
+      }
+      zk.n_lagrange = f.n_public > 1 ? f.n_public : 1;
+      char* lg = (char*)plonk_dev_alloc(zk, zk.n_lagrange * 4 * n * 32);
+      for (size_t j = 0; j < zk.n_lagrange; j++)
+        check(zk.owner, cocg_h2d(zk.owner, lg + j * 4 * n * 32, f.lagrange + j * 5 * n * 32 + n * 32, 4 * n * 32), "lagrange");
+      zk.lagrange = lg;
+      zk.full = true;
+    }
+    *out = z.release();
+  });
+}
+// A shape-faithful synthetic key (BASELINE configs[3]: 2^18 gates; no circom / snarkjs exists here to make a real one): the wire maps
+// come from the caller, every polynomial is filled by the device PRF, p_tau and the vk points are valid curve points generated in HBM.
+// The resulting proofs exercise every kernel of the five rounds at full size; they are not expected to verify.
+extern "C" int cohost_plonk_zkey_create_synthetic(int curve, int device, size_t log_n, size_t n_public, size_t n_vars, size_t n_constraints,
+                                                  const uint32_t* map_a, const uint32_t* map_b, const uint32_t* map_c, const uint8_t* seed,
+                                                  cohost_plonk_zkey** out) {
+  if (!out || !seed || !map_a || !map_b || !map_c) return fail("cohost_plonk_zkey_create_synthetic: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    const size_t n = (size_t)1 << log_n;
+    if (n_constraints > n || n_vars < n_public + 1) throw Error("plonk synthetic key: inconsistent sizes");
+    std::unique_ptr<cohost_plonk_zkey> z(new cohost_plonk_zkey());
+    PlonkZKey& zk = z->zk;
+    zk.curve = curve;
+    zk.device = device;
+    z->lq = curve == COCG_BN254 ? 4 : 6;
+    zk.n_vars = n_vars; zk.n_public = n_public; zk.domain_size = n; zk.pow = log_n; zk.n_additions = 0; zk.n_constraints = n_constraints;
+    for (const uint32_t* m : {map_a, map_b, map_c})
+      for (size_t i = 0; i < n_constraints; i++)
+        if (m[i] >= n_vars) throw Error("plonk synthetic key: wire map index out of range");
+    zk.map_a.assign(map_a, map_a + n_constraints);
+    zk.map_b.assign(map_b, map_b + n_constraints);
+    zk.map_c.assign(map_c, map_c + n_constraints);
+    if (cocg_create(&zk.owner, device, curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
+    uint8_t sd[32];
+    memcpy(sd, seed, 32);
+    check(zk.owner, cocg_bases_generate(zk.owner, COCG_G1, n + 6, sd, &zk.p_tau), "p_tau");
+    plonk_upload_maps(zk);
+    uint32_t ctr = 1;
+    auto filled = [&](size_t elems) {
+      void* p = plonk_dev_alloc(zk, elems * 32);
+      check(zk.owner, cocg_prf_fill(zk.owner, sd, ctr++, p, elems), "cocg_prf_fill");
+      return p;
+    };
+    for (int k = 0; k < 5; k++) { zk.sel_coef[k] = filled(n); zk.sel_eval[k] = filled(4 * n); }
+    for (int k = 0; k < 3; k++) { zk.sig_coef[k] = filled(n); zk.sig_eval[k] = filled(4 * n); }
+    zk.n_lagrange = n_public > 1 ? n_public : 1;
+    zk.lagrange = filled(zk.n_lagrange * 4 * n);
+    cocg_prf_field_host(curve, sd, 1000, 0, zk.k1.l);
+    cocg_prf_field_host(curve, sd, 1000, 1, zk.k2.l);
+    {
+      uint64_t h = 0;
+      sd[31] ^= 0x5a;
+      check(zk.owner, cocg_bases_generate(zk.owner, COCG_G1, 8, sd, &h), "vk points");
+      std::vector<uint64_t> b(8 * 2 * z->lq);
+      check(zk.owner, cocg_bases_download(zk.owner, h, 0, 8, b.data()), "vk points");
+      cocg_bases_free(zk.owner, h);
+      for (int i = 0; i < 8; i++) memcpy(zk.vk_g1[i].l, b.data() + (size_t)i * 2 * z->lq, 2 * z->lq * 8);
+    }
+    check(zk.owner, cocg_sync(zk.owner), "cocg_sync");
+    zk.full = true;
     *out = z.release();
   });
 }
 extern "C" void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z) {
   if (!z) return;
-  if (z->zk.owner) cocg_destroy(z->zk.owner);
+  if (z->zk.owner) {
+    for (void* p : z->zk.owned) cocg_free(z->zk.owner, p);
+    cocg_destroy(z->zk.owner);
+  }
   delete z;
 }
 // info[6] = curve, n_vars, n_public, domain_size, n_additions, n_constraints
@@ -735,61 +844,188 @@ extern "C" int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info) {
   memcpy(info, v, sizeof(v));
   return 0;
 }
-// Round1::round1 with PlainDriver.  public_inputs: n_public + 1 Fr; witness: n_vars - n_additions - n_public - 1 Fr;
-// deterministic != 0 uses the reference's KAT blinders b_i = i (round1.rs:101-108).  commits_out: [a]_1 | [b]_1 | [c]_1 affine.
-extern "C" int cohost_plonk_round1_plain(cohost_plonk_zkey* z, const void* public_inputs, const void* witness, int deterministic, void* commits_out) {
-  if (!z || !public_inputs || !witness || !commits_out) return fail("cohost_plonk_round1_plain: null argument");
+
+// CoPlonk sessions: protocol 0 = CoPlonk<PlainDriver> (one party), 1 = three CoPlonk<Rep3Protocol> provers on three threads over the
+// in-process network (tests/tests/circom/e2e_tests/mod.rs:55-70 runs the reference's Plonk provers the same way).
+struct cohost_plonk_session {
+  cohost_plonk_zkey* zkey = nullptr;
+  int parties = 1;
+  std::unique_ptr<PlainDriver> plain;
+  std::unique_ptr<Rep3TestNetwork> net;
+  std::unique_ptr<Rep3Protocol> drv[3];
+  uint64_t h_tau[3] = {0, 0, 0};
+  bool trace_on = false;
+  std::map<std::string, std::vector<Fr>> traces[3];
+  double round_s[3][5] = {};
+  bool failed = false;
+  DeviceDriver* driver(int i) { return parties == 1 ? (DeviceDriver*)plain.get() : (DeviceDriver*)drv[i].get(); }
+};
+
+extern "C" int cohost_plonk_session_create(cohost_plonk_zkey* z, int protocol, const uint8_t* seeds, cohost_plonk_session** out) {
+  if (!z || !out || !seeds) return fail("cohost_plonk_session_create: null argument");
+  if (protocol != 0 && protocol != 1) return fail("cohost_plonk_session_create: protocol must be 0 (plain) or 1 (REP3)");
+  *out = nullptr;
   return guarded([&] {
-    PlainDriver d(z->zk.curve, z->zk.device);
-    uint64_t h = 0;
-    check(d.ctx, cocg_bases_share(d.ctx, z->zk.owner, z->zk.p_tau, &h), "share p_tau");
-    CoPlonkRound1<PlainDriver> r1(d);
-    Round1Proof p = r1.round1(z->zk, h, (const Fr*)public_inputs, (const Fr*)witness, nullptr, deterministic != 0);
-    uint64_t* o = (uint64_t*)commits_out;
-    memcpy(o, p.commit_a.l, 2 * z->lq * 8);
-    memcpy(o + 2 * z->lq, p.commit_b.l, 2 * z->lq * 8);
-    memcpy(o + 4 * z->lq, p.commit_c.l, 2 * z->lq * 8);
+    std::unique_ptr<cohost_plonk_session> s(new cohost_plonk_session());
+    s->zkey = z;
+    s->parties = protocol == 0 ? 1 : 3;
+    if (protocol == 0) {
+      s->plain.reset(new PlainDriver(z->zk.curve, z->zk.device));
+      memcpy(s->plain->seed, seeds, 32);
+      check(s->plain->ctx, cocg_bases_share(s->plain->ctx, z->zk.owner, z->zk.p_tau, &s->h_tau[0]), "share p_tau");
+    } else {
+      s->net.reset(new Rep3TestNetwork());
+      const char* ex = getenv("COHOST_MPC_EXCHANGE");
+      s->net->device_exchange = ex && std::string(ex) == "device";
+      for (int i = 0; i < 3; i++) s->drv[i].reset(new Rep3Protocol(z->zk.curve, z->zk.device, s->net->party(i), seeds + 32 * i));
+      for (int i = 0; i < 3; i++) {
+        s->drv[i]->finish_setup();
+        check(s->drv[i]->ctx, cocg_bases_share(s->drv[i]->ctx, z->zk.owner, z->zk.p_tau, &s->h_tau[i]), "share p_tau");
+      }
+    }
+    *out = s.release();
   });
 }
-// Same with three Rep3Protocol drivers on three threads.  wit_a[i] / wit_b[i]: party i's HOST share components;
-// commits_out: 3 parties x ([a]_1 | [b]_1 | [c]_1).
-extern "C" int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
-                                        const uint8_t* seeds, int deterministic, void* commits_out) {
-  if (!z || !public_inputs || !wit_a || !wit_b || !seeds || !commits_out) return fail("cohost_plonk_round1_rep3: null argument");
+extern "C" void cohost_plonk_session_destroy(cohost_plonk_session* s) { delete s; }
+
+// One proof.  public_inputs: n_public + 1 Fr; wit_a / wit_b: `parties` pointers each (wit_b may be NULL for the plain driver) to the
+// parties' share components of the private witness, HOST memory or -- wit_on_device -- HBM of the session's device.
+// proofs_out: parties x cohost_plonk_proof_limbs() u64.  rounds = 1 stops after round 1 (commitments a, b, c only).
+static int plonk_prove_impl(cohost_plonk_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b, int deterministic,
+                            int wit_on_device, int rounds, void* proofs_out) {
+  if (!s || !public_inputs || !wit_a || !proofs_out) return fail("cohost_plonk_prove: null argument");
+  if (s->parties == 3 && !wit_b) return fail("cohost_plonk_prove: REP3 needs both share components");
+  if (s->failed) return fail("cohost_plonk_prove: the session's network is closed after an earlier failure");
   return guarded([&] {
-    Rep3TestNetwork net;
-    std::unique_ptr<Rep3Protocol> drv[3];
-    for (int i = 0; i < 3; i++) drv[i].reset(new Rep3Protocol(z->zk.curve, z->zk.device, net.party(i), seeds + 32 * i));
-    for (int i = 0; i < 3; i++) drv[i]->finish_setup();
+    const PlonkZKey& zk = s->zkey->zk;
+    const size_t lq = s->zkey->lq, pl = 18 * lq + 24;
+    if (s->parties == 1) {
+      CoPlonk<PlainDriver> pv(*s->plain);
+      if (s->trace_on) { s->traces[0].clear(); pv.trace = &s->traces[0]; }
+      PlonkProof p = pv.prove(zk, s->h_tau[0], (const Fr*)public_inputs, wit_a[0], nullptr, deterministic != 0, wit_on_device != 0, rounds == 1);
+      memcpy(s->round_s[0], pv.round_s, sizeof(pv.round_s));
+      plonk_proof_pack(p, lq, (uint64_t*)proofs_out);
+      return;
+    }
     std::thread th[3];
     std::string errs[3];
-    Round1Proof proofs[3];
+    PlonkProof proofs[3];
     for (int i = 0; i < 3; i++) {
       const void* a = wit_a[i];
       const void* b = wit_b[i];
       th[i] = std::thread([&, i, a, b] {
         try {
-          uint64_t h = 0;
-          check(drv[i]->ctx, cocg_bases_share(drv[i]->ctx, z->zk.owner, z->zk.p_tau, &h), "share p_tau");
-          CoPlonkRound1<Rep3Protocol> r1(*drv[i]);
-          proofs[i] = r1.round1(z->zk, h, (const Fr*)public_inputs, (const Fr*)a, (const Fr*)b, deterministic != 0);
+          CoPlonk<Rep3Protocol> pv(*s->drv[i]);
+          if (s->trace_on) { s->traces[i].clear(); pv.trace = &s->traces[i]; }
+          proofs[i] = pv.prove(zk, s->h_tau[i], (const Fr*)public_inputs, a, b, deterministic != 0, wit_on_device != 0, rounds == 1);
+          memcpy(s->round_s[i], pv.round_s, sizeof(pv.round_s));
         } catch (const std::exception& e) {
           errs[i] = e.what();
-          net.close_all();
+          s->net->close_all();
         }
       });
     }
     for (auto& t : th) t.join();
     for (int i = 0; i < 3; i++)
-      if (!errs[i].empty()) throw Error("party " + std::to_string(i) + ": " + errs[i]);
-    const size_t lq = z->lq;
-    for (int i = 0; i < 3; i++) {
-      uint64_t* o = (uint64_t*)commits_out + (size_t)i * 6 * lq;
-      memcpy(o, proofs[i].commit_a.l, 2 * lq * 8);
-      memcpy(o + 2 * lq, proofs[i].commit_b.l, 2 * lq * 8);
-      memcpy(o + 4 * lq, proofs[i].commit_c.l, 2 * lq * 8);
-    }
+      if (!errs[i].empty()) {
+        s->failed = true;
+        throw Error("party " + std::to_string(i) + ": " + errs[i]);
+      }
+    for (int i = 0; i < 3; i++) plonk_proof_pack(proofs[i], lq, (uint64_t*)proofs_out + (size_t)i * pl);
   });
+}
+extern "C" int cohost_plonk_prove(cohost_plonk_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b, int deterministic,
+                                  int wit_on_device, void* proofs_out) {
+  return plonk_prove_impl(s, public_inputs, wit_a, wit_b, deterministic, wit_on_device, 5, proofs_out);
+}
+extern "C" size_t cohost_plonk_proof_limbs(cohost_plonk_zkey* z) { return z ? 18 * z->lq + 24 : 0; }
+extern "C" int cohost_plonk_set_mpc_exchange(cohost_plonk_session* s, int device) {
+  if (!s) return fail("cohost_plonk_set_mpc_exchange: null session");
+  if (s->net) s->net->device_exchange = device != 0;
+  return 0;
+}
+extern "C" uint64_t cohost_plonk_launch_count(cohost_plonk_session* s) {
+  uint64_t t = 0;
+  if (s)
+    for (int i = 0; i < s->parties; i++) t += cocg_launch_count(s->driver(i)->ctx);
+  return t;
+}
+extern "C" int cohost_plonk_profile_enable(cohost_plonk_session* s, int on) {
+  if (!s) return fail("null session");
+  for (int i = 0; i < s->parties; i++) cocg_profile_enable(s->driver(i)->ctx, on);
+  return 0;
+}
+extern "C" int cohost_plonk_profile_reset(cohost_plonk_session* s) {
+  if (!s) return fail("null session");
+  for (int i = 0; i < s->parties; i++) cocg_profile_reset(s->driver(i)->ctx);
+  return 0;
+}
+extern "C" int cohost_plonk_profile_read(cohost_plonk_session* s, int cls, double* total_ms, uint64_t* scopes) {
+  if (!s) return fail("null session");
+  double t = 0;
+  uint64_t n = 0;
+  for (int i = 0; i < s->parties; i++) {
+    double ms = 0;
+    uint64_t k = 0;
+    if (cocg_profile_read(s->driver(i)->ctx, cls, &ms, &k)) return fail(cocg_last_error(s->driver(i)->ctx));
+    t += ms;
+    n += k;
+  }
+  if (total_ms) *total_ms = t;
+  if (scopes) *scopes = n;
+  return 0;
+}
+// Host wall-clock per round of the last proof, seconds: out[party * 5 + round].
+extern "C" int cohost_plonk_round_times(cohost_plonk_session* s, double* out) {
+  if (!s || !out) return fail("cohost_plonk_round_times: null argument");
+  for (int i = 0; i < s->parties; i++) memcpy(out + 5 * i, s->round_s[i], 5 * sizeof(double));
+  return 0;
+}
+// Test hook: keep component a of named intermediate vectors of the next proofs (buffer_z, poly_z, t_evals, tz_evals, t1, t2, t3, poly_r,
+// wxi, ...); the sum over the three parties is the plain value.  get: out == NULL queries the length.
+extern "C" int cohost_plonk_trace_enable(cohost_plonk_session* s, int on) {
+  if (!s) return fail("null session");
+  s->trace_on = on != 0;
+  return 0;
+}
+extern "C" int cohost_plonk_trace_get(cohost_plonk_session* s, int party, const char* name, void* out, size_t cap, size_t* n) {
+  if (!s || !name || !n || party < 0 || party >= s->parties) return fail("cohost_plonk_trace_get: bad argument");
+  auto it = s->traces[party].find(name);
+  if (it == s->traces[party].end()) return fail(std::string("cohost_plonk_trace_get: no vector named ") + name);
+  *n = it->second.size();
+  if (out) {
+    if (cap < it->second.size()) return fail("cohost_plonk_trace_get: buffer too small");
+    memcpy(out, it->second.data(), it->second.size() * 32);
+  }
+  return 0;
+}
+
+// Round 1 only (kept from the first build of this path): commitments [a]_1 | [b]_1 | [c]_1, packed affine.
+extern "C" int cohost_plonk_round1_plain(cohost_plonk_zkey* z, const void* public_inputs, const void* witness, int deterministic, void* commits_out) {
+  if (!z || !public_inputs || !witness || !commits_out) return fail("cohost_plonk_round1_plain: null argument");
+  cohost_plonk_session* s = nullptr;
+  uint8_t seed[32] = {};
+  if (cohost_plonk_session_create(z, 0, seed, &s)) return 1;
+  std::vector<uint64_t> pr(18 * z->lq + 24);
+  const void* w[1] = {witness};
+  int rc = plonk_prove_impl(s, public_inputs, w, nullptr, deterministic, 0, 1, pr.data());
+  cohost_plonk_session_destroy(s);
+  if (rc) return rc;
+  memcpy(commits_out, pr.data(), 6 * z->lq * 8);
+  return 0;
+}
+extern "C" int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                        const uint8_t* seeds, int deterministic, void* commits_out) {
+  if (!z || !public_inputs || !wit_a || !wit_b || !seeds || !commits_out) return fail("cohost_plonk_round1_rep3: null argument");
+  cohost_plonk_session* s = nullptr;
+  if (cohost_plonk_session_create(z, 1, seeds, &s)) return 1;
+  const size_t pl = 18 * z->lq + 24;
+  std::vector<uint64_t> pr(3 * pl);
+  int rc = plonk_prove_impl(s, public_inputs, wit_a, wit_b, deterministic, 0, 1, pr.data());
+  cohost_plonk_session_destroy(s);
+  if (rc) return rc;
+  for (int i = 0; i < 3; i++) memcpy((uint64_t*)commits_out + (size_t)i * 6 * z->lq, pr.data() + (size_t)i * pl, 6 * z->lq * 8);
+  return 0;
 }
 
 // How the three co-located parties of a session move share vectors in the mul_vec rounds: 0 = staged through pinned host memory
@@ -824,6 +1060,17 @@ extern "C" int cohost_proof_to_json(int curve, const void* proof, char* out, siz
   return g ? g : rc;
 }
 // pub: count Montgomery Fr, pub[0] = the constant 1 (skipped in the output like the reference's writer)
+extern "C" int cohost_plonk_proof_to_json(int curve, const void* proof, char* out, size_t cap, size_t* len) {
+  if (!proof || !len) return fail("cohost_plonk_proof_to_json: null argument");
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_plonk_proof_to_json: unknown curve");
+  return guarded([&] {
+    std::string s = plonk_proof_to_json(curve, (const uint64_t*)proof);
+    *len = s.size();
+    if (!out) return;
+    if (cap < s.size()) throw Error("cohost_plonk_proof_to_json: buffer too small");
+    memcpy(out, s.data(), s.size());
+  });
+}
 extern "C" int cohost_public_inputs_to_json(int curve, const void* pub, size_t count, char* out, size_t cap, size_t* len) {
   if (!pub && count) return fail("cohost_public_inputs_to_json: null argument");
   if (curve != COCG_BN254 && curve != COCG_BLS12_381) return fail("cohost_public_inputs_to_json: unknown curve");

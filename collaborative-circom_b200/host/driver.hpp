@@ -35,6 +35,15 @@ struct FrOps {
   Fr sub(const Fr& a, const Fr& b) const { return bin(a, b, [](auto x, auto y) { return cocg::fp_sub(x, y); }); }
   Fr mul(const Fr& a, const Fr& b) const { return bin(a, b, [](auto x, auto y) { return cocg::fp_mul(x, y); }); }
   Fr from_mont(const Fr& a) const { return un(a, [](auto x) { return cocg::fp_from_mont(x); }); }
+  Fr neg(const Fr& a) const { return un(a, [](auto x) { return cocg::fp_neg(x); }); }
+  Fr sqr(const Fr& a) const { return un(a, [](auto x) { return cocg::fp_sqr(x); }); }
+  Fr inv(const Fr& a) const { return un(a, [](auto x) { return cocg::fp_inv(x); }); }
+  bool is_zero(const Fr& a) const { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+  Fr from_u64(uint64_t v) const {  // Montgomery form of a small integer
+    Fr acc = zero(), base = one();
+    for (; v; v >>= 1) { if (v & 1) acc = add(acc, base); base = add(base, base); }
+    return acc;
+  }
   Fr zero() const { Fr z; memset(z.l, 0, 32); return z; }
   Fr one() const { return un(zero(), [](auto x) { return decltype(x)::one(); }); }
 };
@@ -91,6 +100,31 @@ class DeviceDriver {
     return v;
   }
   void download(const DevVec& v, void* host) { check(ctx, cocg_d2h(ctx, host, v.p, v.n * 32), "cocg_d2h"); }
+  // non-owning view of a sub-range (never released)
+  static DevVec slice(const DevVec& v, size_t off, size_t n) {
+    if (off + n > v.n) throw Error("slice: range");
+    return DevVec{v.at(off), n};
+  }
+  static FieldShareVec slice(const FieldShareVec& v, size_t off, size_t n) {
+    FieldShareVec o;
+    o.a = slice(v.a, off, n);
+    if (v.b.p) o.b = slice(v.b, off, n);
+    return o;
+  }
+  // ---- public (opened) vectors in HBM: the CoPlonk rounds keep them on the device between steps
+  DevVec pub_mul(const DevVec& a, const DevVec& b) { DevVec o = alloc(a.n); check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.p, b.p, o.p, a.n), "cocg_vec_op"); return o; }
+  void pub_scan_mul(DevVec& v) { check(ctx, cocg_vec_scan(ctx, COCG_OP_MUL, v.p, v.p, v.n), "cocg_vec_scan"); }
+  // 1 / v element-wise; a zero raises the reference's error (rep3.rs:549-554, plain.rs inverse().unwrap())
+  void pub_inv(DevVec& v) {
+    size_t zeros = 0;
+    check(ctx, cocg_vec_inv(ctx, v.p, v.p, v.n, &zeros), "cocg_vec_inv");
+    if (zeros) throw Error("During execution of inverse in MPC: cannot compute inverse of zero");
+  }
+  Fr eval_public(const DevVec& coeffs, size_t n, const Fr& point) {
+    Fr r;
+    check(ctx, cocg_poly_eval(ctx, coeffs.p, n, point.l, r.l), "cocg_poly_eval");
+    return r;
+  }
 
   // ---- O(1) group operations on host Jacobian points (K7)
   Point ec(int group, int op, const Point* a, const void* b = nullptr) {
@@ -203,6 +237,47 @@ class PlainDriver : public DeviceDriver {
   Point open_point(int, const PointShare& a) { return a.a; }
   std::pair<Point, Point> open_two_points(const PointShare& a, const PointShare& b) { return {a.a, b.a}; }
 
+  // ---- CoPlonk (co-plonk/src/round*.rs) driver surface: plain.rs:111-285
+  int pub_comp() const { return 0; }
+  std::vector<FieldShare> mul_many(const std::vector<FieldShare>& a, const std::vector<FieldShare>& b) {  // plain.rs:123-131
+    std::vector<FieldShare> r(a.size());
+    for (size_t i = 0; i < a.size(); i++) r[i] = mul(a[i], b[i]);
+    return r;
+  }
+  std::vector<Fr> open_many(const std::vector<FieldShare>& a) { std::vector<Fr> r; for (auto& x : a) r.push_back(x.a); return r; }
+  FieldShareVec alloc_share(size_t n) { return FieldShareVec{alloc(n), DevVec{}}; }
+  FieldShareVec rand_vec(size_t n) {
+    FieldShareVec o = alloc_share(n);
+    check(ctx, cocg_prf_fill(ctx, seed, ctr++, o.a.p, n), "cocg_prf_fill");
+    return o;
+  }
+  // several independent products: the plain driver has no network round to share
+  std::vector<FieldShareVec> mul_vec_many(const std::vector<std::pair<const FieldShareVec*, const FieldShareVec*>>& ops) {
+    std::vector<FieldShareVec> r;
+    for (auto& o : ops) r.push_back(mul_vec(*o.first, *o.second));
+    return r;
+  }
+  void release_many(std::vector<FieldShareVec>& v) { for (auto& x : v) release(x); v.clear(); }
+  DevVec mul_open_many(const FieldShareVec& a, const FieldShareVec& b) { return pub_mul(a.a, b.a); }  // plain.rs:267-285
+  FieldShareVec inv_many(const FieldShareVec& a) {  // plain.rs:141-152
+    FieldShareVec o = alloc_share(a.len());
+    check(ctx, cocg_d2d(ctx, o.a.p, a.a.p, a.len() * 32), "cocg_d2d");
+    pub_inv(o.a);
+    return o;
+  }
+  void mul_assign_public_vec(FieldShareVec& a, const DevVec& pub) { check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.a.p, pub.p, a.a.p, a.len()), "cocg_vec_op"); }
+  // array_prod_mul! (round2.rs:17-42): prefix products; without a network the blinding by random r is pointless, the value is the same
+  FieldShareVec array_prod_mul(const FieldShareVec& inp) {
+    FieldShareVec o = alloc_share(inp.len());
+    check(ctx, cocg_vec_scan(ctx, COCG_OP_MUL, inp.a.p, o.a.p, inp.len()), "cocg_vec_scan");
+    return o;
+  }
+  FieldShare evaluate_poly_public(const FieldShareVec& poly, size_t n, const Fr& point) { return FieldShare{eval_public(poly.a, n, point), fr.zero()}; }
+  // the party's additive output of a fused kernel becomes the share itself
+  FieldShareVec reshare(DevVec local) { return FieldShareVec{local, DevVec{}}; }
+  const uint8_t* seed_own() const { return seed; }
+  const uint8_t* seed_prev() const { return seed; }
+  uint32_t take_ctr(uint32_t k) { uint32_t c = ctr; ctr += k; return c; }
  private:
   void ntt(FieldShareVec& v, const Domain& d, int inverse, const Fr* coset_g) {
     if (v.len() != d.size()) throw Error("fft: vector length != domain size");
@@ -398,7 +473,181 @@ class Rep3Protocol : public DeviceDriver {
     return {ec_add(1, r1, ec_add(1, a.a, a.b)), ec_add(2, r2, ec_add(2, b.a, b.b))};
   }
 
+  // ---- CoPlonk (co-plonk/src/round*.rs) driver surface: rep3.rs:503-760
+  int pub_comp() const { return id() == 0 ? 0 : id() == 1 ? 1 : -1; }
+  const uint8_t* seed_own() const { return seed1; }
+  const uint8_t* seed_prev() const { return seed2; }
+  uint32_t take_ctr(uint32_t k) { uint32_t c = ctr; ctr += k; return c; }
+  FieldShareVec alloc_share(size_t n) { return FieldShareVec{alloc(n), alloc(n)}; }
+  // mul_many on a handful of scalars (rep3.rs:513-528): one message for all of them
+  std::vector<FieldShare> mul_many(const std::vector<FieldShare>& a, const std::vector<FieldShare>& b) {
+    std::vector<Fr> loc(a.size()), rcv(a.size());
+    for (size_t i = 0; i < a.size(); i++)
+      loc[i] = fr.add(fr.add(fr.mul(a[i].a, fr.add(b[i].a, b[i].b)), fr.mul(a[i].b, b[i].a)), masking_field_element());
+    net->send_next_bytes(loc.data(), loc.size() * 32);
+    net->recv_prev_bytes(rcv.data(), rcv.size() * 32);
+    std::vector<FieldShare> r(a.size());
+    for (size_t i = 0; i < a.size(); i++) r[i] = FieldShare{loc[i], rcv[i]};
+    return r;
+  }
+  std::vector<Fr> open_many(const std::vector<FieldShare>& a) {  // rep3.rs:620-628
+    std::vector<Fr> bs(a.size()), cs(a.size());
+    for (size_t i = 0; i < a.size(); i++) bs[i] = a[i].b;
+    net->send_next_bytes(bs.data(), bs.size() * 32);
+    net->recv_prev_bytes(cs.data(), cs.size() * 32);
+    for (size_t i = 0; i < a.size(); i++) cs[i] = fr.add(cs[i], fr.add(a[i].a, a[i].b));
+    return cs;
+  }
+  FieldShareVec rand_vec(size_t n) {  // n x rand(): (F(seed1), F(seed2)) under one vector counter
+    FieldShareVec o = alloc_share(n);
+    check(ctx, cocg_prf_fill(ctx, seed1, ctr, o.a.p, n), "cocg_prf_fill");
+    check(ctx, cocg_prf_fill(ctx, seed2, ctr, o.b.p, n), "cocg_prf_fill");
+    ctr++;
+    return o;
+  }
+  // send `local` to the next party, receive the previous party's vector of the same length (send_next_many / recv_prev_many)
+  DevVec exchange_next(const DevVec& local) {
+    const size_t n = local.n;
+    if (net->device_exchange()) {
+      DevVec copy = alloc(n);
+      check(ctx, cocg_d2d(ctx, copy.p, local.p, n * 32), "cocg_d2d");
+      check(ctx, cocg_sync(ctx), "cocg_sync");
+      Message s;
+      s.bytes = n * 32;
+      s.device = copy.p;
+      net->send_next(std::move(s));
+      Message m = net->recv_prev();
+      if (m.bytes != n * 32 || !m.device) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
+      return DevVec{m.device, n};
+    }
+    std::shared_ptr<void> buf = pinned(n * 32);
+    check(ctx, cocg_d2h(ctx, buf.get(), local.p, n * 32), "cocg_d2h");
+    net->send_next(Message{buf, n * 32});
+    buf.reset();
+    Message m = net->recv_prev();
+    if (m.bytes != n * 32) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
+    DevVec r = alloc(n);
+    check(ctx, cocg_h2d(ctx, r.p, m.data.get(), n * 32), "cocg_h2d");
+    return r;
+  }
+  FieldShareVec reshare(DevVec local) { DevVec b = exchange_next(local); return FieldShareVec{local, b}; }
+  // Several independent products in ONE network round: the local steps write slices of one buffer, one message carries them all.
+  // Results are views into two pooled buffers; release_many() returns those.
+  std::vector<FieldShareVec> mul_vec_many(const std::vector<std::pair<const FieldShareVec*, const FieldShareVec*>>& ops) {
+    size_t total = 0;
+    for (auto& o : ops) { if (o.first->len() != o.second->len()) throw Error("mul_vec: length mismatch"); total += o.first->len(); }
+    DevVec loc = alloc(total);
+    size_t off = 0;
+    for (auto& o : ops) {
+      const size_t n = o.first->len();
+      check(ctx, cocg_rep3_mul_local_prf(ctx, o.first->a.p, o.first->b.p, o.second->a.p, o.second->b.p, seed1, seed2, ctr++, loc.at(off), n), "cocg_rep3_mul_local_prf");
+      off += n;
+    }
+    DevVec rcv = exchange_next(loc);
+    std::vector<FieldShareVec> r;
+    off = 0;
+    for (auto& o : ops) {
+      const size_t n = o.first->len();
+      r.push_back(FieldShareVec{slice(loc, off, n), slice(rcv, off, n)});
+      off += n;
+    }
+    many_owned_.push_back({r.empty() ? nullptr : r[0].a.p, loc, rcv});
+    return r;
+  }
+  void release_many(std::vector<FieldShareVec>& v) {
+    if (!v.empty())
+      for (size_t k = 0; k < many_owned_.size(); k++)
+        if (many_owned_[k].key == v[0].a.p) {
+          release(many_owned_[k].loc);
+          release(many_owned_[k].rcv);
+          many_owned_.erase(many_owned_.begin() + k);
+          break;
+        }
+    v.clear();
+  }
+  // mul_open_many (rep3.rs:738-757): local product + mask to BOTH other parties, sum of the three
+  DevVec mul_open_many(const FieldShareVec& a, const FieldShareVec& b) {
+    const size_t n = a.len();
+    DevVec loc = alloc(n);
+    check(ctx, cocg_rep3_mul_local_prf(ctx, a.a.p, a.b.p, b.a.p, b.b.p, seed1, seed2, ctr++, loc.p, n), "cocg_rep3_mul_local_prf");
+    DevVec from_prev, from_next;
+    const int nxt = (id() + 1) % 3, prv = (id() + 2) % 3;
+    if (net->device_exchange()) {
+      for (int k = 0; k < 2; k++) {
+        DevVec copy = alloc(n);
+        check(ctx, cocg_d2d(ctx, copy.p, loc.p, n * 32), "cocg_d2d");
+        check(ctx, cocg_sync(ctx), "cocg_sync");
+        Message s;
+        s.bytes = n * 32;
+        s.device = copy.p;
+        net->send(k == 0 ? nxt : prv, std::move(s));
+      }
+      Message m1 = net->recv(prv), m2 = net->recv(nxt);
+      if (m1.bytes != n * 32 || m2.bytes != n * 32 || !m1.device || !m2.device) throw Error("mul_open_many: Invalid number of elements received");
+      from_prev = DevVec{m1.device, n};
+      from_next = DevVec{m2.device, n};
+    } else {
+      std::shared_ptr<void> buf = pinned(n * 32);
+      check(ctx, cocg_d2h(ctx, buf.get(), loc.p, n * 32), "cocg_d2h");
+      net->send(nxt, Message{buf, n * 32});
+      net->send(prv, Message{buf, n * 32});
+      buf.reset();
+      Message m1 = net->recv(prv), m2 = net->recv(nxt);
+      if (m1.bytes != n * 32 || m2.bytes != n * 32) throw Error("mul_open_many: Invalid number of elements received");
+      from_prev = alloc(n);
+      from_next = alloc(n);
+      check(ctx, cocg_h2d(ctx, from_prev.p, m1.data.get(), n * 32), "cocg_h2d");
+      check(ctx, cocg_h2d(ctx, from_next.p, m2.data.get(), n * 32), "cocg_h2d");
+    }
+    check(ctx, cocg_vec_op(ctx, COCG_OP_ADD, loc.p, from_prev.p, loc.p, n), "cocg_vec_op");
+    check(ctx, cocg_vec_op(ctx, COCG_OP_ADD, loc.p, from_next.p, loc.p, n), "cocg_vec_op");
+    release(from_prev);
+    release(from_next);
+    return loc;
+  }
+  void mul_assign_public_vec(FieldShareVec& a, const DevVec& pub) {  // mul_with_public per element
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.a.p, pub.p, a.a.p, a.len()), "cocg_vec_op");
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.b.p, pub.p, a.b.p, a.len()), "cocg_vec_op");
+  }
+  FieldShareVec inv_many(const FieldShareVec& a) {  // rep3.rs:544-558: r random, y = open(a * r), a^-1 = r / y
+    FieldShareVec r = rand_vec(a.len());
+    DevVec y = mul_open_many(a, r);
+    pub_inv(y);
+    mul_assign_public_vec(r, y);
+    release(y);
+    return r;
+  }
+  // array_prod_mul! (round2.rs:17-42, after Ozdemir-Boneh): prefix products of a shared vector in a constant number of rounds
+  FieldShareVec array_prod_mul(const FieldShareVec& inp) {
+    const size_t len = inp.len();
+    FieldShareVec r = rand_vec(len + 1);
+    FieldShareVec r_inv = inv_many(r);
+    Fr h[2];
+    check(ctx, cocg_d2h(ctx, h[0].l, r_inv.a.p, 32), "cocg_d2h");
+    check(ctx, cocg_d2h(ctx, h[1].l, r_inv.b.p, 32), "cocg_d2h");
+    FieldShareVec r_inv0 = alloc_share(len);  // vec![r_inv[0]; len]
+    check(ctx, cocg_vec_fill(ctx, r_inv0.a.p, len, h[0].l), "cocg_vec_fill");
+    check(ctx, cocg_vec_fill(ctx, r_inv0.b.p, len, h[1].l), "cocg_vec_fill");
+    const FieldShareVec r_tail = slice(r, 1, len), r_head = slice(r, 0, len), r_inv_tail = slice(r_inv, 1, len);
+    std::vector<FieldShareVec> pr = mul_vec_many({{&r_inv0, &r_tail}, {&r_head, &inp}});  // unblind | mul
+    DevVec open = mul_open_many(pr[1], r_inv_tail);
+    pub_scan_mul(open);
+    FieldShareVec unblind = alloc_share(len);
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, pr[0].a.p, open.p, unblind.a.p, len), "cocg_vec_op");
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, pr[0].b.p, open.p, unblind.b.p, len), "cocg_vec_op");
+    release(open);
+    release_many(pr);
+    release(r_inv0);
+    release(r);
+    release(r_inv);
+    return unblind;
+  }
+  FieldShare evaluate_poly_public(const FieldShareVec& poly, size_t n, const Fr& point) {  // rep3.rs:923-928
+    return FieldShare{eval_public(poly.a, n, point), eval_public(poly.b, n, point)};
+  }
  private:
+  struct ManyOwned { void* key; DevVec loc, rcv; };
+  std::vector<ManyOwned> many_owned_;
   void ntt(FieldShareVec& v, const Domain& d, int inverse, const Fr* coset_g) {
     if (v.len() != d.size()) throw Error("fft: vector length != domain size");
     void* vecs[2] = {v.a.p, v.b.p};

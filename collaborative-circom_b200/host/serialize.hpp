@@ -84,6 +84,24 @@ inline std::string proof_to_json(int curve, const uint64_t* proof) {
   return s;
 }
 
+// PlonkProof via serde_json (circom-types/src/plonk/proof.rs:7-87): A B C Z T1 T2 T3 Wxi Wxiw as G1 [x, y, "1"], then eval_a eval_b eval_c
+// eval_s1 eval_s2 eval_zw as decimal strings, "protocol":"plonk", "curve".  proof: 9 packed affine points | 6 Fr (what cohost_plonk_prove writes)
+inline std::string plonk_proof_to_json(int curve, const uint64_t* proof) {
+  const size_t lq = curve == COCG_BN254 ? 4 : 6;
+  auto q = [&](const uint64_t* p) { return "\"" + field_to_decimal(curve, false, p) + "\""; };
+  auto g1 = [&](const uint64_t* p) {
+    if (limbs_zero(p, 2 * lq)) return std::string("[\"0\",\"1\",\"0\"]");
+    return "[" + q(p) + "," + q(p + lq) + ",\"1\"]";
+  };
+  static const char* pn[9] = {"A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw"};
+  static const char* en[6] = {"eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"};
+  std::string s = "{";
+  for (int i = 0; i < 9; i++) s += std::string(i ? "," : "") + "\"" + pn[i] + "\":" + g1(proof + (size_t)i * 2 * lq);
+  for (int i = 0; i < 6; i++) s += std::string(",\"") + en[i] + "\":\"" + field_to_decimal(curve, true, proof + 18 * lq + (size_t)i * 4) + "\"";
+  s += std::string(",\"protocol\":\"plonk\",\"curve\":\"") + (curve == COCG_BN254 ? "bn128" : "bls12381") + "\"}";
+  return s;
+}
+
 // pub: n_public + 1 Montgomery Fr with the constant 1 in front (SharedWitness::public_inputs); the 1 is skipped
 inline std::string public_inputs_to_json(int curve, const uint64_t* pub, size_t count) {
   std::string s = "[";

@@ -28,6 +28,10 @@ HOST_SYMBOLS = [
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
     "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
+    "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
+    "cohost_plonk_prove", "cohost_plonk_set_mpc_exchange", "cohost_plonk_launch_count", "cohost_plonk_profile_enable",
+    "cohost_plonk_profile_reset", "cohost_plonk_profile_read", "cohost_plonk_round_times", "cohost_plonk_trace_enable",
+    "cohost_plonk_trace_get", "cohost_plonk_proof_to_json",
 ]
 PROF_CLASSES = ["msm_sort", "msm_accumulate", "msm_reduce", "ntt", "vec", "spmv"]
 
@@ -98,6 +102,23 @@ def load_host():
     L.cohost_plonk_zkey_get_info.argtypes = [vp, ctypes.POINTER(sz)]
     L.cohost_plonk_round1_plain.argtypes = [vp, vp, vp, ci, vp]
     L.cohost_plonk_round1_rep3.argtypes = [vp, vp, pvp, pvp, vp, ci, vp]
+    L.cohost_plonk_zkey_create_synthetic.argtypes = [ci, ci, sz, sz, sz, sz, vp, vp, vp, vp, pvp]
+    L.cohost_plonk_proof_limbs.argtypes = [vp]
+    L.cohost_plonk_proof_limbs.restype = sz
+    L.cohost_plonk_session_create.argtypes = [vp, ci, vp, pvp]
+    L.cohost_plonk_session_destroy.argtypes = [vp]
+    L.cohost_plonk_session_destroy.restype = None
+    L.cohost_plonk_prove.argtypes = [vp, vp, pvp, pvp, ci, ci, vp]
+    L.cohost_plonk_set_mpc_exchange.argtypes = [vp, ci]
+    L.cohost_plonk_launch_count.argtypes = [vp]
+    L.cohost_plonk_launch_count.restype = u64
+    L.cohost_plonk_profile_enable.argtypes = [vp, ci]
+    L.cohost_plonk_profile_reset.argtypes = [vp]
+    L.cohost_plonk_profile_read.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
+    L.cohost_plonk_round_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.cohost_plonk_trace_enable.argtypes = [vp, ci]
+    L.cohost_plonk_trace_get.argtypes = [vp, ci, ctypes.c_char_p, vp, sz, ctypes.POINTER(sz)]
+    L.cohost_plonk_proof_to_json.argtypes = [ci, vp, vp, sz, ctypes.POINTER(sz)]
     L.cohost_rep3_set_mpc_exchange.argtypes = [vp, ci]
     L.cohost_rep3_phase_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.cohost_shamir_session_create.argtypes = [vp, ci, ci, vp, pvp]
@@ -535,21 +556,45 @@ class ShamirSession:
             self.h = None
 
 
-class PlonkZKey:
-    """What round 1 of the Plonk prover consumes from a snarkjs Plonk zkey (p_tau resident in HBM)."""
+def plonk_proof_to_json(curve: int, proof) -> str:
+    """snarkjs / serde_json text of a Plonk proof block (9 points | 6 evaluations) as `co-circom generate-proof plonk` writes it."""
+    L = load_host()
+    p = _c(proof)
+    return _sized(lambda out, cap, n: L.cohost_plonk_proof_to_json(curve, p.ctypes.data, out, cap, n)).decode()
 
-    def __init__(self, path: str, device: int = 0):
-        h = vp()
-        _ck(load_host().cohost_plonk_zkey_load_file(path.encode(), device, ctypes.byref(h)))
+
+class PlonkZKey:
+    """A snarkjs Plonk proving key resident in HBM: wire maps, selector / sigma / Lagrange polynomials, p_tau."""
+
+    def __init__(self, path: str | None = None, device: int = 0, _handle=None):
+        if _handle is None:
+            h = vp()
+            _ck(load_host().cohost_plonk_zkey_load_file(path.encode(), device, ctypes.byref(h)))
+        else:
+            h = _handle
         self.h = h
         info = (sz * 6)()
         _ck(load_host().cohost_plonk_zkey_get_info(h, info))
         self.curve, self.n_vars, self.n_public, self.domain_size, self.n_additions, self.n_constraints = (int(x) for x in info)
         self.lq = 4 if self.curve == _lib.BN254 else 6
+        self.n_witness = self.n_vars - self.n_additions - self.n_public - 1
+        self.proof_limbs = int(load_host().cohost_plonk_proof_limbs(h))
+
+    @classmethod
+    def synthetic(cls, curve: int, log_n: int, n_public: int, n_vars: int, maps, seed: bytes, device: int = 0) -> "PlonkZKey":
+        """Shape-faithful benchmark key: maps = (map_a, map_b, map_c) uint32 arrays of n_constraints wire indices < n_vars."""
+        _need(len(seed) == 32, "synthetic plonk key: seed must be 32 bytes")
+        ma, mb, mc = (_c(m, np.uint32) for m in maps)
+        _need(ma.size == mb.size == mc.size, "synthetic plonk key: the three wire maps must have the same length")
+        sd = np.frombuffer(seed, dtype=np.uint8).copy()
+        h = vp()
+        _ck(load_host().cohost_plonk_zkey_create_synthetic(curve, device, log_n, n_public, n_vars, ma.size, ma.ctypes.data, mb.ctypes.data, mc.ctypes.data,
+                                                           sd.ctypes.data, ctypes.byref(h)))
+        return cls(_handle=h)
 
     def round1_plain(self, public_inputs, witness, deterministic=True) -> np.ndarray:
         pub, wit = _c(public_inputs), _c(witness)
-        _need(pub.size == 4 * (self.n_public + 1) and wit.size == 4 * (self.n_vars - self.n_additions - self.n_public - 1), "round1: wrong input length")
+        _need(pub.size == 4 * (self.n_public + 1) and wit.size == 4 * self.n_witness, "round1: wrong input length")
         out = np.zeros((3, 2 * self.lq), dtype=np.uint64)
         _ck(load_host().cohost_plonk_round1_plain(self.h, pub.ctypes.data, wit.ctypes.data, 1 if deterministic else 0, out.ctypes.data))
         return out
@@ -557,6 +602,7 @@ class PlonkZKey:
     def round1_rep3(self, public_inputs, wit_a, wit_b, seeds: bytes = bytes(range(96)), deterministic=True) -> np.ndarray:
         pub = _c(public_inputs)
         wa, wb = [_c(x) for x in wit_a], [_c(x) for x in wit_b]
+        _need(pub.size == 4 * (self.n_public + 1) and all(x.size == 4 * self.n_witness for x in wa + wb), "round1: wrong input length")
         A = (vp * 3)(*[x.ctypes.data for x in wa])
         B = (vp * 3)(*[x.ctypes.data for x in wb])
         sd = np.frombuffer(seeds, dtype=np.uint8).copy()
@@ -567,4 +613,81 @@ class PlonkZKey:
     def close(self):
         if self.h:
             load_host().cohost_plonk_zkey_destroy(self.h)
+            self.h = None
+
+
+class PlonkSession:
+    """CoPlonk::prove: protocol 'plain' (one party) or 'rep3' (three parties on three threads, in-process network)."""
+
+    def __init__(self, zkey: PlonkZKey, protocol: str = "plain", seeds: bytes | None = None):
+        _need(protocol in ("plain", "rep3"), "PlonkSession: protocol must be plain or rep3")
+        self.zkey, self.parties = zkey, (1 if protocol == "plain" else 3)
+        seeds = os.urandom(32 * self.parties) if seeds is None else seeds  # blinders and masks derive from these: entropy by default
+        _need(len(seeds) == 32 * self.parties, "PlonkSession: seeds must be 32 bytes per party")
+        self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
+        h = vp()
+        _ck(load_host().cohost_plonk_session_create(zkey.h, 0 if protocol == "plain" else 1, self._seeds.ctypes.data, ctypes.byref(h)))
+        self.h = h
+
+    def prove(self, public_inputs, wit_a, wit_b=None, deterministic=False, device_ptrs=False) -> np.ndarray:
+        """wit_a / wit_b: one array (or raw address) per party.  Returns (parties, proof_limbs) uint64."""
+        zk = self.zkey
+        pub = _c(public_inputs)
+        _need(pub.size == 4 * (zk.n_public + 1), f"prove: expected {zk.n_public + 1} public inputs")
+        keep = []
+
+        def addr(x):
+            if isinstance(x, int):
+                return x
+            a = _c(x)
+            _need(a.size == 4 * zk.n_witness, f"prove: expected {zk.n_witness} witness share elements")
+            keep.append(a)
+            return a.ctypes.data
+
+        _need(len(wit_a) == self.parties and (self.parties == 1 or (wit_b is not None and len(wit_b) == 3)), "prove: one share per party")
+        A = (vp * self.parties)(*[addr(x) for x in wit_a])
+        B = None if wit_b is None else (vp * self.parties)(*[addr(x) for x in wit_b])
+        out = np.zeros((self.parties, zk.proof_limbs), dtype=np.uint64)
+        _ck(load_host().cohost_plonk_prove(self.h, pub.ctypes.data, A, B, 1 if deterministic else 0, 1 if device_ptrs else 0, out.ctypes.data))
+        return out
+
+    def set_mpc_exchange(self, mode: str):
+        _need(mode in ("host", "device"), "set_mpc_exchange: mode must be host or device")
+        _ck(load_host().cohost_plonk_set_mpc_exchange(self.h, 1 if mode == "device" else 0))
+
+    def launch_count(self) -> int:
+        return int(load_host().cohost_plonk_launch_count(self.h))
+
+    def profile(self, on: bool = True):
+        _ck(load_host().cohost_plonk_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        _ck(load_host().cohost_plonk_profile_reset(self.h))
+
+    def profile_read(self) -> dict:
+        out = {}
+        for i, name in enumerate(PROF_CLASSES):
+            ms, k = ctypes.c_double(), u64()
+            _ck(load_host().cohost_plonk_profile_read(self.h, i, ctypes.byref(ms), ctypes.byref(k)))
+            out[name] = (ms.value, int(k.value))
+        return out
+
+    def round_times(self) -> np.ndarray:
+        out = (ctypes.c_double * 15)()
+        _ck(load_host().cohost_plonk_round_times(self.h, out))
+        return np.array(out).reshape(3, 5)[:self.parties]
+
+    def trace(self, on: bool = True):
+        _ck(load_host().cohost_plonk_trace_enable(self.h, 1 if on else 0))
+
+    def trace_get(self, party: int, name: str) -> np.ndarray:
+        n = sz(0)
+        _ck(load_host().cohost_plonk_trace_get(self.h, party, name.encode(), None, 0, ctypes.byref(n)))
+        out = np.zeros((n.value, 4), dtype=np.uint64)
+        _ck(load_host().cohost_plonk_trace_get(self.h, party, name.encode(), out.ctypes.data, n.value, ctypes.byref(n)))
+        return out
+
+    def close(self):
+        if self.h:
+            load_host().cohost_plonk_session_destroy(self.h)
             self.h = None

@@ -169,6 +169,62 @@ COCG_API int cocg_csr_share(cocg_ctx* ctx, cocg_ctx* owner, uint64_t owner_handl
  * rep3.rs:600-608 -- and z_wit).  out: DEVICE pointer, rows elements. */
 COCG_API int cocg_spmv(cocg_ctx* ctx, uint64_t csr, const void* z_pub, size_t npub, const void* z_wit, void* out);
 
+/* ---- CoPlonk vector primitives (csrc/poly.cu) -- DEVICE pointers, n Fr elements ---------------------------
+ * out[i] = src[idx[i]] (idx: DEVICE u32 array; an index >= src_n selects zero).  The wire buffers of round 1: witness values picked
+ * through the zkey's A / B / C maps (co-plonk/src/round1.rs:121-166, plonk_utils::get_witness lib.rs:113-137). */
+COCG_API int cocg_vec_gather(cocg_ctx* ctx, const void* src, size_t src_n, const uint32_t* idx, void* out, size_t n);
+/* Inclusive prefix scan, op = COCG_OP_MUL (array_prod_mul's `open[i] *= open[i-1]`, round2.rs:33-35) or COCG_OP_ADD (the closed form of
+ * div_by_zerofier, round5.rs:97-115).  out may alias x. */
+COCG_API int cocg_vec_scan(cocg_ctx* ctx, int op, const void* x, void* out, size_t n);
+/* out[i] = 1 / x[i] by Montgomery's trick (inv_many's `y.inverse()` loop, rep3.rs:544-558).  Zero inputs give zero outputs and are
+ * counted in *zeros (may be NULL: no synchronisation then) so the caller can raise "cannot compute inverse of zero".  out may alias x. */
+COCG_API int cocg_vec_inv(cocg_ctx* ctx, const void* x, void* out, size_t n, size_t* zeros);
+/* out (HOST, one Fr) = sum_i coeffs[i] * point^i: evaluate_poly_public (rep3.rs:923-928, round4.rs:136-142) per share component.
+ * point: HOST pointer to one Montgomery Fr.  Synchronises. */
+COCG_API int cocg_poly_eval(cocg_ctx* ctx, const void* coeffs, size_t n, const void* point, void* out);
+/* out[i] = sum_k factors[k] * vecs[k][i] over the vectors with lens[k] > i (nv <= 8; factors: HOST array of nv Montgomery Fr):
+ * the mul_with_public / add loops of compute_r and compute_wxi (round5.rs:140-330).  out must not alias an input. */
+COCG_API int cocg_vec_lincomb(cocg_ctx* ctx, int nv, const void* const* vecs, const size_t* lens, const void* factors, void* out, size_t n);
+
+/* out[i] = value (HOST pointer to one Fr): a shared scalar broadcast to a vector (`vec![r_inv[0].clone(); len]`, round2.rs:25). */
+COCG_API int cocg_vec_fill(cocg_ctx* ctx, void* out, size_t n, const void* value);
+
+/* ---- CoPlonk fused round kernels (csrc/plonk.cu) ----------------------------------------------------------------------------
+ * Round 2, compute_z (round2.rs:146-206): numerator / denominator factors for ONE share component.
+ * out = n1 n2 n3 d1 d2 d3; add_public = 1 for the component that receives public addends (add_with_public, rep3.rs:600-608). */
+typedef struct cocg_plonk_z_args {
+  const void *a, *b, *c;                 /* DEVICE: wire buffers, n elements */
+  const void *sigma1, *sigma2, *sigma3;  /* DEVICE: 4n evaluations each (element 4 i is read) */
+  const void *beta, *gamma, *k1, *k2;    /* HOST: one Montgomery Fr each */
+  const void* omega;                     /* HOST: generator of the n domain */
+  void* out[6];                          /* DEVICE */
+} cocg_plonk_z_args;
+COCG_API int cocg_plonk_z_factors(cocg_ctx* ctx, const cocg_plonk_z_args* args, size_t n, int add_public);
+/* Round 3, compute_t (round3.rs:237-471) in two levels (see csrc/plonk.cu for the algebra): level 1 writes the party's additive, masked
+ * shares of 10 product vectors (out: 10 x n4), level 2 those of t and tz (out: 2 x n4).  The caller re-shares after each level. */
+typedef struct cocg_plonk_quotient_args {
+  int components;                        /* 1 plain, 2 REP3 (a | b) */
+  int pub_comp;                          /* component that receives public addends: 0 plain / party 0, 1 party 1, -1 party 2 */
+  size_t n4;                             /* extended domain size 4n */
+  size_t n_public, n_lagrange;           /* public inputs; Lagrange polynomials resident (>= max(1, n_public)) */
+  const void *eval_a[2], *eval_b[2], *eval_c[2], *eval_z[2];   /* DEVICE: n4 evaluations per component */
+  const void* buffer_a[2];               /* DEVICE: wire buffer a (its first n_public elements feed PI) */
+  const void *sigma1, *sigma2, *sigma3, *qm, *ql, *qr, *qo, *qc;  /* DEVICE: n4 public evaluations each */
+  const void* lagrange;                  /* DEVICE: n_lagrange x n4 evaluations, contiguous */
+  const void* level1[2];                 /* DEVICE (level 2 only): the re-shared level-1 vectors, 10 x n4 per component */
+  const void *beta, *gamma, *alpha, *k1, *k2, *omega_n, *omega_4n;  /* HOST Fr */
+  const void* blinders;                  /* HOST: b0..b8 as 9 x 2 Fr (component a | b; b ignored when components = 1) */
+  const void* scalar_products;           /* HOST (level 2): shares of b1b3 b0b3 b1b2 b0b2 b5b8 b5b7 b5b6 b4b8 b4b7 b4b6, 10 x 2 Fr */
+  const void *seed_own, *seed_prev;      /* HOST: 32-byte PRF seeds (REP3 zero-masks; csrc/prf.cuh) */
+  uint32_t ctr;                          /* first PRF vector counter; level 1 consumes 10, level 2 consumes 2 */
+  void* out;                             /* DEVICE */
+} cocg_plonk_quotient_args;
+COCG_API int cocg_plonk_quotient_l1(cocg_ctx* ctx, const cocg_plonk_quotient_args* args);
+COCG_API int cocg_plonk_quotient_l2(cocg_ctx* ctx, const cocg_plonk_quotient_args* args);
+/* Coefficients of T from ifft(t), ifft(tz) (n4 = 4n each): negate / divide by Z_H / add / split into t1 (n + 1) | t2 (n + 1) | t3 (n + 6)
+ * (round3.rs:433-468); elements t1[n], t2[n] are left for the caller's b9 / b10 patches. */
+COCG_API int cocg_plonk_t_finish(cocg_ctx* ctx, const void* ct, const void* ctz, size_t n, void* t1, void* t2, void* t3);
+
 /* ---- K7: O(1) group operations on HOST Jacobian points (proof assembly, groth16.rs:257-312) -----------
  * op: 0 add(a,b)  1 scalar-mul(a, b = canonical 32-byte scalar)  2 to_affine(a) -> packed affine
  *     3 from_affine(a)  4 neg(a)  5 double(a)  6 generator() (a, b ignored).  Replaces EcMpcProtocol::{add_points, scalar_mul_public_point,

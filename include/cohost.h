@@ -119,16 +119,49 @@ COHOST_API int cohost_rep3_phase_times(cohost_rep3_session* s, double* out);
 COHOST_API int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out);
 COHOST_API void cohost_shamir_session_destroy(cohost_shamir_session* s);
 COHOST_API int cohost_shamir_prove(cohost_shamir_session* s, const void* public_inputs, const void* const* wit, void* proofs_out, void* rs_out);
-/* Plonk, round 1 of CoPlonk::prove (co-plonk/src/round1.rs): the zkey reader for what the round consumes (header, additions, wire
- * maps, p_tau: circom-types/src/plonk/zkey.rs:160-330) and the wire commitments [a]_1 | [b]_1 | [c]_1 (packed affine) with the plain
- * driver or three REP3 parties.  deterministic != 0: the reference's KAT blinders b_i = i (round1.rs:101-108).
- * info[6] = curve, n_vars, n_public, domain_size, n_additions, n_constraints. */
+/* CoPlonk::prove (co-plonk/src/lib.rs:80-99, round1.rs .. round5.rs) on the GPU.
+ *  - cohost_plonk_zkey_load_file: the Plonk zkey reader (circom-types/src/plonk/zkey.rs:160-420): header incl. the verifying-key tail,
+ *    additions, wire maps, selector / sigma / Lagrange polynomials and p_tau, all resident in HBM afterwards.
+ *    info[6] = curve, n_vars, n_public, domain_size, n_additions, n_constraints.
+ *  - cohost_plonk_zkey_create_synthetic: a shape-faithful key for the 2^18-gate benchmark (BASELINE configs[3]): caller's wire maps,
+ *    PRF-filled polynomials, generated curve points; seed = 32 bytes.  Its proofs exercise every kernel but are not expected to verify.
+ *  - sessions: protocol 0 = CoPlonk<PlainDriver> (seeds: 32 bytes), 1 = three CoPlonk<Rep3Protocol> provers on three threads over the
+ *    in-process network (seeds: 3 x 32 bytes).
+ *  - cohost_plonk_prove: public_inputs = n_public + 1 Fr (the leading entry is ignored, PlonkWitness::new types.rs:105-108);
+ *    wit_a / wit_b: one pointer per party to its share components of the private witness (n_vars - n_additions - n_public - 1 Fr; wit_b
+ *    NULL for the plain driver), HOST memory or, with wit_on_device, HBM; deterministic != 0: the reference's KAT blinders b_i = i
+ *    (round1.rs:101-108).  proofs_out: per party cohost_plonk_proof_limbs() u64 = A B C Z T1 T2 T3 Wxi Wxiw (packed affine
+ *    Montgomery) | eval_a eval_b eval_c eval_s1 eval_s2 eval_zw (Montgomery Fr) -- the field order of PlonkProof (plonk/proof.rs).
+ *  - cohost_plonk_round1_*: round 1 alone, commitments [a]_1 | [b]_1 | [c]_1 (per party for REP3). */
+typedef struct cohost_plonk_session cohost_plonk_session;
 COHOST_API int cohost_plonk_zkey_load_file(const char* path, int device, cohost_plonk_zkey** out);
+COHOST_API int cohost_plonk_zkey_create_synthetic(int curve, int device, size_t log_n, size_t n_public, size_t n_vars, size_t n_constraints,
+                                                  const uint32_t* map_a, const uint32_t* map_b, const uint32_t* map_c, const uint8_t* seed,
+                                                  cohost_plonk_zkey** out);
 COHOST_API void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z);
 COHOST_API int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info);
+COHOST_API size_t cohost_plonk_proof_limbs(cohost_plonk_zkey* z);
+COHOST_API int cohost_plonk_session_create(cohost_plonk_zkey* z, int protocol, const uint8_t* seeds, cohost_plonk_session** out);
+COHOST_API void cohost_plonk_session_destroy(cohost_plonk_session* s);
+COHOST_API int cohost_plonk_prove(cohost_plonk_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                  int deterministic, int wit_on_device, void* proofs_out);
+COHOST_API int cohost_plonk_set_mpc_exchange(cohost_plonk_session* s, int device);
+COHOST_API uint64_t cohost_plonk_launch_count(cohost_plonk_session* s);
+COHOST_API int cohost_plonk_profile_enable(cohost_plonk_session* s, int on);
+COHOST_API int cohost_plonk_profile_reset(cohost_plonk_session* s);
+COHOST_API int cohost_plonk_profile_read(cohost_plonk_session* s, int cls, double* total_ms, uint64_t* scopes);
+/* Host wall-clock per round of the last proof, seconds: out[party * 5 + round]. */
+COHOST_API int cohost_plonk_round_times(cohost_plonk_session* s, double* out);
+/* Test hook: record component a of named intermediate vectors of the following proofs (buffer_a, poly_a, eval_a, buffer_z, poly_z,
+ * t_evals, tz_evals, t1, t2, t3, poly_r, wxi); summed over the three parties they are the plain values.  get with out == NULL
+ * returns the element count in *n. */
+COHOST_API int cohost_plonk_trace_enable(cohost_plonk_session* s, int on);
+COHOST_API int cohost_plonk_trace_get(cohost_plonk_session* s, int party, const char* name, void* out, size_t cap, size_t* n);
 COHOST_API int cohost_plonk_round1_plain(cohost_plonk_zkey* z, const void* public_inputs, const void* witness, int deterministic, void* commits_out);
 COHOST_API int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
                                         const uint8_t* seeds, int deterministic, void* commits_out);
+/* serde_json of PlonkProof (circom-types/src/plonk/proof.rs:7-87) from the block cohost_plonk_prove writes; same writer protocol as below. */
+COHOST_API int cohost_plonk_proof_to_json(int curve, const void* proof, char* out, size_t cap, size_t* len);
 /* Output-side formats of the path, byte-compatible with what `co-circom generate-proof` / `split-witness` write.
  * Writers fill `out` (capacity `cap`) and set *len; out == NULL only queries the length.  Strings carry no terminating NUL.
  *  - cohost_proof_to_json: serde_json of Groth16Proof (circom-types/src/groth16/proof.rs:7-29, traits.rs:186-233); `proof` is the

@@ -98,7 +98,7 @@ def round2_challenges(zk: PlonkZKey, values, commits):
     return beta, t.get_challenge()
 
 
-def z_polynomial(zk: PlonkZKey, values, beta, gamma, blinders=tuple(range(11))):
+def z_polynomial(zk: PlonkZKey, values, beta, gamma, blinders=tuple(range(11)), trace=None):
     """compute_z (round2.rs:146-236) with the plain driver: grand product of the permutation argument over the domain, rotated by
     one, iFFT, blinded with b[6..9]: n + 3 coefficients."""
     c = zk.curve
@@ -121,6 +121,8 @@ def z_polynomial(zk: PlonkZKey, values, beta, gamma, blinders=tuple(range(11))):
         den[i] = den[i] * den[i - 1] % r
     buf = [x * pow(d, -1, r) % r for x, d in zip(num, den)]
     buf = buf[-1:] + buf[:-1]                              # rotate_right(1)
+    if trace is not None:
+        trace["buffer_z"] = list(buf)
     poly = intt(buf, omega, r)
     b6, b7, b8 = blinders[6:9]                             # blind_coefficients(poly, b[6..9]): coefficients given in reverse
     poly[0] = (poly[0] - b8) % r
@@ -146,7 +148,7 @@ def _extended_evals(zk, coeffs):
     return ntt(list(coeffs) + [0] * (4 * zk.domain_size - len(coeffs)), roots[zk.pow + 2], c.r)
 
 
-def quotient_polynomials(zk: PlonkZKey, values, beta, gamma, alpha, blinders=tuple(range(11))):
+def quotient_polynomials(zk: PlonkZKey, values, beta, gamma, alpha, blinders=tuple(range(11)), trace=None):
     """compute_t (round3.rs:237-470) with the plain driver: T(X) on the 4n coset structure snarkjs uses -- every wire / z evaluation
     carries its blinding part separately (the *p vectors, multiplied by Z_H, Z_H^2, Z_H^3 through z1, z2, z3), the unblinded part is
     divided by Z_H in coefficient form.  Returns the coefficient lists of t1, t2, t3 (n + 1, n + 1, n + 6)."""
@@ -211,6 +213,8 @@ def quotient_polynomials(zk: PlonkZKey, values, beta, gamma, alpha, blinders=tup
         t_vec.append((e1 + e2 - e3 + e4) % r)
         tz_vec.append((e1z + e2zv - e3zv + e4z) % r)
         w = w * w_4n % r
+    if trace is not None:
+        trace["t_evals"], trace["tz_evals"] = list(t_vec), list(tz_vec)
     ct = intt(t_vec, w_4n, r)
     for i in range(n):                                   # neg_vec_in_place_limit
         ct[i] = (-ct[i]) % r
@@ -257,7 +261,7 @@ def _div_by_linear(poly, beta, r):
     return res[:-1]
 
 
-def prove_plain(zk: PlonkZKey, values, blinders=tuple(range(11))):
+def prove_plain(zk: PlonkZKey, values, blinders=tuple(range(11)), trace=None):
     """CoPlonk::prove with the plain driver and fixed blinders (co-plonk/src/lib.rs:80-99, round1.rs .. round5.rs): the snarkjs proof
     object -- commitments affine, evaluations ints."""
     c = zk.curve
@@ -268,13 +272,15 @@ def prove_plain(zk: PlonkZKey, values, blinders=tuple(range(11))):
     commit = lambda p: c.to_affine(c.msm(zk.p_tau[:len(p)], p, 1), 1)
     A, B, C = commit(pa), commit(pb), commit(pc)
     beta, gamma = round2_challenges(zk, values, [A, B, C])
-    pz = z_polynomial(zk, values, beta, gamma, blinders)
+    pz = z_polynomial(zk, values, beta, gamma, blinders, trace=trace)
     Z = commit(pz)
     t = Keccak256Transcript(c)
     t.add_scalar(beta); t.add_scalar(gamma); t.add_point(Z)
     alpha = t.get_challenge()
-    t1, t2, t3 = quotient_polynomials(zk, values, beta, gamma, alpha, blinders)
+    t1, t2, t3 = quotient_polynomials(zk, values, beta, gamma, alpha, blinders, trace=trace)
     T1, T2, T3 = commit(t1), commit(t2), commit(t3)
+    if trace is not None:
+        trace.update(poly_a=list(pa), poly_z=list(pz), t1=list(t1), t2=list(t2), t3=list(t3), buffer_a=wire_buffers(zk, values)[0])
     # round 4 (round4.rs:114-165)
     t = Keccak256Transcript(c)
     t.add_scalar(alpha); t.add_point(T1); t.add_point(T2); t.add_point(T3)
@@ -327,6 +333,8 @@ def prove_plain(zk: PlonkZKey, values, blinders=tuple(range(11))):
             res[i] = (res[i] + f * x) % r
     res[0] = (res[0] - v[0] * ev["eval_a"] - v[1] * ev["eval_b"] - v[2] * ev["eval_c"] - v[3] * ev["eval_s1"] - v[4] * ev["eval_s2"]) % r
     wxi = _div_by_linear(res, xi, r)
+    if trace is not None:
+        trace.update(poly_r=list(pr), wxi=list(wxi))
     zq = list(pz)
     zq[0] = (zq[0] - ev["eval_zw"]) % r
     wxiw = _div_by_linear(zq, xiw, r)

@@ -156,9 +156,23 @@ def plonk_round2():
     return out
 
 
+def plonk_poseidon_full():
+    """The full BN254 poseidon Plonk zkey (n = 4096, 2228 additions, 6.3 MB; xz-compressed here) + witness: the mid-size VALID circuit
+    the GPU tests of rounds 2-5 prove and verify (co-plonk/src/lib.rs:232-275 test_poseidon_bn254)."""
+    import lzma
+    src = os.path.join(REF, "test_vectors", "Plonk", "bn254", "poseidon")
+    dst = os.path.join(OUT, "plonk", "bn254", "poseidon")
+    os.makedirs(dst, exist_ok=True)
+    with open(os.path.join(src, "circuit.zkey"), "rb") as f, lzma.open(os.path.join(dst, "circuit.zkey.xz"), "wb", preset=9) as g:
+        g.write(f.read())
+    shutil.copyfile(os.path.join(src, "witness.wtns"), os.path.join(dst, "witness.wtns"))
+    os.chmod(os.path.join(dst, "witness.wtns"), 0o644)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     copy_fixtures()
+    plonk_poseidon_full()
     with open(os.path.join(OUT, "plonk_round1_kats.json"), "w") as f:
         json.dump(plonk_round1(), f, indent=1)
     with open(os.path.join(OUT, "plonk_round2_kats.json"), "w") as f:
