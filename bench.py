@@ -578,6 +578,217 @@ def run_own_msm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE configs[3]: Plonk
+def plonk_config(args, world):
+    n = 1 << args.log_n
+    return {"workload": f"Plonk prove, synthetic 2^{args.log_n}-gate circuit, BN254, REP3 3-party in-process (BASELINE configs[3])",
+            "curve": "bn254", "protocol": "rep3", "domain_size": n, "extended_domain": 4 * n, "n_public": 1,
+            "per_party": "2 components x (4 iNTT(n) + 4 NTT(4n) + 2 iNTT(4n) + 9 G1 MSMs of ~n over p_tau), 2 fused quotient kernels on 4n, "
+                         "prefix-product / inverse / Horner scans on n",
+            "mpc_exchanges_per_party": "12 vectors of 4n (round 3, two rounds) + ~16 vectors of n (round 2)",
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one proof per GPU per step, no collective)",
+            "l2_policy": "inputs_exceed_l2 (>= 1.5 GB of evaluation vectors and tables streamed per proof vs 126 MB L2)"}
+
+
+def plonk_synthetic_maps(log_n, rng):
+    n = 1 << log_n
+    n_public, n_vars, n_constraints = 1, n - 6, n - 4
+    base = np.arange(n_constraints, dtype=np.int64)
+    maps = [((base + rng.integers(-64, 64, size=n_constraints)) % n_vars).astype(np.uint32) for _ in range(3)]
+    return n_public, n_vars, n_constraints, maps
+
+
+class CpuPlonkSlice:
+    """The reference's CPU work for ONE (party, share component) slice of a REP3 Plonk proof on the C oracle (OpenMP, all host threads):
+    4 iNTT(n) + 4 NTT(4n) + 2 iNTT(4n), 9 MSMs over p_tau, and the element-wise work of compute_z / compute_t as the reference does it:
+    half of its 52 + 8 mul_vec local steps (3 products + mask each: 26 on 4n, 4 on n) and ~20 mul_with_public passes over 4n
+    (round3.rs:268-431).  A proof is six such slices; proofs/s = 1 / (6 x slice time)."""
+
+    SLICES_PER_PROOF = 6
+
+    def __init__(self, log_n):
+        from oracle import cref, ntt as ontt
+        from oracle.curves import BN254 as C
+        self.cref, self.C, self.log_n = cref, C, log_n
+        L = cref.lib()
+        L.orc_set_threads(host_threads())
+        self.cores = L.orc_num_threads()
+        rng = np.random.default_rng(SEED)
+        n = 1 << log_n
+        self.n = n
+        p0 = cref.g_to_mont(C, [C.mul(C.gen(1), 1001, 1)], 1)[0]
+        q = cref.g_to_mont(C, [C.mul(C.gen(1), 78, 1)], 1)[0]
+        self.p_tau = cref.gen_chain(C, 1, p0, q, n + 6)
+        self.v = [rand_fr(n, rng) for _ in range(4)]
+        self.e = [rand_fr(4 * n, rng) for _ in range(4)]
+        _, roots = ontt.roots_of_unity(C)
+        f = lambda x: cref.fr_to_mont(C, [x])
+        self.w_n, self.w_ni = f(roots[log_n]), f(pow(roots[log_n], -1, C.r))
+        self.w_4n, self.w_4ni = f(roots[log_n + 2]), f(pow(roots[log_n + 2], -1, C.r))
+
+    def step(self):
+        cref, C, n = self.cref, self.C, self.n
+        t0 = time.perf_counter()
+        for k in range(4):                       # a, b, c, z: coefficients and extended evaluations
+            cref.ntt(C, self.v[k], self.w_ni, inverse=True)
+            cref.ntt(C, self.e[k], self.w_4n)
+        for _ in range(4):                       # round 2 products on n
+            cref.rep3_mul_local(C, self.v[0], self.v[1], self.v[2], self.v[3], None)
+        for _ in range(26):                      # half of the 52 mul_vec local steps of compute_t
+            cref.rep3_mul_local(C, self.e[0], self.e[1], self.e[2], self.e[3], None)
+        for k in range(20):                      # mul_with_public / add_mul_public passes over the 4n domain
+            cref.fr_vec_op(C, cref.OP_MUL, self.e[k % 4], self.e[(k + 1) % 4])
+        for k in range(2):                       # t, tz -> coefficients
+            cref.ntt(C, self.e[k], self.w_4ni, inverse=True)
+        for k in range(9):                       # a b c z t1 t2 t3 Wxi Wxiw
+            cref.msm(C, 1, self.p_tau, self.v[k % 4])
+        return time.perf_counter() - t0
+
+    def sample_text(self, steps):
+        return (f"each step = 1 of the 6 (party, share component) slices of one 2^{self.log_n}-gate REP3 Plonk proof: 4 iNTT(n) + 4 NTT(4n) + 2 iNTT(4n), "
+                f"9 G1 MSMs of 2^{self.log_n}, 30 mul_vec local steps and 20 public-multiplication passes (the reference's compute_z / compute_t op "
+                f"count, round3.rs:268-431); C oracle (port; the Rust reference cannot be built here), OpenMP on {self.cores} host threads; "
+                f"proofs/s = 1 / (6 x mean step time) over {steps} timed steps")
+
+
+def run_reference_plonk(args):
+    sl = CpuPlonkSlice(args.log_n)
+    for _ in range(args.warmup):
+        sl.step()
+    t = float(np.mean([sl.step() for _ in range(args.steps)]))
+    value = 1.0 / (sl.SLICES_PER_PROOF * t)
+    print(json.dumps({
+        "impl": "reference", "metric": "plonk_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 limbs (256-bit Montgomery)", "data": "synthetic", "config": plonk_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": sl.cores, "kind": "port", "sample": sl.sample_text(args.steps)},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_own_plonk(args):
+    import hashlib
+
+    import torch
+    import torch.distributed as dist
+
+    import cocg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    log_n = args.log_n
+    n = 1 << log_n
+    rng = np.random.default_rng(SEED)
+    n_public, n_vars, n_constraints, maps = plonk_synthetic_maps(log_n, rng)
+    zk = cocg.PlonkZKey.synthetic(cocg.BN254, log_n, n_public, n_vars, maps, SEED.to_bytes(8, "little") * 4, device=local)
+    sess = cocg.PlonkSession(zk, "rep3", seeds=PRF_SEEDS)
+    n_wit = zk.n_witness
+    xs = []
+    for i in range(3):
+        t = torch.empty(n_wit * 4, dtype=torch.int64).pin_memory()
+        t.numpy().view(np.uint64).reshape(n_wit, 4)[:] = rand_fr(n_wit, rng)
+        xs.append(t)
+    host_a = [xs[i].data_ptr() for i in range(3)]
+    host_b = [xs[(i - 1) % 3].data_ptr() for i in range(3)]
+    ctx = cocg.Context(cocg.BN254, local)
+    dev = [ctx.upload(xs[i].numpy().view(np.uint64).reshape(n_wit, 4)) for i in range(3)]
+    dev_a = [dev[i].ptr for i in range(3)]
+    dev_b = [dev[(i - 1) % 3].ptr for i in range(3)]
+    r1 = pow(2, 256, BN254_R)
+    pub = np.stack([limbs_of(r1), limbs_of(12345 * r1 % BN254_R)])
+
+    def timed(fn, steps, sample_clocks=False):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks, out
+
+    resident = lambda: sess.prove(pub, dev_a, dev_b, device_ptrs=True)
+    e2e_fn = lambda: sess.prove(pub, host_a, host_b)
+    sess.set_mpc_exchange("device")
+    for _ in range(args.warmup):
+        resident()
+    sess.profile(True)
+    sess.profile_reset()
+    l0 = sess.launch_count()
+    ms, clocks, proofs = timed(resident, args.steps, sample_clocks=True)
+    launches = sess.launch_count() - l0
+    prof = sess.profile_read()
+    sess.profile(False)
+    assert np.array_equal(proofs[0], proofs[1]) and np.array_equal(proofs[1], proofs[2]), "the three parties disagree on the proof"
+    rounds = sess.round_times().max(axis=0) * 1e3
+    sess.set_mpc_exchange("host")
+    for _ in range(min(args.warmup, 2)):
+        e2e_fn()
+    ms_e2e, _, _ = timed(e2e_fn, args.steps)
+    rounds_e2e = sess.round_times().max(axis=0) * 1e3
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # algorithmic bytes per proof (SURVEY 8(d)): MSM N x (64 + 32); NTT 64 B per element per transform
+        msm_terms = 3 * 2 * (3 * (n + 2) + (n + 3) + 2 * (n + 1) + (n + 6) + (n + 5) + (n + 2))
+        ntt_elems = 3 * 2 * (4 * n + 4 * 4 * n + 2 * 4 * n)
+        alg = {"msm_sort": msm_terms * 96, "msm_accumulate": msm_terms * 96, "msm_reduce": msm_terms * 96, "ntt": ntt_elems * 64}
+        kernels = {}
+        total_ms = sum(v[0] for v in prof.values()) or 1.0
+        for name, (tms, cnt) in prof.items():
+            per = tms / args.steps
+            kernels[name] = {"ms_per_proof_summed_over_parties": round(per, 3), "scopes": cnt, "share_of_timed_scopes": round(tms / total_ms, 3),
+                             "algorithmic_GBps": round(alg[name] / (per * 1e-3) / 1e9, 1) if per and name in alg else None}
+        dom = max(("ntt", "msm_accumulate"), key=lambda k: prof[k][0])
+        dom_ms = prof[dom][0] / args.steps
+        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+        value = world * args.steps / (ms / 1e3)
+        exch = 3 * (12 * 4 * n + 16 * n) * 32
+        o = {
+            "metric": "plonk_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (256-bit Montgomery integers; no floating point)", "data": "synthetic", "config": plonk_config(args, world),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "proof_sha256": hashlib.sha256(np.ascontiguousarray(proofs[0]).tobytes()).hexdigest(),
+            "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 3 * 2 * n_wit * 32 + 64, "d2h_bytes_per_step": int(3 * zk.proof_limbs * 8),
+                    "mpc_exchange_bytes_per_step": int(2 * exch),
+                    "note": "witness shares uploaded from pinned host memory every step, proofs read back, every MPC payload staged through pinned "
+                            "host memory (D2H + H2D); the `value` leg keeps witness and payloads in HBM"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": f"{dom} class (largest share of device time), CUDA events on the launching streams, three parties running concurrently",
+                         "peak_source": peak_src},
+            "kernels": kernels,
+            "host_round_ms": {"value_leg": [round(float(x), 2) for x in rounds], "e2e_leg": [round(float(x), 2) for x in rounds_e2e]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sl = CpuPlonkSlice(log_n)
+            k_cpu = 2
+            t = float(np.mean([sl.step() for _ in range(k_cpu)]))
+            o["cpu_baseline"] = {"value": 1.0 / (sl.SLICES_PER_PROOF * t), "unit": "proofs/s", "cores": sl.cores, "kind": "port", "sample": sl.sample_text(k_cpu)}
+        print(json.dumps(o))
+    sess.close()
+    zk.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_own_shamir(args, cocg, torch, curve_id, modulus, local, r1cs, seed_bytes, rng):
     """Non-default configuration: CoGroth16<ShamirProtocol>, 3 parties, threshold 1, one GPU (BASELINE configs[4] flavour).  The
     double-random preprocessing of the two mul_vec rounds (shamir.rs:923-1010) is inside the timed region, as in the reference."""
@@ -624,7 +835,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--log-n", type=int, default=None, help="default: 20 (groth16, msm), 18 (plonk)")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="groth16", choices=["groth16", "msm", "plonk"],
                     help="groth16 = BASELINE configs[2] (the headline); msm = configs[1] (BN254 G1 MSM 2^20); plonk = configs[3] (Plonk 2^18 gates, REP3)")
@@ -632,6 +843,8 @@ def main():
     ap.add_argument("--protocol", default="rep3", choices=["rep3", "shamir"], help="non-default: Shamir (3,1), single GPU only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.log_n is None:
+        args.log_n = 18 if args.workload == "plonk" else 20
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "msm":
