@@ -360,9 +360,7 @@ def run_own(args):
         pa = ctx.profile_read()
         ctx.profile(False)
         ctx.bases_free(h_alone)
-        lg = (per_alone + per_alone // 2).bit_length() - 1
-        c_bits = min(max(lg, 4), 20)
-        nwin = (bits + c_bits) // c_bits
+        c_bits, nwin = cocg.msm_plan(curve_id, per_alone)
         alone = {"ms": pa["msm_accumulate"][0] / max(pa["msm_accumulate"][1], 1), "terms": per_alone, "window_bits": c_bits, "windows": nwin}
 
     value = args.steps / (ms / 1e3)
@@ -536,8 +534,7 @@ def run_own_msm(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         acc_ms = prof["msm_accumulate"][0] / max(prof["msm_accumulate"][1], 1)
-        bits, c_bits = 254, min(max((n + n // 2).bit_length() - 1, 4), 20)
-        nwin = (bits + c_bits) // c_bits
+        c_bits, nwin = cocg.msm_plan(cocg.BN254, n)
         ceiling = ctx.fp_mul_ceiling(base_field=True)
         fq_mul = n * nwin * 10 / (acc_ms * 1e-3) / 1e9
         value = world * args.steps / (ms / 1e3)

@@ -26,10 +26,17 @@ SYMBOLS = [
     "cocg_bases_share", "cocg_csr_share", "cocg_bases_generate", "cocg_bases_download", "cocg_profile_enable",
     "cocg_profile_read", "cocg_profile_reset", "cocg_msm_multi", "cocg_vec_axpy", "cocg_csr_upload_form", "cocg_csr_download", "cocg_bases_generate_range",
     "cocg_fp_mul_ceiling", "cocg_vec_gather", "cocg_vec_scan", "cocg_vec_inv", "cocg_poly_eval", "cocg_vec_lincomb", "cocg_vec_fill",
-    "cocg_plonk_z_factors", "cocg_plonk_quotient_l1", "cocg_plonk_quotient_l2", "cocg_plonk_t_finish",
+    "cocg_msm_plan", "cocg_plonk_z_factors", "cocg_plonk_quotient_l1", "cocg_plonk_quotient_l2", "cocg_plonk_t_finish",
 ]
 
 _lib = None
+
+
+def msm_plan(curve: int, n: int):
+    """(window bits, windows per scalar) of the table built for an n-point query."""
+    c, w = ctypes.c_int(), ctypes.c_int()
+    load().cocg_msm_plan(curve, n, ctypes.byref(c), ctypes.byref(w))
+    return c.value, w.value
 
 
 class CocgError(RuntimeError):
@@ -86,6 +93,7 @@ def load():
         "cocg_profile_read": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),
         "cocg_profile_reset": (ci, [vp]),
         "cocg_fp_mul_ceiling": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double)]),
+        "cocg_msm_plan": (ci, [ci, sz, ctypes.POINTER(ci), ctypes.POINTER(ci)]),
         "cocg_vec_gather": (ci, [vp, vp, sz, vp, vp, sz]),
         "cocg_vec_scan": (ci, [vp, ci, vp, vp, sz]),
         "cocg_vec_inv": (ci, [vp, vp, vp, sz, ctypes.POINTER(sz)]),

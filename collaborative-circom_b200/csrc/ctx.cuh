@@ -148,14 +148,17 @@ inline int pinned_get(cocg_ctx* ctx, size_t bytes, void** out) {
 
 // Window width c of the MSM table built for a query of n points (msm_impl.cuh): about log2(n), capped at 20 bits
 // (13 windows for 254/255-bit scalars, 2^19 buckets of ~26 points at n = 2^20).  Measured alternatives at n = 2^20 (G1, ms):
-// c = 17 with 4 lanes per bucket 3.70, c = 19 3.92, c = 20 3.36.
-inline int msm_plan_window_bits(size_t n) {
+// c = 17 with 4 lanes per bucket 3.70, c = 19 3.92, c = 20 3.36.  If one bit less needs no extra window it is preferred: half the
+// buckets to reduce for the same number of additions, and a top window that is not degenerate (254 bits: c = 18 -> 15 windows with a
+// 2-bit top window whose 3 buckets collect n / 4 entries each; c = 17 -> 15 windows with a 16-bit top window).
+inline int msm_plan_window_bits(size_t n, int scalar_bits) {
   int lg = 0;
   size_t v = n + n / 2;  // round to the nearest power of two
   while (((size_t)1 << (lg + 1)) <= v) lg++;
   int c = lg;
   if (c < 4) c = 4;
   if (c > 20) c = 20;
+  while (c > 4 && (scalar_bits + c - 1) / (c - 1) == (scalar_bits + c) / c) c--;
   return c;
 }
 

@@ -8,8 +8,8 @@
 namespace cocg {
 // window bits / count for a query of n points: must match msm_impl.cuh (the table is allocated before it is built)
 int msm_table_windows(int curve, size_t n) {
-  int c = msm_plan_window_bits(n);
   int bits = curve == COCG_BN254 ? 254 : 255;
+  int c = msm_plan_window_bits(n, bits);
   return (bits + c) / c;
 }
 int msm_precompute(cocg_ctx* ctx, BasesEntry& be) {
@@ -59,6 +59,15 @@ extern "C" int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size
     if (!ctx->bases[i].d) { ctx->bases[i] = be; *handle = i + 1; return 0; }
   ctx->bases.push_back(be);
   *handle = ctx->bases.size();
+  return 0;
+}
+
+extern "C" int cocg_msm_plan(int curve, size_t n, int* window_bits, int* windows) {
+  if (curve != COCG_BN254 && curve != COCG_BLS12_381) return 1;
+  const int bits = curve == COCG_BN254 ? 254 : 255;
+  const int c = msm_plan_window_bits(n, bits);
+  if (window_bits) *window_bits = c;
+  if (windows) *windows = (bits + c) / c;
   return 0;
 }
 

@@ -30,10 +30,13 @@
 
 namespace cocg {
 
-constexpr int kHeavy = 1024;         // runs longer than this are cut into kHeavy-entry chunks, one warp each
+constexpr int kHeavy = 1024;         // runs longer than this leave the thread-per-bucket path ...
+constexpr int kHeavyChunk = 256;     // ... and are cut into chunks of this many entries, one warp each.  A top window only a few bits wide
+                                     // (c = 18: bits 252..253) puts n / 4 entries into each of 3 buckets; with 1024-entry chunks those were
+                                     // 256 warps of 37 dependent additions = 207 us per 2^18-term MSM (ncu, round 2), a third of the
+                                     // accumulate time.  256-entry chunks give 4x the warps and a quarter of the chain.
 constexpr int kIdxBits = 25;         // entry = sign << 31 | window << 25 | point index
 
-static int msm_window_bits(size_t n) { return msm_plan_window_bits(n); }  // ctx.cuh: shared with the table allocation
 template <class FrP>
 static int msm_num_windows(int c) {
   return (FrP::BITS + c) / c;  // ceil((BITS+1)/c): room for the final carry of the signed recoding
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kAccumulateThreads, kAccumulateMinBlocks<F>) m
   const uint32_t gb = order[t];
   const uint32_t beg = start[gb], end = start[gb + 1];
   if (end - beg > (uint32_t)kHeavy) {
-    uint32_t nch = (end - beg + kHeavy - 1) / kHeavy;
+    uint32_t nch = (end - beg + kHeavyChunk - 1) / kHeavyChunk;
     uint32_t h = atomicAdd(&heavy_count[0], 1u);
     uint32_t first = atomicAdd(&heavy_count[1], nch);
     heavy_list[h] = HeavyRec{gb, first, nch};
@@ -322,8 +325,8 @@ __global__ void __launch_bounds__(128) msm_heavy_chunks_kernel(const void* __res
   const uint32_t nchunks = heavy_count[1];
   for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < nchunks; ch += nwarps) {
     const HeavyRec rec = heavy_list[chunk_owner[ch]];
-    uint32_t beg = start[rec.bucket] + (ch - rec.first_chunk) * kHeavy;
-    uint32_t end = min(beg + (uint32_t)kHeavy, start[rec.bucket + 1]);
+    uint32_t beg = start[rec.bucket] + (ch - rec.first_chunk) * kHeavyChunk;
+    uint32_t end = min(beg + (uint32_t)kHeavyChunk, start[rec.bucket + 1]);
     XYZZ<F> acc = xyzz_inf<F>();
     accumulate_run<F>(acc, table, tstride, sorted, beg + lane, end, 32);
     for (int delta = 16; delta >= 1; delta >>= 1) {
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(32) msm_final_kernel(const XYZZ<F>* __restrict
 // ------------------------------------------------------------------ drivers
 template <class F, class FrP>
 int msm_precompute_impl(cocg_ctx* ctx, BasesEntry& be) {
-  be.c = msm_window_bits(be.n);
+  be.c = msm_plan_window_bits(be.n, FrP::BITS);
   be.nwin = msm_num_windows<FrP>(be.c);
   if (be.n == 0) return 0;
   msm_precompute_kernel<F><<<(unsigned)((be.n + 127) / 128), 128, 0, ctx->stream>>>(reinterpret_cast<Affine<F>*>(be.d), be.n, be.c, be.nwin);
@@ -456,7 +459,7 @@ struct MsmSorted {
   uint32_t nb = 0;
   uint32_t *sorted = nullptr, *start = nullptr, *order = nullptr, *heavy = nullptr, *chunk_owner = nullptr;
   HeavyRec* heavy_list = nullptr;
-  size_t max_heavy = 0;
+  size_t max_heavy = 0, max_chunks = 0;
 };
 
 template <class FrP>
@@ -466,7 +469,8 @@ int msm_sort_impl(cocg_ctx* ctx, const void* scalars, size_t n, int c, int mont,
   const size_t scan_blocks = ((size_t)nb + kScanBlock - 1) / kScanBlock;
   uint32_t *dig, *counts, *bsums, *shist;
   S.n = n; S.c = c; S.nwin = nwin; S.nb = nb;
-  S.max_heavy = (size_t)nwin * n / kHeavy + 1;  // buckets with more than kHeavy entries; chunks <= 2 x that
+  S.max_heavy = (size_t)nwin * n / kHeavy + 1;  // buckets with more than kHeavy entries
+  S.max_chunks = (size_t)nwin * n / kHeavyChunk + S.max_heavy + 1;  // sum over heavy buckets of ceil(len / kHeavyChunk)
   void* p;
   COCG_TRY(scratch_get(ctx, 1, (size_t)nwin * n * 4, &p)); dig = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 2, (size_t)nwin * n * 4, &p)); S.sorted = (uint32_t*)p;
@@ -475,7 +479,7 @@ int msm_sort_impl(cocg_ctx* ctx, const void* scalars, size_t n, int c, int mont,
   COCG_TRY(scratch_get(ctx, 5, (scan_blocks + 2) * 4, &p)); bsums = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 6, 16 + S.max_heavy * sizeof(HeavyRec), &p)); S.heavy = (uint32_t*)p;  // [0], [1] = counters, records from +16 B
   S.heavy_list = reinterpret_cast<HeavyRec*>(S.heavy + 4);
-  COCG_TRY(scratch_get(ctx, 13, 2 * S.max_heavy * 4, &p)); S.chunk_owner = (uint32_t*)p;
+  COCG_TRY(scratch_get(ctx, 13, S.max_chunks * 4, &p)); S.chunk_owner = (uint32_t*)p;
   COCG_TRY(scratch_get(ctx, 10, ((size_t)nb + kSizeBins) * 4, &p)); S.order = (uint32_t*)p; shist = S.order + nb;
   cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, COCG_PROF_MSM_SORT);
@@ -512,7 +516,7 @@ int msm_buckets_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmS
   void* p;
   // bucket sets of one group live side by side (slot sized by cocg_msm_multi before the first set is written)
   COCG_TRY(scratch_get(ctx, msm_bucket_slot(be.group), (size_t)(set + 1) * nb * sizeof(X), &p)); buckets = (X*)p + (size_t)set * nb;
-  COCG_TRY(scratch_get(ctx, 12, 2 * S.max_heavy * sizeof(X), &p)); hpartial = (X*)p;
+  COCG_TRY(scratch_get(ctx, 12, S.max_chunks * sizeof(X), &p)); hpartial = (X*)p;
   const char* table = (const char*)be.d + off * be.point_bytes;  // T[w][off + i] = table[w * be.n + i]
   cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);

@@ -24,6 +24,16 @@
 
 namespace cocg {
 
+// The fused kernels below contain 30-60 field products and up to 20 ChaCha12 blocks per element.  Inlined, that is several hundred KB of
+// SASS -- far beyond the instruction cache (measured: 14 ms per 2^20-element launch, ~30x the multiplier bound).  The product and the PRF
+// are therefore CALLED (operands and result in registers), as the Fq2 product of the G2 group law is (ec.cuh).
+template <class P>
+__device__ __noinline__ Fp<P> fmul(Fp<P> a, Fp<P> b) { return fp_mul(a, b); }
+template <class P>
+__device__ __noinline__ Fp<P> zero_mask(const PrfKey& own, const PrfKey& prev, uint32_t ctr, size_t i) {
+  return fp_sub(prf_field<P>(own, ctr, i), prf_field<P>(prev, ctr, i));
+}
+
 template <class P, int K>
 struct Sh {
   Fp<P> v[K];
@@ -46,7 +56,7 @@ template <class P, int K>
 __device__ __forceinline__ Sh<P, K> sh_scale(const Sh<P, K>& a, const Fp<P>& f) {  // mul_with_public
   Sh<P, K> r;
 #pragma unroll
-  for (int k = 0; k < K; k++) r.v[k] = fp_mul(a.v[k], f);
+  for (int k = 0; k < K; k++) r.v[k] = fmul<P>(a.v[k], f);
   return r;
 }
 // add_with_public (rep3.rs:600-608): the constant enters component `pub_comp` only (party 0: a, party 1: b, party 2: none)
@@ -61,8 +71,8 @@ __device__ __forceinline__ Sh<P, K> sh_add_pub(const Sh<P, K>& a, const Fp<P>& f
 // The party's additive share of x * y: plain x*y; REP3 x.a*y.a + x.a*y.b + x.b*y.a (rep3.rs:656-660) as two products
 template <class P, int K>
 __device__ __forceinline__ Fp<P> sh_lmul(const Sh<P, K>& x, const Sh<P, K>& y) {
-  if (K == 1) return fp_mul(x.v[0], y.v[0]);
-  return fp_add(fp_mul(x.v[0], fp_add(y.v[0], y.v[K - 1])), fp_mul(x.v[K - 1], y.v[0]));
+  if (K == 1) return fmul<P>(x.v[0], y.v[0]);
+  return fp_add(fmul<P>(x.v[0], fp_add(y.v[0], y.v[K - 1])), fmul<P>(x.v[K - 1], y.v[0]));
 }
 
 // ---------------------------------------------------------------------------------------------- round 2: factors of z
@@ -137,16 +147,11 @@ __device__ __forceinline__ Blind<P, K> blinding_evals(const QuotScalars<P>& s, c
   o.ap = sh_add(blinder<P, K>(s, 1), sh_scale(blinder<P, K>(s, 0), w));
   o.bp = sh_add(blinder<P, K>(s, 3), sh_scale(blinder<P, K>(s, 2), w));
   o.cp = sh_add(blinder<P, K>(s, 5), sh_scale(blinder<P, K>(s, 4), w));
-  const Fp<P> w2 = fp_sqr(w);
+  const Fp<P> w2 = fmul<P>(w, w);
   o.zp = sh_add(blinder<P, K>(s, 8), sh_add(sh_scale(blinder<P, K>(s, 7), w), sh_scale(blinder<P, K>(s, 6), w2)));
-  const Fp<P> ww = fp_mul(w, s.omega), ww2 = fp_sqr(ww);
+  const Fp<P> ww = fmul<P>(w, s.omega), ww2 = fmul<P>(ww, ww);
   o.zwp = sh_add(blinder<P, K>(s, 8), sh_add(sh_scale(blinder<P, K>(s, 7), ww), sh_scale(blinder<P, K>(s, 6), ww2)));
   return o;
-}
-
-template <class P>
-__device__ __forceinline__ Fp<P> zero_mask(const PrfKey& own, const PrfKey& prev, uint32_t ctr, size_t i) {
-  return fp_sub(prf_field<P>(own, ctr, i), prf_field<P>(prev, ctr, i));
 }
 
 template <class P, int K>
@@ -160,29 +165,30 @@ __global__ void __launch_bounds__(128) plonk_quotient_l1_kernel(QuotArgs g, Quot
   Fp<P> o[kQuotL1Outs];
   o[0] = sh_lmul(a, b);                                    // a*b
   o[1] = fp_add(sh_lmul(a, bl.bp), sh_lmul(bl.ap, b));     // a*bp + ap*b
-  const Fp<P> betaw = fp_mul(s.beta, w);
+  const Fp<P> betaw = fmul<P>(s.beta, w);
   {
     const Sh<P, K> A = sh_add_pub(a, fp_add(betaw, s.gamma), pub_comp);
-    const Sh<P, K> B = sh_add_pub(b, fp_add(fp_mul(betaw, s.k1), s.gamma), pub_comp);
-    const Sh<P, K> C = sh_add_pub(c, fp_add(fp_mul(betaw, s.k2), s.gamma), pub_comp);
+    const Sh<P, K> B = sh_add_pub(b, fp_add(fmul<P>(betaw, s.k1), s.gamma), pub_comp);
+    const Sh<P, K> C = sh_add_pub(c, fp_add(fmul<P>(betaw, s.k2), s.gamma), pub_comp);
     o[2] = sh_lmul(A, B);
     o[3] = fp_add(sh_lmul(bl.ap, B), sh_lmul(A, bl.bp));
     o[4] = sh_lmul(C, z);
     o[5] = fp_add(sh_lmul(bl.cp, z), sh_lmul(C, bl.zp));
   }
   {
-    const Sh<P, K> A = sh_add_pub(a, fp_add(fp_mul(load_fp_ro<P>(g.s1, i), s.beta), s.gamma), pub_comp);
-    const Sh<P, K> B = sh_add_pub(b, fp_add(fp_mul(load_fp_ro<P>(g.s2, i), s.beta), s.gamma), pub_comp);
-    const Sh<P, K> C = sh_add_pub(c, fp_add(fp_mul(load_fp_ro<P>(g.s3, i), s.beta), s.gamma), pub_comp);
+    const Sh<P, K> A = sh_add_pub(a, fp_add(fmul<P>(load_fp_ro<P>(g.s1, i), s.beta), s.gamma), pub_comp);
+    const Sh<P, K> B = sh_add_pub(b, fp_add(fmul<P>(load_fp_ro<P>(g.s2, i), s.beta), s.gamma), pub_comp);
+    const Sh<P, K> C = sh_add_pub(c, fp_add(fmul<P>(load_fp_ro<P>(g.s3, i), s.beta), s.gamma), pub_comp);
     o[6] = sh_lmul(A, B);
     o[7] = fp_add(sh_lmul(bl.ap, B), sh_lmul(A, bl.bp));
     o[8] = sh_lmul(C, zw);
     o[9] = fp_add(sh_lmul(bl.cp, zw), sh_lmul(C, bl.zwp));
   }
-#pragma unroll
-  for (int j = 0; j < kQuotL1Outs; j++) {
-    if (K == 2) o[j] = fp_add(o[j], zero_mask<P>(own, prev, ctr + j, i));
-    store_fp<P>(g.out, (size_t)j * n4 + i, o[j]);
+#pragma unroll 1
+  for (int j = 0; j < kQuotL1Outs; j++) {  // rolled: one copy of the PRF call in the instruction stream
+    Fp<P> v = o[j];
+    if (K == 2) v = fp_add(v, zero_mask<P>(own, prev, ctr + j, i));
+    store_fp<P>(g.out, (size_t)j * n4 + i, v);
   }
 }
 
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(128) plonk_quotient_l2_kernel(QuotArgs g, Quot
   if (i >= n4) return;
   const int m = (int)(i & 3);
   const bool pub0 = pub_comp == 0;  // the additive output carries public constants for the plain driver and REP3 party 0 only
-  const Fp<P> w = load_fp_ro<P>(g.wpow, i), w2 = fp_sqr(w), w3 = fp_mul(w2, w);
+  const Fp<P> w = load_fp_ro<P>(g.wpow, i), w2 = fmul<P>(w, w), w3 = fmul<P>(w2, w);
   const Blind<P, K> bl = blinding_evals<P, K>(s, w);
   auto L1 = [&](int j) {
     Sh<P, K> r;
@@ -203,29 +209,29 @@ __global__ void __launch_bounds__(128) plonk_quotient_l2_kernel(QuotArgs g, Quot
   };
   // products of two blinding polynomials from the shared scalar products
   const Sh<P, K> X2 = sh_add(sprod<P, K>(s, 0), sh_add(sh_scale(sh_add(sprod<P, K>(s, 1), sprod<P, K>(s, 2)), w), sh_scale(sprod<P, K>(s, 3), w2)));
-  const Fp<P> om = s.omega, om2 = fp_sqr(om);
+  const Fp<P> om = s.omega, om2 = fmul<P>(om, om);
   const Sh<P, K> Y2 = sh_add(sh_add(sprod<P, K>(s, 4), sh_scale(sh_add(sprod<P, K>(s, 5), sprod<P, K>(s, 7)), w)),
                              sh_add(sh_scale(sh_add(sprod<P, K>(s, 6), sprod<P, K>(s, 8)), w2), sh_scale(sprod<P, K>(s, 9), w3)));
   const Sh<P, K> Y2w = sh_add(sh_add(sprod<P, K>(s, 4), sh_scale(sh_add(sh_scale(sprod<P, K>(s, 5), om), sprod<P, K>(s, 7)), w)),
                               sh_add(sh_scale(sh_add(sh_scale(sprod<P, K>(s, 6), om2), sh_scale(sprod<P, K>(s, 8), om)), w2),
-                                     sh_scale(sprod<P, K>(s, 9), fp_mul(om2, w3))));
+                                     sh_scale(sprod<P, K>(s, 9), fmul<P>(om2, w3))));
   const Fp<P> qm = load_fp_ro<P>(g.qm, i), ql = load_fp_ro<P>(g.ql, i), qr = load_fp_ro<P>(g.qr, i), qo = load_fp_ro<P>(g.qo, i);
   const Fp<P> l0 = load_fp_ro<P>(g.lagrange, i);
-  const Fp<P> a2l0 = fp_mul(s.alpha2, l0);
+  const Fp<P> a2l0 = fmul<P>(s.alpha2, l0);
   // ---- linear parts, component a only (the party's own additive share)
   Fp<P> t, tz;
   {
     const Fp<P> a = load_fp<P>(g.ea[0], i), b = load_fp<P>(g.eb[0], i), c = load_fp<P>(g.ec[0], i), z = load_fp<P>(g.ez[0], i);
     const Fp<P> p1 = load_fp<P>(g.l1[0], i), p23 = load_fp<P>(g.l1[0], n4 + i);
-    t = fp_add(fp_add(fp_mul(qm, p1), fp_mul(ql, a)), fp_add(fp_mul(qr, b), fp_mul(qo, c)));
+    t = fp_add(fp_add(fmul<P>(qm, p1), fmul<P>(ql, a)), fp_add(fmul<P>(qr, b), fmul<P>(qo, c)));
     for (int j = 0; j < n_public; j++)  // pi = - sum_j L_j(w^i) * buffer_a[j]   (round3.rs:367-373)
-      t = fp_sub(t, fp_mul(load_fp_ro<P>(g.lagrange, (size_t)j * n4 + i), load_fp<P>(g.buf_a[0], j)));
-    t = fp_add(t, fp_mul(a2l0, z));
+      t = fp_sub(t, fmul<P>(load_fp_ro<P>(g.lagrange, (size_t)j * n4 + i), load_fp<P>(g.buf_a[0], j)));
+    t = fp_add(t, fmul<P>(a2l0, z));
     if (pub0) t = fp_add(t, fp_sub(load_fp_ro<P>(g.qc, i), a2l0));  // + qc - alpha^2 L_1
     Fp<P> a0 = p23;
-    if (m) a0 = fp_add(a0, fp_mul(s.zeta[m], X2.v[0]));
-    tz = fp_add(fp_add(fp_mul(qm, a0), fp_mul(ql, bl.ap.v[0])), fp_add(fp_mul(qr, bl.bp.v[0]), fp_mul(qo, bl.cp.v[0])));
-    tz = fp_add(tz, fp_mul(a2l0, bl.zp.v[0]));
+    if (m) a0 = fp_add(a0, fmul<P>(s.zeta[m], X2.v[0]));
+    tz = fp_add(fp_add(fmul<P>(qm, a0), fmul<P>(ql, bl.ap.v[0])), fp_add(fmul<P>(qr, bl.bp.v[0]), fmul<P>(qo, bl.cp.v[0])));
+    tz = fp_add(tz, fmul<P>(a2l0, bl.zp.v[0]));
   }
   // ---- bilinear parts
   Fp<P> e23 = Fp<P>::zero(), e23z = Fp<P>::zero();
@@ -241,13 +247,13 @@ __global__ void __launch_bounds__(128) plonk_quotient_l2_kernel(QuotArgs g, Quot
       const Fp<P> ze = s.zeta[m];
       const Sh<P, K> Xz = sh_add(X0, sh_scale(sh_add(X1, sh_scale(X2, ze)), ze));
       const Sh<P, K> Yz = sh_add(Y0, sh_scale(sh_add(Y1, sh_scale(Y2g, ze)), ze));
-      post = fp_mul(fp_sub(sh_lmul(Xz, Yz), r), s.zeta_inv[m]);
+      post = fmul<P>(fp_sub(sh_lmul(Xz, Yz), r), s.zeta_inv[m]);
     }
     if (grp == 0) { e23 = r; e23z = post; }
     else { e23 = fp_sub(e23, r); e23z = fp_sub(e23z, post); }
   }
-  t = fp_add(t, fp_mul(s.alpha, e23));
-  tz = fp_add(tz, fp_mul(s.alpha, e23z));
+  t = fp_add(t, fmul<P>(s.alpha, e23));
+  tz = fp_add(tz, fmul<P>(s.alpha, e23z));
   if (K == 2) {
     t = fp_add(t, zero_mask<P>(own, prev, ctr, i));
     tz = fp_add(tz, zero_mask<P>(own, prev, ctr + 1, i));

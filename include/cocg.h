@@ -125,6 +125,9 @@ COCG_API int cocg_ntt(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, c
  * mont = 1 if coordinates are Montgomery limbs, 0 if canonical. */
 COCG_API int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size_t n, size_t stride, int mont, uint64_t* handle);
 COCG_API int cocg_bases_free(cocg_ctx* ctx, uint64_t handle);
+/* The window plan of the resident table built for a query of n points: signed digits of window_bits bits, `windows` of them per scalar
+ * (= table rows = additions per scalar).  No GPU needed; bench.py reports the additions per MSM from it. */
+COCG_API int cocg_msm_plan(int curve, size_t n, int* window_bits, int* windows);
 /* Synthetic bases generated in HBM: P0 + i*Q for two points derived from `seed` (HOST pointer, 32 bytes) -- valid, distinct
  * curve points for the 2^20..2^22 benchmark configurations, for which no zkey ships (csrc/gen.cu). */
 COCG_API int cocg_bases_generate(cocg_ctx* ctx, int group, size_t n, const void* seed, uint64_t* handle);
