@@ -516,6 +516,16 @@ struct cohost_shamir_session {
   std::vector<std::unique_ptr<CoGroth16<ShamirProtocol>>> prover;
   std::vector<CoGroth16<ShamirProtocol>::Handles> hd;
   bool failed = false;
+  // multi-GPU (index-range sharded MSMs, SURVEY 8(e) / BASELINE configs[4]): the parties' partial sums are exchanged by ONE all-gather per
+  // proof, performed by the caller's callback on the thread of the last party to arrive
+  int rank = 0, world = 1;
+  cohost_gather_cb gather = nullptr;
+  void* gather_user = nullptr;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  bool combined = false, abort_wait = false;
+  std::vector<MsmPartials> partials;
 };
 
 extern "C" int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out) {
@@ -536,6 +546,64 @@ extern "C" int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int
     *out = s.release();
   });
 }
+// Index-range sharding of every MSM over `world` GPUs (one process per GPU; the zkey must have been created with the same rank / world).
+// gather(user, local, bytes, gathered): must fill `gathered` (world x bytes, rank order) with every rank's `local` -- one all-gather.
+extern "C" int cohost_shamir_session_set_shard(cohost_shamir_session* s, int rank, int world, cohost_gather_cb gather, void* user) {
+  if (!s) return fail("cohost_shamir_session_set_shard: null session");
+  if (world < 1 || rank < 0 || rank >= world) return fail("cohost_shamir_session_set_shard: bad rank / world");
+  if (world > 1 && !gather) return fail("cohost_shamir_session_set_shard: a gather callback is required when world > 1");
+  if (s->zkey->zk.world != 1 && (s->zkey->zk.world != world || s->zkey->zk.rank != rank)) return fail("cohost_shamir_session_set_shard: the zkey holds another rank's shard");
+  s->rank = rank;
+  s->world = world;
+  s->gather = gather;
+  s->gather_user = user;
+  s->partials.assign(s->n, MsmPartials());
+  cohost_shamir_session* sp = s;
+  for (int i = 0; i < s->n; i++) {
+    s->prover[i]->shard.rank = rank;
+    s->prover[i]->shard.world = world;
+    if (world == 1) { s->prover[i]->combine = nullptr; continue; }
+    s->prover[i]->combine = [sp](int party, MsmPartials& m) {
+      const size_t lq = sp->zkey->lq, pl = 18 * lq;  // h, l, a, b1 (G1 Jacobian) | b2 (G2 Jacobian), one component
+      std::unique_lock<std::mutex> lk(sp->mu);
+      sp->partials[party] = m;
+      if (++sp->arrived == sp->n) {
+        std::vector<uint64_t> local((size_t)sp->n * pl), all((size_t)sp->world * sp->n * pl);
+        for (int i = 0; i < sp->n; i++) {
+          const MsmPartials& q = sp->partials[i];
+          const Point* g1[4] = {&q.h_acc.a, &q.l_acc.a, &q.a_acc.a, &q.b1_acc.a};
+          for (int k = 0; k < 4; k++) memcpy(local.data() + i * pl + k * 3 * lq, g1[k]->l, 3 * lq * 8);
+          memcpy(local.data() + i * pl + 12 * lq, q.b2_acc.a.l, 6 * lq * 8);
+        }
+        int rc = sp->gather(sp->gather_user, local.data(), local.size() * 8, all.data());
+        if (rc) {
+          sp->abort_wait = true;
+          sp->cv.notify_all();
+          throw Error("the multi-GPU gather callback failed");
+        }
+        ShamirProtocol& d = *sp->drv[0];
+        for (int i = 0; i < sp->n; i++) {
+          MsmPartials& q = sp->partials[i];
+          Point* g1[4] = {&q.h_acc.a, &q.l_acc.a, &q.a_acc.a, &q.b1_acc.a};
+          for (int k = 0; k < 5; k++) {
+            const int g = k < 4 ? 1 : 2;
+            Point acc = d.infinity(g);
+            for (int r = 0; r < sp->world; r++)
+              acc = d.ec_add(g, acc, load_point(all.data() + ((size_t)r * sp->n + i) * pl + (k < 4 ? k * 3 * lq : 12 * lq), 3 * g * lq));
+            (k < 4 ? *g1[k] : q.b2_acc.a) = acc;
+          }
+        }
+        sp->combined = true;
+        sp->cv.notify_all();
+      } else {
+        sp->cv.wait(lk, [&] { return sp->combined || sp->abort_wait; });
+        if (sp->abort_wait) throw Error("prove aborted while waiting for the multi-GPU combine");
+      }
+      m = sp->partials[party];
+    };
+  }
+  return 0;
+}
 extern "C" void cohost_shamir_session_destroy(cohost_shamir_session* s) {
   if (!s) return;
   for (size_t i = 0; i < s->drv.size(); i++) s->drv[i]->release(s->prover[i]->last_h);
@@ -552,6 +620,9 @@ extern "C" int cohost_shamir_prove(cohost_shamir_session* s, const void* public_
   std::vector<std::string> errs(s->n);
   std::vector<Groth16Proof> proofs(s->n);
   std::vector<const void*> w(wit, wit + s->n);
+  s->arrived = 0;
+  s->combined = false;
+  s->abort_wait = false;
   for (int i = 0; i < s->n; i++) {
     th[i] = std::thread([&, i] {
       try {
@@ -566,6 +637,11 @@ extern "C" int cohost_shamir_prove(cohost_shamir_session* s, const void* public_
       } catch (const std::exception& e) {
         errs[i] = e.what();
         s->net->close_all();
+        {
+          std::lock_guard<std::mutex> lk(s->mu);
+          s->abort_wait = true;
+        }
+        s->cv.notify_all();
       }
     });
   }

@@ -28,7 +28,7 @@ HOST_SYMBOLS = [
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
     "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
-    "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
+    "cohost_shamir_session_set_shard", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
     "cohost_plonk_prove", "cohost_plonk_set_mpc_exchange", "cohost_plonk_launch_count", "cohost_plonk_profile_enable",
     "cohost_plonk_profile_reset", "cohost_plonk_profile_read", "cohost_plonk_round_times", "cohost_plonk_trace_enable",
     "cohost_plonk_trace_get", "cohost_plonk_proof_to_json",
@@ -53,6 +53,8 @@ class ZKeyInfo(ctypes.Structure):
 class Rep3Randomness(ctypes.Structure):
     _fields_ = [("r", vp), ("s", vp), ("mask_rs", vp), ("mask_pt", vp), ("masks1", vp * 3), ("masks2", vp * 3)]
 
+
+GATHER_CB = ctypes.CFUNCTYPE(ci, vp, vp, sz, vp)
 
 _host = None
 
@@ -125,6 +127,7 @@ def load_host():
     L.cohost_shamir_session_destroy.argtypes = [vp]
     L.cohost_shamir_session_destroy.restype = None
     L.cohost_shamir_prove.argtypes = [vp, vp, pvp, vp, vp]
+    L.cohost_shamir_session_set_shard.argtypes = [vp, ci, ci, GATHER_CB, vp]
     L.cohost_msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     L.cohost_proof_to_json.argtypes = [ci, vp, vp, sz, ctypes.POINTER(sz)]
     L.cohost_public_inputs_to_json.argtypes = [ci, vp, sz, vp, sz, ctypes.POINTER(sz)]
@@ -525,7 +528,10 @@ class Rep3Session:
 class ShamirSession:
     """n CoGroth16<ShamirProtocol> provers (threshold t) on n threads over an in-process network."""
 
-    def __init__(self, zkey: Groth16ZKey, num_parties: int = 3, threshold: int = 1, seeds: bytes | None = None):
+    def __init__(self, zkey: Groth16ZKey, num_parties: int = 3, threshold: int = 1, seeds: bytes | None = None, rank: int = 0, world: int = 1,
+                 all_gather=None):
+        """world > 1: MSMs sharded by index range over `world` ranks; all_gather(np.ndarray uint64) -> concatenation over ranks (one
+        NCCL all-gather per proof).  Every rank must pass the same seeds."""
         self.zkey, self.n, self.t = zkey, num_parties, threshold
         # every double-random pair, and through rand() the Groth16 blinders r and s, derive from these seeds: entropy by default
         # (ShamirProtocol::new seeds its RngType from entropy, shamir.rs:196-245); fixed seeds are for tests and the benchmark only
@@ -535,6 +541,25 @@ class ShamirSession:
         h = vp()
         _ck(load_host().cohost_shamir_session_create(zkey.h, num_parties, threshold, self._seeds.ctypes.data, ctypes.byref(h)))
         self.h = h
+        self._cb = None
+        if world > 1:
+            _need(all_gather is not None, "ShamirSession: world > 1 needs an all_gather function")
+
+            def cb(_user, local, nbytes, gathered):
+                try:
+                    loc = np.ctypeslib.as_array(ctypes.cast(local, ctypes.POINTER(ctypes.c_uint64)), shape=(nbytes // 8,))
+                    out = np.ascontiguousarray(all_gather(loc.copy()), dtype=np.uint64)
+                    if out.size != world * (nbytes // 8):
+                        return 1
+                    ctypes.memmove(gathered, out.ctypes.data, out.nbytes)
+                    return 0
+                except Exception:  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+
+            self._cb = GATHER_CB(cb)
+            _ck(load_host().cohost_shamir_session_set_shard(self.h, rank, world, self._cb, None))
 
     def prove(self, public_inputs, wit):
         """wit: n host share vectors.  Returns (proofs (n, A|B|C), rs (n, 2, 4): each party's shares of r and s)."""

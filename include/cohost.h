@@ -116,6 +116,11 @@ COHOST_API int cohost_rep3_phase_times(cohost_rep3_session* s, double* out);
 /* num_parties CoGroth16<ShamirProtocol> provers (mpc-core/src/protocols/shamir.rs), threshold t with 2t + 1 <= num_parties, on
  * one thread each over an in-process network; seeds: num_parties x 32 bytes.  wit[i]: party i's HOST share vector; proofs_out:
  * num_parties x (A | B | C); rs_out: NULL or num_parties x (share of r | share of s) for tests. */
+/* Multi-GPU Shamir (BASELINE configs[4]): every MSM is sharded by index range over `world` ranks (the zkey created with the same rank /
+ * world keeps only this rank's slice of each query resident); the partial sums of all parties travel in ONE all-gather per proof, which
+ * the caller supplies: gather(user, local, bytes, gathered) fills gathered[world x bytes] in rank order and returns 0. */
+typedef int (*cohost_gather_cb)(void* user, const void* local, size_t bytes, void* gathered);
+COHOST_API int cohost_shamir_session_set_shard(cohost_shamir_session* s, int rank, int world, cohost_gather_cb gather, void* user);
 COHOST_API int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out);
 COHOST_API void cohost_shamir_session_destroy(cohost_shamir_session* s);
 COHOST_API int cohost_shamir_prove(cohost_shamir_session* s, const void* public_inputs, const void* const* wit, void* proofs_out, void* rs_out);

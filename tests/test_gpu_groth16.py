@@ -321,3 +321,61 @@ def test_rep3_device_exchange_equals_host_exchange(cocg):
     assert groth16.verify(vk, *proof_points(c, want[0]), public)
     sess.close()
     dz.close()
+
+
+def test_shamir_prove_sharded_msm_equals_single(cocg):
+    """BASELINE configs[4] in miniature: CoGroth16<ShamirProtocol> with every MSM sharded by index range over `world` ranks and ONE
+    all-gather of the partial sums per proof (mpc-core/src/protocols/shamir.rs:1027-1039 is the call being sharded), emulated with two
+    sessions on one GPU whose gather callbacks meet at a barrier: the sharded runs open the single-GPU proof, on both curves."""
+    import threading
+    for curve in ("bn254", "bls12_381"):
+        zk, wt, vk, public = load_fixture(curve, "poseidon")
+        c = zk.curve
+        prover, dz = device_zkey(cocg, zk)
+        rng = random.Random(66)
+        ell = zk.n_public
+        pub = cref.fr_to_mont(c, wt[:ell + 1])
+        shares = [cref.fr_to_mont(c, s) for s in _share_shamir([v % c.r for v in wt[ell + 1:]], 3, 1, rng, c.r)]
+        seeds = bytes(range(96))
+        single = prover.ShamirSession(dz, 3, 1, seeds=seeds)
+        want, _ = single.prove(pub, shares)
+        single.close()
+        world = 2
+        barrier = threading.Barrier(world)
+        slots = [None] * world
+
+        def gather_for(rank):
+            def gather(local):
+                slots[rank] = local
+                barrier.wait()
+                out = np.concatenate(slots)
+                barrier.wait()
+                return out
+            return gather
+
+        c_g1 = lambda pts: cref.g_to_mont(c, pts, 1)
+        c_g2 = lambda pts: cref.g_to_mont(c, pts, 2)
+        cid = cocg.BN254 if c is BN254 else cocg.BLS12_381
+        zks = [prover.Groth16ZKey(cid, zk.n_public, zk.n_vars, zk.pow, zk.num_constraints, csr_of(c, zk.a_rows), csr_of(c, zk.b_rows),
+                                  c_g1(zk.a_query), c_g1(zk.b_g1_query), c_g2(zk.b_g2_query), c_g1(zk.h_query), c_g1(zk.l_query),
+                                  c_g1([zk.alpha_g1]), c_g1([zk.beta_g1]), c_g1([zk.delta_g1]), c_g2([zk.beta_g2]), c_g2([zk.delta_g2]),
+                                  rank=k, world=world) for k in range(world)]
+        sessions = [prover.ShamirSession(zks[k], 3, 1, seeds=seeds, rank=k, world=world, all_gather=gather_for(k)) for k in range(world)]
+        outs = [None] * world
+
+        def run(k):
+            outs[k] = sessions[k].prove(pub, shares)[0]
+
+        th = [threading.Thread(target=run, args=(k,)) for k in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for k in range(world):
+            assert [proof_points(c, p) for p in outs[k]] == [proof_points(c, p) for p in want], (curve, k)
+        assert groth16.verify(vk, *proof_points(c, outs[0][0]), public)
+        for s_ in sessions:
+            s_.close()
+        for z_ in zks:
+            z_.close()
+        dz.close()
