@@ -221,7 +221,11 @@ def workload_config(args, world):
                         + (" (BASELINE configs[2])" if default else " (non-default configuration)"),
             "curve": args.curve, "protocol": args.protocol, "domain_size": n, "n_vars": n, "n_public": 1, "nnz_per_row": 2,
             "msm_per_proof": f"3 parties x {comps} components x (4 G1 + 1 G2)", "ntt_per_proof": 18 * comps,
-            "parallelism": "single GPU" if world == 1 else f"MSM bases sharded by index range over {world} GPUs, NTT replicated, 1 all-gather/proof",
+            "parallelism": "single GPU" if world == 1 else (
+                f"15 equal blocks of the proof (per party: witness map + h MSMs; per party and share component: the l/a/b_g1 MSMs, the b_g2 MSM) "
+                f"spread over {world} GPUs at full size, mul_vec payloads GPU to GPU over NCCL, 1 all-gather/proof"
+                if args.protocol == "rep3" and getattr(args, "shard_mode", "blocks") == "blocks" else
+                f"MSM bases sharded by index range over {world} GPUs, NTT replicated, 1 all-gather/proof"),
             "l2_policy": "inputs_exceed_l2 (>= 0.9 GB of bases + share vectors streamed per proof vs 126 MB L2)"}
 
 
@@ -251,8 +255,11 @@ def run_own(args):
     modulus = BN254_R if args.curve == "bn254" else BLS381_R
     if args.protocol == "shamir":
         return run_own_shamir(args, cocg, torch, curve_id, modulus, local, (n_public, n_vars, rows, A, B), seed_bytes, rng)
-    zk = cocg.Groth16ZKey(curve_id, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes, rank=rank, world=world)
-    sess = cocg.Rep3Session(zk, seeds=PRF_SEEDS, rank=rank, world=world)
+    from importlib import import_module
+    distmod = import_module("collaborative-circom_b200.distributed")
+    mode = args.shard_mode if world > 1 else "ranges"
+    zk = cocg.Groth16ZKey(curve_id, n_public, n_vars, log_n, rows, A, B, device=local, synthetic_seed=seed_bytes, rank=rank, world=world, shard_mode=mode)
+    sess = cocg.Rep3Session(zk, seeds=PRF_SEEDS, rank=rank, world=world, comm=distmod.make_p2p(torch.device("cuda", local)) if mode == "blocks" else None)
     # witness: x = x0 + x1 + x2, party i holds (x_i, x_{i-1}) (rep3.rs:57-68); pinned host copies + resident device copies
     xs = []
     for i in range(3):
@@ -269,8 +276,7 @@ def run_own(args):
     pub = np.stack([limbs_of(r1), limbs_of(12345 * r1 % modulus)])
     setup_s = time.perf_counter() - t_setup
 
-    from importlib import import_module
-    all_gather = import_module("collaborative-circom_b200.distributed").make_all_gather(world, torch.device("cuda", local))
+    all_gather = distmod.make_all_gather(world, torch.device("cuda", local))
 
     def step(device_resident):
         if device_resident:
@@ -345,37 +351,44 @@ def run_own(args):
         sess1.close()
         zk1.close()
 
-    # The same accumulate kernel timed ALONE (one context, one stream, no other party competing for the SMs): the in-situ scope times
-    # above include the time slices the GPU gives to the other two parties' kernels.  One G1 query of this rank's shard size, k = 1.
+    # The accumulate kernel timed ALONE (one context, one stream, nothing else on the GPU): the in-situ scope times above contain the
+    # time slices the GPU gives to the other parties' kernels.  One G1 and one G2 query of the size a rank runs (the full query in
+    # block mode and at N = 1; this rank's index range in `ranges` mode), one share component each.
     alone = None
-    if world == 1:
-        bits = 254 if args.curve == "bn254" else 255
-        per_alone = n_aux
-        h_alone = ctx.bases_generate(1, per_alone, bytes([77] * 32))
-        ctx.msm(h_alone, [dev[0]], n=per_alone)
-        ctx.profile(True)
-        ctx.profile_reset()
-        for _ in range(5):
-            ctx.msm(h_alone, [dev[0]], n=per_alone)
-        ctx.sync()
-        pa = ctx.profile_read()
-        ctx.profile(False)
-        ctx.bases_free(h_alone)
-        c_bits, nwin = cocg.msm_plan(curve_id, per_alone)
-        alone = {"ms": pa["msm_accumulate"][0] / max(pa["msm_accumulate"][1], 1), "terms": per_alone, "window_bits": c_bits, "windows": nwin}
+    if rank == 0:
+        per_alone = n_aux if mode == "blocks" or world == 1 else (n_aux + world - 1) // world
+        alone = {"terms": per_alone}
+        for grp, key in ((1, "g1"), (2, "g2")):
+            hb = ctx.bases_generate(grp, per_alone, bytes([77 + grp] * 32))
+            ctx.msm(hb, [dev[0]], n=per_alone)
+            ctx.profile(True)
+            ctx.profile_reset()
+            for _ in range(5):
+                ctx.msm(hb, [dev[0]], n=per_alone)
+            ctx.sync()
+            pa = ctx.profile_read()
+            ctx.profile(False)
+            ctx.bases_free(hb)
+            alone[key + "_ms"] = pa["msm_accumulate"][0] / max(pa["msm_accumulate"][1], 1)
+        alone["window_bits"], alone["windows"] = cocg.msm_plan(curve_id, per_alone)
 
     value = args.steps / (ms / 1e3)
     e2e = args.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak()
-    # roofline of the dominant kernel: MSM bucket accumulation.  Algorithmic bytes per launch scope = one read of every point of
-    # the rank's slice + one read of its scalar: G1 96 B/term, G2 160 B/term; one scope = one share component.
-    per = (n_aux + world - 1) // world
-    perh = (n + world - 1) // world
-    scopes_per_proof = 3 * 2 * 5
+    # roofline of the dominant kernel: MSM bucket accumulation.  Algorithmic bytes per launch = one read of every point + one read of
+    # its scalar: G1 96 B/term, G2 160 B/term.  A proof launches it 4 x G1 : 1 x G2 per party and share component, so
+    # the reported figure is (4 x 96 + 160) x terms bytes over (4 x t_G1 + t_G2), with the kernel times measured alone (above);
+    # `in_situ` is the same ratio from the event scopes inside the timed proofs (they overlap with the other parties' kernels).
+    per = n_aux if mode == "blocks" or world == 1 else (n_aux + world - 1) // world
+    perh = n if mode == "blocks" or world == 1 else (n + world - 1) // world
     bytes_per_proof = 3 * 2 * (perh * 96 + 3 * per * 96 + per * 160)
     acc_ms, acc_n = prof["msm_accumulate"]
-    avg_ms = acc_ms / max(acc_n, 1)
-    achieved = (bytes_per_proof / scopes_per_proof) / (avg_ms * 1e-3) / 1e9 if acc_n else 0.0
+    in_situ = None
+    if acc_n and world == 1:
+        in_situ = bytes_per_proof / (acc_ms / args.steps * 1e-3) / 1e9
+    achieved = 0.0
+    if alone:
+        achieved = alone["terms"] * (4 * 96 + 160) / ((4 * alone["g1_ms"] + alone["g2_ms"]) * 1e-3) / 1e9
     kernels = {}
     alg = {"msm_sort": bytes_per_proof, "msm_accumulate": bytes_per_proof, "msm_reduce": bytes_per_proof,
            "ntt": 36 * 64 * n, "vec": 3 * (2 * 160 + 2 * 96) * n, "spmv": 3 * 2 * 2 * (2 * rows * 68 + rows * 36)}
@@ -398,9 +411,10 @@ def run_own(args):
             "proof_sha256": proof_sha256,
             "proof_sha256_of": f"proof number {args.warmup + args.steps} of the value leg (A | B | C packed affine Montgomery limbs), fixed PRF seeds",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(world),
-                         "kernel": "msm_accumulate_kernel (+ msm_heavy_kernel), per share-component launch, timed in situ with the three "
-                                   "parties' streams running concurrently", "peak_source": peak_src,
-                         "note": "MSM is bound by 32-bit integer multiply-add issue, not HBM (DESIGN.md)"},
+                         "kernel": "msm_accumulate_kernel: algorithmic bytes of the 4 G1 + 1 G2 launches of one party and share component over their "
+                                   "durations, each instantiation timed alone with CUDA events on its launching stream in this run",
+                         "in_situ": in_situ, "peak_source": peak_src,
+                         "note": "MSM is bound by 32-bit integer multiply-add issue, not HBM (DESIGN.md section 4): see `issue`"},
             "replicas": replicas,
             "kernels": kernels, "setup_s": round(setup_s, 2),
             "host_phases_ms": {"witness_map": round(float(phases[0]), 2), "msm": round(float(phases[1]), 2),
@@ -408,17 +422,17 @@ def run_own(args):
                                "value_leg": [round(float(x), 2) for x in phases_value]},
         }
         if alone:
-            # issue roofline of the same kernel: 10 Fq multiplications (8M + 2S) per table point added; ceiling = 148 SMs x 32
-            # IMAD.WIDE/clk x sm_max_mhz / 144 multiply-pipe instructions per 8-limb Montgomery product (SASS count)
-            fq_mul = alone["terms"] * alone["windows"] * 10 / (alone["ms"] * 1e-3) / 1e9
+            # issue roofline of the same kernel: 10 Fq multiplications (8M + 2S) per table point added
+            fq_mul = alone["terms"] * alone["windows"] * 10 / (alone["g1_ms"] * 1e-3) / 1e9
             # measured in this run: a pure dependent chain of the library's own Montgomery product on every SM (cocg_fp_mul_ceiling);
             # the hardware figure beside it is 148 SMs x 32 IMAD.WIDE/clk x sm_max_mhz / 128 wide products per 8-limb multiplication
             ceiling = ctx.fp_mul_ceiling(base_field=True)
             hw = 148 * 32 * ((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 128 / 1e9
             ceiling_src = f"fp_mul chain measured in this run (cocg_fp_mul_ceiling); IMAD.WIDE hardware bound {hw:.1f} G/s"
             out["roofline"].update({
-                "achieved_alone": alone["terms"] * 96 / (alone["ms"] * 1e-3) / 1e9, "frac_alone": alone["terms"] * 96 / (alone["ms"] * 1e-3) / 1e9 / peak,
-                "alone_ms": alone["ms"],
+                "g1": {"ms": alone["g1_ms"], "GBps": alone["terms"] * 96 / (alone["g1_ms"] * 1e-3) / 1e9},
+                "g2": {"ms": alone["g2_ms"], "GBps": alone["terms"] * 160 / (alone["g2_ms"] * 1e-3) / 1e9},
+                "terms_per_launch": alone["terms"],
                 "issue": {"unit": "G Fq-mul/s", "achieved": fq_mul, "peak": ceiling, "frac": fq_mul / ceiling,
                           "note": f"G1 accumulate alone: {alone['terms']} terms x {alone['windows']} windows (c = {alone['window_bits']}) x 10 "
                                   f"Montgomery products; peak = {ceiling_src}"}})
@@ -862,6 +876,8 @@ def main():
     ap.add_argument("--curve", default="bn254", choices=["bn254", "bls12_381"], help="non-default: BLS12-381 (BASELINE configs[4] flavour)")
     ap.add_argument("--protocol", default="rep3", choices=["rep3", "shamir"], help="non-default: Shamir (3,1), single GPU only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-mode", default="blocks", choices=["blocks", "ranges"],
+                    help="N > 1, groth16 REP3: blocks = whole witness maps / MSM bundles per rank (default); ranges = every MSM cut into N index ranges")
     args = ap.parse_args()
     if args.log_n is None:
         args.log_n = 18 if args.workload == "plonk" else 20

@@ -26,7 +26,7 @@ SYMBOLS = [
     "cocg_bases_share", "cocg_csr_share", "cocg_bases_generate", "cocg_bases_download", "cocg_profile_enable",
     "cocg_profile_read", "cocg_profile_reset", "cocg_msm_multi", "cocg_vec_axpy", "cocg_csr_upload_form", "cocg_csr_download", "cocg_bases_generate_range",
     "cocg_fp_mul_ceiling", "cocg_vec_gather", "cocg_vec_scan", "cocg_vec_inv", "cocg_poly_eval", "cocg_vec_lincomb", "cocg_vec_fill",
-    "cocg_msm_plan", "cocg_plonk_z_factors", "cocg_plonk_quotient_l1", "cocg_plonk_quotient_l2", "cocg_plonk_t_finish",
+    "cocg_msm_plan", "cocg_bases_check", "cocg_plonk_z_factors", "cocg_plonk_quotient_l1", "cocg_plonk_quotient_l2", "cocg_plonk_t_finish",
 ]
 
 _lib = None
@@ -94,6 +94,7 @@ def load():
         "cocg_profile_reset": (ci, [vp]),
         "cocg_fp_mul_ceiling": (ci, [vp, ci, ctypes.POINTER(ctypes.c_double)]),
         "cocg_msm_plan": (ci, [ci, sz, ctypes.POINTER(ci), ctypes.POINTER(ci)]),
+        "cocg_bases_check": (ci, [vp, u64, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]),
         "cocg_vec_gather": (ci, [vp, vp, sz, vp, vp, sz]),
         "cocg_vec_scan": (ci, [vp, ci, vp, vp, sz]),
         "cocg_vec_inv": (ci, [vp, vp, vp, sz, ctypes.POINTER(sz)]),

@@ -191,6 +191,12 @@ class Context:
         self._groups[hdl.value] = group
         return hdl.value
 
+    def bases_check(self, handle: int, subgroup: bool = True):
+        """-> (number of points off the curve / outside the prime-order subgroup, smallest such index or None)"""
+        bad, first = ctypes.c_size_t(), ctypes.c_size_t()
+        self._ck(self.L.cocg_bases_check(self.h, handle, 1 if subgroup else 0, ctypes.byref(bad), ctypes.byref(first)))
+        return int(bad.value), (int(first.value) if bad.value else None)
+
     def bases_download(self, handle: int, off: int, n: int) -> np.ndarray:
         group = self._groups[handle]
         out = np.zeros((n, 2 * group * self.lq), dtype=np.uint64)

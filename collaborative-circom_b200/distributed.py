@@ -40,3 +40,32 @@ def make_all_gather(world: int, device=None):
         return dst.cpu().numpy().view(np.uint64)
 
     return all_gather
+
+
+class _DevBuf:
+    """A raw device range as a __cuda_array_interface__ object, so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def make_p2p(device):
+    """The cross-GPU leg of the REP3 network in block mode (host/network.hpp DeviceBridge): returns comm(ops) for Rep3Session, which
+    issues the listed sends / receives between GPUs as ONE grouped NCCL call (batch_isend_irecv: sends and receives of a round cannot
+    deadlock) and returns when the data has arrived.  ops: (dir, peer_rank, device_ptr, nbytes), dir 0 = send, 1 = receive."""
+    import torch
+    import torch.distributed as dist
+
+    def comm(ops):
+        with torch.cuda.device(device):
+            reqs = []
+            keep = []
+            for d, peer, ptr, nbytes in ops:
+                t = torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+                keep.append(t)
+                reqs.append(dist.P2POp(dist.isend if d == 0 else dist.irecv, t, peer))
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+            torch.cuda.current_stream().synchronize()
+
+    return comm

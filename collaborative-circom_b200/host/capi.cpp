@@ -52,6 +52,7 @@ struct cohost_rep3_session {
   std::unique_ptr<CoGroth16<Rep3Protocol>> prover[3];
   CoGroth16<Rep3Protocol>::Handles hd[3];
   DevVec pub[3];
+  std::unique_ptr<DeviceBridge> bridge;  // block mode: cross-GPU leg of the witness maps' mul_vec rounds
   // multi-GPU two-phase state
   int world = 1, rank = 0;
   std::mutex mu;
@@ -117,8 +118,10 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
     zk.rank = d->world > 1 ? d->rank : 0;
     zk.world = d->world > 1 ? d->world : 1;
     if (zk.rank < 0 || zk.rank >= zk.world) throw Error("zkey: bad rank / world");
+    zk.blocks = zk.world > 1 && d->shard_mode == 1;
+    if (zk.blocks) zk.plan = BlockPlan::make(zk.world);
     size_t len_h = zk.domain_size(), len_x = zk.n_aux();
-    if (zk.world > 1) {
+    if (zk.world > 1 && !zk.blocks) {
       MsmShard sh;
       sh.rank = zk.rank;
       sh.world = zk.world;
@@ -128,12 +131,14 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
       zk.l_first = off_x;
       zk.a_first = zk.b_g1_first = zk.b_g2_first = 1 + l + off_x;
     }
-    const size_t len_q = zk.world > 1 ? len_x : m;  // a / b queries: whole (heads included) or the aux slice
-    bases(COCG_G1, d->a_query, zk.a_first, len_q, 1, &zk.a_query, "a_query");
-    bases(COCG_G1, d->b_g1_query, zk.b_g1_first, len_q, 2, &zk.b_g1_query, "b_g1_query");
-    bases(COCG_G2, d->b_g2_query, zk.b_g2_first, len_q, 3, &zk.b_g2_query, "b_g2_query");
-    bases(COCG_G1, d->h_query, zk.h_first, len_h, 4, &zk.h_query, "h_query");
-    bases(COCG_G1, d->l_query, zk.l_first, len_x, 5, &zk.l_query, "l_query");
+    const size_t len_q = (zk.world > 1 && !zk.blocks) ? len_x : m;  // a / b queries: whole (heads included) or the aux slice
+    // block mode: whole queries, but only those of the blocks this rank runs (types.hpp BlockPlan)
+    const bool want_g1 = !zk.blocks || zk.plan.has_g1(zk.rank), want_g2 = !zk.blocks || zk.plan.has_g2(zk.rank), want_h = !zk.blocks || zk.plan.has_wm(zk.rank);
+    if (want_g1) bases(COCG_G1, d->a_query, zk.a_first, len_q, 1, &zk.a_query, "a_query");
+    if (want_g1) bases(COCG_G1, d->b_g1_query, zk.b_g1_first, len_q, 2, &zk.b_g1_query, "b_g1_query");
+    if (want_g2) bases(COCG_G2, d->b_g2_query, zk.b_g2_first, len_q, 3, &zk.b_g2_query, "b_g2_query");
+    if (want_h) bases(COCG_G1, d->h_query, zk.h_first, len_h, 4, &zk.h_query, "h_query");
+    if (want_g1) bases(COCG_G1, d->l_query, zk.l_first, len_x, 5, &zk.l_query, "l_query");
     check(c, cocg_csr_upload_form(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, d->coeff_form, &zk.csr_a), "csr_a");
     check(c, cocg_csr_upload_form(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, d->coeff_form, &zk.csr_b), "csr_b");
     zk.a_head.resize(l + 1);
@@ -187,11 +192,12 @@ extern "C" void cohost_zkey_destroy(cohost_zkey* z) {
 
 template <class H>
 static void share_handles(cocg_ctx* ctx, const ZKey& zk, H& hd) {
-  check(ctx, cocg_bases_share(ctx, zk.owner, zk.a_query, &hd.a_query), "share a_query");
-  check(ctx, cocg_bases_share(ctx, zk.owner, zk.b_g1_query, &hd.b_g1_query), "share b_g1_query");
-  check(ctx, cocg_bases_share(ctx, zk.owner, zk.b_g2_query, &hd.b_g2_query), "share b_g2_query");
-  check(ctx, cocg_bases_share(ctx, zk.owner, zk.h_query, &hd.h_query), "share h_query");
-  check(ctx, cocg_bases_share(ctx, zk.owner, zk.l_query, &hd.l_query), "share l_query");
+  hd.a_query = hd.b_g1_query = hd.b_g2_query = hd.h_query = hd.l_query = 0;  // 0 = not resident on this rank (block mode)
+  if (zk.a_query) check(ctx, cocg_bases_share(ctx, zk.owner, zk.a_query, &hd.a_query), "share a_query");
+  if (zk.b_g1_query) check(ctx, cocg_bases_share(ctx, zk.owner, zk.b_g1_query, &hd.b_g1_query), "share b_g1_query");
+  if (zk.b_g2_query) check(ctx, cocg_bases_share(ctx, zk.owner, zk.b_g2_query, &hd.b_g2_query), "share b_g2_query");
+  if (zk.h_query) check(ctx, cocg_bases_share(ctx, zk.owner, zk.h_query, &hd.h_query), "share h_query");
+  if (zk.l_query) check(ctx, cocg_bases_share(ctx, zk.owner, zk.l_query, &hd.l_query), "share l_query");
   check(ctx, cocg_csr_share(ctx, zk.owner, zk.csr_a, &hd.csr_a), "share csr_a");
   check(ctx, cocg_csr_share(ctx, zk.owner, zk.csr_b, &hd.csr_b), "share csr_b");
 }
@@ -246,7 +252,20 @@ extern "C" int cohost_plain_prove(cohost_plain_session* s, const void* public_in
 }
 
 // ------------------------------------------------------------------------------------------------ REP3, three parties
+static int rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_comm_cb comm, void* comm_user, cohost_rep3_session** out);
 extern "C" int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds /* 3 x 32 */, int rank, int world, cohost_rep3_session** out) {
+  if (z && z->zk.blocks) return fail("cohost_rep3_session_create: the zkey was made for block mode; use cohost_rep3_session_create_blocks");
+  return rep3_session_create(z, seeds, rank, world, nullptr, nullptr, out);
+}
+// Block mode (types.hpp BlockPlan): `comm` carries the witness maps' mul_vec payloads between GPUs -- the caller issues the listed sends
+// and receives as ONE grouped NCCL call (ops[i].dptr are device buffers of this rank) and returns 0 when they have completed.
+extern "C" int cohost_rep3_session_create_blocks(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_comm_cb comm, void* user,
+                                                 cohost_rep3_session** out) {
+  if (!z || !z->zk.blocks) return fail("cohost_rep3_session_create_blocks: the zkey was not made with shard_mode = 1");
+  if (!comm) return fail("cohost_rep3_session_create_blocks: a transfer callback is required");
+  return rep3_session_create(z, seeds, rank, world, comm, user, out);
+}
+static int rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_comm_cb comm, void* comm_user, cohost_rep3_session** out) {
   if (!z || !out || !seeds) return fail("cohost_rep3_session_create: null argument");
   if (world < 1 || rank < 0 || rank >= world) return fail("cohost_rep3_session_create: bad rank/world");
   if (z->zk.world != 1 && (z->zk.world != world || z->zk.rank != rank)) return fail("cohost_rep3_session_create: the zkey holds another rank's shard");
@@ -261,11 +280,21 @@ extern "C" int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds /
       s->net->device_exchange = ex && std::string(ex) == "device";
     }
     for (int i = 0; i < 3; i++) s->drv[i].reset(new Rep3Protocol(z->zk.curve, z->device, s->net->party(i), seeds + 32 * i));
+    if (z->zk.blocks) {
+      static_assert(sizeof(CommOp) == sizeof(cohost_comm_op), "CommOp must mirror cohost_comm_op");
+      s->bridge.reset(new DeviceBridge(rank, z->zk.plan.wm, (CommCallback)comm, comm_user));
+      s->net->device_exchange = true;  // co-located witness maps hand their payloads over in HBM
+    }
     for (int i = 0; i < 3; i++) {
       s->drv[i]->finish_setup();
       s->prover[i].reset(new CoGroth16<Rep3Protocol>(*s->drv[i]));
       s->prover[i]->shard.rank = rank;
       s->prover[i]->shard.world = world;
+      if (z->zk.blocks) {
+        s->drv[i]->bridge = s->bridge.get();
+        s->prover[i]->blocks = &z->zk.plan;
+        s->prover[i]->block_rank = rank;
+      }
       share_handles(s->drv[i]->ctx, z->zk, s->hd[i]);
     }
     cohost_rep3_session* sp = s.get();
@@ -372,11 +401,15 @@ static int rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, c
         d.release(s->pub[i]);
         s->pub[i] = d.upload(public_inputs, zk.num_inputs());
         FieldShareVec wit;
+        bool need[2] = {true, true};  // block mode: only the components of this party that a block of this rank reads
+        if (zk.blocks)
+          for (int c = 0; c < 2; c++) need[c] = zk.plan.wm[i] == s->rank || zk.plan.g1[i][c] == s->rank || zk.plan.g2[i][c] == s->rank;
         if (wit_on_device) {  // borrowed: the caller keeps ownership
           wit.a = DevVec{const_cast<void*>(wit_a_i), zk.n_aux()};
           wit.b = DevVec{const_cast<void*>(wit_b_i), zk.n_aux()};
         } else {
-          wit = d.share_vec_from_host(wit_a_i, wit_b_i, zk.n_aux());
+          if (need[0]) wit.a = d.upload(wit_a_i, zk.n_aux());
+          if (need[1]) wit.b = d.upload(wit_b_i, zk.n_aux());
         }
         s->proofs[i] = s->prover[i]->prove(zk, s->hd[i], s->pub[i], pub_host, wit);
         if (!wit_on_device) d.release(wit);
@@ -385,6 +418,7 @@ static int rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, c
         s->errs[i] = e.what();
         s->drv[i]->injected = nullptr;
         s->net->close_all();  // unblock the peers (a dead party aborts the proof)
+        if (s->bridge) s->bridge->abort();
         {
           std::lock_guard<std::mutex> lk(s->mu);
           s->abort_wait = true;
@@ -497,6 +531,14 @@ extern "C" int cohost_rep3_profile_reset(cohost_rep3_session* s) {
   return 0;
 }
 
+extern "C" int cohost_block_plan(int world, int* out) {
+  if (world < 1 || !out) return fail("cohost_block_plan: bad argument");
+  BlockPlan p = BlockPlan::make(world);
+  for (int q = 0; q < 3; q++) out[q] = p.wm[q];
+  for (int q = 0; q < 3; q++)
+    for (int c = 0; c < 2; c++) { out[3 + 2 * q + c] = p.g1[q][c]; out[9 + 2 * q + c] = p.g2[q][c]; }
+  return 0;
+}
 // The index-range partition of an n-term MSM over `world` ranks (MsmShard::range); no GPU needed.
 extern "C" int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len) {
   if (!off || !len || world < 1 || rank < 0 || rank >= world) return fail("cohost_msm_shard_range: bad argument");
@@ -665,6 +707,31 @@ extern "C" int cohost_shamir_prove(cohost_shamir_session* s, const void* public_
 }
 
 // ------------------------------------------------------------------------------------------------ snarkjs files
+namespace {
+template <class CP>
+void check_vk_points_impl(const void* const* g1s, int n1, const void* const* g2s, int n2) {
+  using E = typename CP::E;
+  for (int i = 0; i < n1; i++) {
+    typename E::G1 p;
+    memcpy(&p, g1s[i], sizeof(p));
+    if (p.is_inf()) continue;
+    if (!on_curve(p, CP::b1()) || !scalar_mul_affine(p, CP::order()).is_inf()) throw Error("zkey: InvalidData: a verifying-key G1 point is not on the curve / in the subgroup");
+  }
+  for (int i = 0; i < n2; i++) {
+    typename E::G2 p;
+    memcpy(&p, g2s[i], sizeof(p));
+    if (p.is_inf()) continue;
+    if (!on_curve(p, CP::b2()) || !scalar_mul_affine(p, CP::order()).is_inf()) throw Error("zkey: InvalidData: a verifying-key G2 point is not on the curve / in the subgroup");
+  }
+}
+void check_vk_points(int curve, const void* a1, const void* b1, const void* d1, const void* b2, const void* d2) {
+  const void* g1s[3] = {a1, b1, d1};
+  const void* g2s[2] = {b2, d2};
+  if (curve == COCG_BN254) check_vk_points_impl<Bn254Pairing>(g1s, 3, g2s, 2);
+  else check_vk_points_impl<Bls381Pairing>(g1s, 3, g2s, 2);
+}
+}  // namespace
+
 // ZKey::from_reader (circom-types/src/groth16/zkey.rs:109, :139-251): parse a Groth16 .zkey image and make it resident in HBM.
 extern "C" int cohost_zkey_load(const void* data, size_t len, int device, cohost_zkey** out) {
   if (!data || !out) return fail("cohost_zkey_load: null argument");
@@ -685,6 +752,24 @@ extern "C" int cohost_zkey_load(const void* data, size_t len, int device, cohost
     d.a_query = f.a_query; d.b_g1_query = f.b_g1_query; d.b_g2_query = f.b_g2_query; d.h_query = f.h_query; d.l_query = f.l_query;
     d.alpha_g1 = f.alpha_g1; d.beta_g1 = f.beta_g1; d.delta_g1 = f.delta_g1; d.beta_g2 = f.beta_g2; d.delta_g2 = f.delta_g2;
     if (cohost_zkey_create(&d, out)) throw Error(cohost_last_error());
+    // g1_from_bytes / g2_from_bytes (circom-types/src/traits.rs:107-155) reject every point that is off the curve or outside the
+    // prime-order subgroup while parsing; here the query arrays are already in HBM and one kernel per query checks them
+    try {
+      const ZKey& zk = (*out)->zk;
+      const std::pair<const char*, uint64_t> qs[5] = {{"A", zk.a_query}, {"B1", zk.b_g1_query}, {"B2", zk.b_g2_query}, {"H", zk.h_query}, {"L", zk.l_query}};
+      for (const auto& q : qs) {
+        size_t bad = 0, first = 0;
+        check(zk.owner, cocg_bases_check(zk.owner, q.second, 1, &bad, &first), "cocg_bases_check");
+        if (bad)
+          throw Error(std::string("zkey: InvalidData: point ") + std::to_string(first) + " of section " + q.first + " is not on the curve or not in the "
+                      "prime-order subgroup (" + std::to_string(bad) + " such points)");
+      }
+      check_vk_points(f.curve, f.alpha_g1, f.beta_g1, f.delta_g1, f.beta_g2, f.delta_g2);
+    } catch (...) {
+      cohost_zkey_destroy(*out);
+      *out = nullptr;
+      throw;
+    }
   });
 }
 extern "C" int cohost_zkey_load_file(const char* path, int device, cohost_zkey** out) {
@@ -763,6 +848,12 @@ extern "C" int cohost_rep3_phase_times(cohost_rep3_session* s, double* out) {
 struct cohost_plonk_zkey {
   PlonkZKey zk;
   size_t lq = 4;
+  ~cohost_plonk_zkey() {  // also runs when loading fails half-way (a rejected point): nothing stays allocated on the device
+    if (zk.owner) {
+      for (void* p : zk.owned) cocg_free(zk.owner, p);
+      cocg_destroy(zk.owner);
+    }
+  }
 };
 
 namespace {
@@ -823,6 +914,11 @@ extern "C" int cohost_plonk_zkey_load_file(const char* path, int device, cohost_
     rd_map(f.map_c, zk.map_c);
     if (cocg_create(&zk.owner, device, f.curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
     check(zk.owner, cocg_bases_upload(zk.owner, COCG_G1, f.p_tau, f.domain_size + 6, 2 * f.n8q, 1, &zk.p_tau), "p_tau");
+    {  // taus() -> g1_vec_from_reader checks every point (plonk/zkey.rs:222-225, traits.rs:107-126)
+      size_t bad = 0, first = 0;
+      check(zk.owner, cocg_bases_check(zk.owner, zk.p_tau, 1, &bad, &first), "cocg_bases_check");
+      if (bad) throw Error("zkey: InvalidData: point " + std::to_string(first) + " of the p_tau section is not on the curve or not in the prime-order subgroup");
+    }
     plonk_upload_maps(zk);
     // rounds 2-5: selector / sigma / Lagrange polynomials (n coefficients | 4n evaluations each, Montgomery) and the vk tail
     if (f.k1 && f.sigma && f.lagrange && f.sel[0] && f.sel[1] && f.sel[2] && f.sel[3] && f.sel[4]) {
@@ -904,14 +1000,7 @@ extern "C" int cohost_plonk_zkey_create_synthetic(int curve, int device, size_t 
     *out = z.release();
   });
 }
-extern "C" void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z) {
-  if (!z) return;
-  if (z->zk.owner) {
-    for (void* p : z->zk.owned) cocg_free(z->zk.owner, p);
-    cocg_destroy(z->zk.owner);
-  }
-  delete z;
-}
+extern "C" void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z) { delete z; }
 // info[6] = curve, n_vars, n_public, domain_size, n_additions, n_constraints
 extern "C" int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info) {
   if (!z || !info) return fail("cohost_plonk_zkey_get_info: null argument");

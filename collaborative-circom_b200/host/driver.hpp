@@ -298,6 +298,7 @@ class Rep3Protocol : public DeviceDriver {
   void finish_setup() { net->recv_prev_bytes(seed2, 32); }  // split so three drivers can be built on one thread
 
   Rep3Network* net;
+  DeviceBridge* bridge = nullptr;  // block-mode multi-GPU: share vectors to / from parties whose witness map runs on another rank
   InjectedRandomness* injected = nullptr;
   uint8_t seed1[32], seed2[32];
   uint32_t ctr = 0;  // advanced in lock-step by the three parties (every consumer below is called by all of them)
@@ -356,7 +357,7 @@ class Rep3Protocol : public DeviceDriver {
   FieldShareVec mul_vec(const FieldShareVec& a, const FieldShareVec& b) {
     size_t n = a.len();
     if (b.len() != n) throw Error("mul_vec: length mismatch");
-    FieldShareVec o{alloc(n), alloc(n)};
+    FieldShareVec o{alloc(n), DevVec{}};
     if (injected && injected->i_vec < injected->mul_vec_masks.size()) {
       DevVec m = upload(injected->mul_vec_masks[injected->i_vec++], n);
       check(ctx, cocg_rep3_mul_local(ctx, a.a.p, a.b.p, b.a.p, b.b.p, m.p, o.a.p, n), "cocg_rep3_mul_local");
@@ -365,27 +366,7 @@ class Rep3Protocol : public DeviceDriver {
     } else {
       check(ctx, cocg_rep3_mul_local_prf(ctx, a.a.p, a.b.p, b.a.p, b.b.p, seed1, seed2, ctr++, o.a.p, n), "cocg_rep3_mul_local_prf");
     }
-    if (net->device_exchange()) {  // co-located parties on one GPU: hand a copy over in HBM, the receiver adopts it as its `b`
-      DevVec out_copy = alloc(n);
-      check(ctx, cocg_d2d(ctx, out_copy.p, o.a.p, n * 32), "cocg_d2d");
-      check(ctx, cocg_sync(ctx), "cocg_sync");
-      Message s;
-      s.bytes = n * 32;
-      s.device = out_copy.p;
-      net->send_next(std::move(s));
-      Message m = net->recv_prev();
-      if (m.bytes != n * 32 || !m.device) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
-      release(o.b);
-      o.b = DevVec{m.device, n};
-      return o;
-    }
-    std::shared_ptr<void> buf = pinned(n * 32);
-    check(ctx, cocg_d2h(ctx, buf.get(), o.a.p, n * 32), "cocg_d2h");
-    net->send_next(Message{buf, n * 32});
-    buf.reset();
-    Message m = net->recv_prev();
-    if (m.bytes != n * 32) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
-    check(ctx, cocg_h2d(ctx, o.b.p, m.data.get(), n * 32), "cocg_h2d");
+    o.b = exchange_next(o.a);  // send_next_many / recv_prev_many (in HBM, through pinned host memory, or across GPUs)
     return o;
   }
   void sub_assign_vec(FieldShareVec& a, const FieldShareVec& b) {  // rep3.rs:672-679
@@ -427,6 +408,18 @@ class Rep3Protocol : public DeviceDriver {
       memcpy(r[q].a.l, packed[q].data(), nl * 8);
       memcpy(r[q].b.l, packed[q].data() + nl, nl * 8);
     }
+    return r;
+  }
+  // one share component of several queries (block mode: the {l, a, b_g1} bundle or the b_g2 MSM of one component on this rank)
+  std::vector<Point> msm_public_points_multi_comp(const std::vector<int>& groups, const std::vector<uint64_t>& bases, const std::vector<size_t>& offs,
+                                                  size_t n, const FieldShareVec& scalars, int comp, size_t scalar_off = 0) {
+    const int nq = (int)bases.size();
+    std::vector<Point> r(nq);
+    std::vector<void*> outs(nq);
+    for (int q = 0; q < nq; q++) outs[q] = r[q].l;
+    const void* sc[1] = {comp == 0 ? scalars.a.at(scalar_off) : scalars.b.at(scalar_off)};
+    check(ctx, cocg_msm_multi(ctx, bases.data(), offs.data(), nq, n, sc, 1, 1, outs.data()), "cocg_msm_multi");
+    (void)groups;
     return r;
   }
   // ---- EcMpcProtocol (rep3.rs:769-862)
@@ -505,9 +498,40 @@ class Rep3Protocol : public DeviceDriver {
     ctr++;
     return o;
   }
+  // A mul_vec that another rank executes for this party (block mode): keep the PRF counter / injected masks in lock-step
+  void skip_mul_vec(int k) {
+    if (injected && injected->i_vec < injected->mul_vec_masks.size()) injected->i_vec += k;
+    else ctr += k;
+  }
   // send `local` to the next party, receive the previous party's vector of the same length (send_next_many / recv_prev_many)
   DevVec exchange_next(const DevVec& local) {
     const size_t n = local.n;
+    if (bridge && !(bridge->local((id() + 1) % 3) && bridge->local((id() + 2) % 3))) {
+      const int nxt = (id() + 1) % 3, prv = (id() + 2) % 3;
+      check(ctx, cocg_sync(ctx), "cocg_sync");  // the payload is complete before anyone reads it
+      if (bridge->local(nxt)) {  // the neighbour's witness map runs on this GPU: hand a copy over in HBM
+        DevVec copy = alloc(n);
+        check(ctx, cocg_d2d(ctx, copy.p, local.p, n * 32), "cocg_d2d");
+        check(ctx, cocg_sync(ctx), "cocg_sync");
+        Message s;
+        s.bytes = n * 32;
+        s.device = copy.p;
+        net->send_next(std::move(s));
+      } else {
+        bridge->post(CommOp{0, bridge->owner(nxt), local.p, n * 32});
+      }
+      DevVec r;
+      if (bridge->local(prv)) {
+        Message m = net->recv_prev();
+        if (m.bytes != n * 32 || !m.device) throw Error("During execution of mul_vec in MPC: Invalid number of elements received");
+        r = DevVec{m.device, n};
+      } else {
+        r = alloc(n);
+        bridge->post(CommOp{1, bridge->owner(prv), r.p, n * 32});
+      }
+      bridge->flush();
+      return r;
+    }
     if (net->device_exchange()) {
       DevVec copy = alloc(n);
       check(ctx, cocg_d2d(ctx, copy.p, local.p, n * 32), "cocg_d2d");

@@ -101,6 +101,9 @@ class CoGroth16 {
   T& driver;
   MsmShard shard;
   MsmCombine combine;
+  // block mode (types.hpp BlockPlan): this rank runs whole blocks of the proof instead of an index range of every MSM
+  const BlockPlan* blocks = nullptr;
+  int block_rank = 0;
   FieldShareVec last_h;  // kept for parity tests (released by the next prove)
   FieldShare last_r, last_s;
   // host wall-clock of the last prove per phase, seconds (the reference logs "Proof generation took {} ms", co-circom.rs:503-506;
@@ -118,7 +121,9 @@ class CoGroth16 {
                      const FieldShareVec& private_witness) {
     driver.release(last_h);
     const double t0 = now();
-    FieldShareVec h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
+    FieldShareVec h;
+    if (!blocks || blocks->wm[party_id()] == block_rank) h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
+    else skip_witness_map();  // another rank runs this party's witness map: stay in step with its randomness
     check(driver.ctx, cocg_sync(driver.ctx), "cocg_sync");
     phase_s[0] = now() - t0;
     FieldShare r = driver.rand();
@@ -183,6 +188,9 @@ class CoGroth16 {
     // ---- all secret-scalar MSMs first (msm_public_points at groth16.rs:248, 251-255 and inside calculate_coeff :221-225)
     MsmPartials m;
     size_t off, len;
+    if (blocks) {
+      block_msms(zkey, hd, h, aux_assignment, m);
+    } else {
     if (zkey.world != 1 && (zkey.world != shard.world || zkey.rank != shard.rank)) throw Error("the zkey holds another rank's shard of the queries");
     shard.range(std::min(h.len(), zkey.domain_size()), off, len);
     m.h_acc = driver.msm_public_points(1, hd.h_query, off - zkey.h_first, len, h, off);
@@ -195,6 +203,7 @@ class CoGroth16 {
       m.a_acc = r[1];
       m.b1_acc = r[2];
       m.b2_acc = r[3];
+    }
     }
     const double t_msm = now();
     phase_s[1] = t_msm - t_start;
@@ -235,6 +244,37 @@ class CoGroth16 {
   }
 
  private:
+  // ---- block mode helpers (REP3 only: the plan speaks of two share components)
+  template <class U = T>
+  auto skip_witness_map_impl(int) -> decltype(std::declval<U&>().skip_mul_vec(2)) { driver.skip_mul_vec(2); }
+  void skip_witness_map_impl(long) {}
+  void skip_witness_map() { skip_witness_map_impl(0); }
+  template <class U = T>
+  auto block_msms_impl(int, const ZKey& zkey, const Handles& hd, const FieldShareVec& h, const FieldShareVec& aux, MsmPartials& m)
+      -> decltype(std::declval<U&>().msm_public_points_multi_comp({}, {}, {}, 0, aux, 0), void()) {
+    const int p = party_id();
+    const size_t l = zkey.n_public, n_aux = zkey.n_aux();
+    const Point inf1 = driver.infinity(1), inf2 = driver.infinity(2);
+    m.h_acc = m.l_acc = m.a_acc = m.b1_acc = PointShare{inf1, inf1};
+    m.b2_acc = PointShare{inf2, inf2};
+    if (blocks->wm[p] == block_rank) m.h_acc = driver.msm_public_points(1, hd.h_query, 0, std::min(h.len(), zkey.domain_size()), h, 0);
+    for (int c = 0; c < 2; c++) {
+      if (blocks->g1[p][c] == block_rank) {  // l, a, b_g1 of one component: one digit sort
+        std::vector<Point> r = driver.msm_public_points_multi_comp({1, 1, 1}, {hd.l_query, hd.a_query, hd.b_g1_query}, {0, 1 + l, 1 + l}, n_aux, aux, c);
+        (c ? m.l_acc.b : m.l_acc.a) = r[0];
+        (c ? m.a_acc.b : m.a_acc.a) = r[1];
+        (c ? m.b1_acc.b : m.b1_acc.a) = r[2];
+      }
+      if (blocks->g2[p][c] == block_rank) {
+        std::vector<Point> r = driver.msm_public_points_multi_comp({2}, {hd.b_g2_query}, {1 + l}, n_aux, aux, c);
+        (c ? m.b2_acc.b : m.b2_acc.a) = r[0];
+      }
+    }
+  }
+  void block_msms_impl(long, const ZKey&, const Handles&, const FieldShareVec&, const FieldShareVec&, MsmPartials&) {
+    throw Error("block-mode multi-GPU proving is implemented for the REP3 driver");
+  }
+  void block_msms(const ZKey& zkey, const Handles& hd, const FieldShareVec& h, const FieldShareVec& aux, MsmPartials& m) { block_msms_impl(0, zkey, hd, h, aux, m); }
   template <class U = T>
   auto party_id_impl(int) -> decltype(std::declval<U&>().id()) { return driver.id(); }
   int party_id_impl(long) { return 0; }

@@ -12,6 +12,7 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "types.hpp"
 
@@ -79,6 +80,68 @@ class Rep3Network {
     if (m.bytes != n) throw Error("network: invalid number of bytes received");  // rep3.rs:663-668
     memcpy(p, m.data.get(), n);
   }
+};
+
+// Cross-GPU leg of the REP3 network (block mode, one process per GPU): the witness maps of the three parties run on different ranks,
+// so their mul_vec payloads travel GPU to GPU (NCCL send / recv over NVLink, issued by the caller's callback) instead of through the
+// in-process channels.  Party threads of one rank post their transfers of a round; the last one to arrive hands the whole batch to the
+// callback (one grouped NCCL call per rank and round, so sends and receives cannot deadlock) and releases the others.
+struct CommOp {
+  int dir;        // 0 = send, 1 = receive
+  int peer;       // rank
+  void* dptr;     // DEVICE buffer on this rank's GPU
+  size_t bytes;
+};
+typedef int (*CommCallback)(void* user, const CommOp* ops, int nops);
+class DeviceBridge {
+ public:
+  DeviceBridge(int rank, const int owner_of_party[3], CommCallback cb, void* user) : rank_(rank), cb_(cb), user_(user) {
+    for (int p = 0; p < 3; p++) owner_[p] = owner_of_party[p];
+    for (int p = 0; p < 3; p++)  // a party of this rank posts iff one of its ring neighbours lives elsewhere
+      if (owner_[p] == rank_ && (owner_[(p + 1) % 3] != rank_ || owner_[(p + 2) % 3] != rank_)) posters_++;
+  }
+  int rank() const { return rank_; }
+  int owner(int party) const { return owner_[party]; }
+  bool local(int party) const { return owner_[party] == rank_; }
+  void post(const CommOp& op) {
+    std::lock_guard<std::mutex> lk(mu_);
+    ops_.push_back(op);
+  }
+  // called once per round by every posting party thread
+  void flush() {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (failed_) throw Error("device bridge: an earlier transfer failed");
+    const uint64_t gen = gen_;
+    if (++arrived_ == posters_) {
+      int rc = cb_(user_, ops_.data(), (int)ops_.size());
+      ops_.clear();
+      arrived_ = 0;
+      gen_++;
+      if (rc) failed_ = true;
+      cv_.notify_all();
+      if (rc) throw Error("device bridge: the transfer callback failed");
+    } else {
+      cv_.wait(lk, [&] { return gen_ != gen || failed_; });
+      if (failed_) throw Error("device bridge: a transfer failed");
+    }
+  }
+  void abort() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      failed_ = true;
+    }
+    cv_.notify_all();
+  }
+
+ private:
+  int rank_, owner_[3], posters_ = 0, arrived_ = 0;
+  CommCallback cb_;
+  void* user_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::vector<CommOp> ops_;
+  uint64_t gen_ = 0;
+  bool failed_ = false;
 };
 
 class Rep3TestNetwork;

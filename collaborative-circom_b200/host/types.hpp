@@ -64,6 +64,50 @@ struct Domain {
   size_t size() const { return (size_t)1 << log_n; }
 };
 
+// Multi-GPU work distribution of one REP3 Groth16 proof by BLOCKS.  A proof is 15 blocks of nearly equal device time
+// (B200, 2^20 constraints: 9.8 / 9.1 / 8.8 ms): per party its witness map together with the two h-query MSMs; per (party, share
+// component) the {l, a, b_g1} MSMs, which share one digit sort; per (party, share component) the b_g2 MSM.  Every block runs at FULL
+// size on one rank -- the same kernels, window width and occupancy as the single-GPU proof -- instead of every MSM being cut into
+// `world` index ranges (smaller windows, more additions per scalar, launch-latency-bound reductions).  The partial results still meet in
+// one all-gather per proof.  The plan is a pure function of `world`, so all ranks agree on it without talking.
+struct BlockPlan {
+  int world = 1;
+  int wm[3] = {0, 0, 0};                 // rank of party p's witness map + h MSMs
+  int g1[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // rank of the {l, a, b_g1} bundle of (party, component)
+  int g2[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // rank of the b_g2 MSM of (party, component)
+  static BlockPlan make(int world) {
+    BlockPlan p;
+    p.world = world;
+    std::vector<double> load(world, 0.0);
+    auto place = [&](double cost) {
+      int best = 0;
+      for (int r = 1; r < world; r++)
+        if (load[r] < load[best] - 1e-9) best = r;
+      load[best] += cost;
+      return best;
+    };
+    for (int q = 0; q < 3; q++) p.wm[q] = place(9.8);
+    for (int q = 0; q < 3; q++)
+      for (int c = 0; c < 2; c++) p.g2[q][c] = place(8.8);
+    for (int q = 0; q < 3; q++)
+      for (int c = 0; c < 2; c++) p.g1[q][c] = place(9.1);
+    return p;
+  }
+  bool has_wm(int rank) const { return wm[0] == rank || wm[1] == rank || wm[2] == rank; }
+  bool has_g1(int rank) const {
+    for (int q = 0; q < 3; q++)
+      for (int c = 0; c < 2; c++)
+        if (g1[q][c] == rank) return true;
+    return false;
+  }
+  bool has_g2(int rank) const {
+    for (int q = 0; q < 3; q++)
+      for (int c = 0; c < 2; c++)
+        if (g2[q][c] == rank) return true;
+    return false;
+  }
+};
+
 // Device-resident proving key.  Query arrays live in HBM behind bases handles of `owner`; drivers alias them
 // (cocg_bases_share), as the reference's three in-process drivers borrow one &ZKey.
 struct ZKey {
@@ -81,6 +125,9 @@ struct ZKey {
   // the index, in the full query, of the resident table's entry 0 (0 when the whole query is resident).
   int rank = 0, world = 1;
   size_t a_first = 0, b_g1_first = 0, b_g2_first = 0, h_first = 0, l_first = 0;
+  // block mode (BlockPlan): whole queries are resident, but only those of the blocks this rank runs (handle 0 = not resident)
+  bool blocks = false;
+  BlockPlan plan;
   uint64_t csr_a = 0, csr_b = 0;
   // the first 1 + l points of each coefficient query stay on the host as well (calculate_coeff groth16.rs:219-231)
   std::vector<Point> a_head, b_g1_head, b_g2_head;  // packed affine

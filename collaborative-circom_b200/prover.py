@@ -28,7 +28,7 @@ HOST_SYMBOLS = [
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
     "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
-    "cohost_shamir_session_set_shard", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
+    "cohost_shamir_session_set_shard", "cohost_rep3_session_create_blocks", "cohost_block_plan", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
     "cohost_plonk_prove", "cohost_plonk_set_mpc_exchange", "cohost_plonk_launch_count", "cohost_plonk_profile_enable",
     "cohost_plonk_profile_reset", "cohost_plonk_profile_read", "cohost_plonk_round_times", "cohost_plonk_trace_enable",
     "cohost_plonk_trace_get", "cohost_plonk_proof_to_json",
@@ -43,7 +43,11 @@ class ZKeyDesc(ctypes.Structure):
                 ("a_rowptr", vp), ("a_col", vp), ("a_coeff", vp), ("a_nnz", sz),
                 ("b_rowptr", vp), ("b_col", vp), ("b_coeff", vp), ("b_nnz", sz),
                 ("a_query", vp), ("b_g1_query", vp), ("b_g2_query", vp), ("h_query", vp), ("l_query", vp),
-                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp), ("rank", ci), ("world", ci), ("coeff_form", ci)]
+                ("alpha_g1", vp), ("beta_g1", vp), ("delta_g1", vp), ("beta_g2", vp), ("delta_g2", vp), ("synthetic_seed", vp), ("rank", ci), ("world", ci), ("coeff_form", ci), ("shard_mode", ci)]
+
+
+class CommOp(ctypes.Structure):
+    _fields_ = [("dir", ci), ("peer", ci), ("dptr", vp), ("bytes", sz)]
 
 
 class ZKeyInfo(ctypes.Structure):
@@ -55,6 +59,7 @@ class Rep3Randomness(ctypes.Structure):
 
 
 GATHER_CB = ctypes.CFUNCTYPE(ci, vp, vp, sz, vp)
+COMM_CB = ctypes.CFUNCTYPE(ci, vp, ctypes.POINTER(CommOp), ci)
 
 _host = None
 
@@ -77,6 +82,8 @@ def load_host():
     L.cohost_plain_session_destroy.restype = None
     L.cohost_plain_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.cohost_rep3_session_create.argtypes = [vp, vp, ci, ci, pvp]
+    L.cohost_rep3_session_create_blocks.argtypes = [vp, vp, ci, ci, COMM_CB, vp, pvp]
+    L.cohost_block_plan.argtypes = [ci, ctypes.POINTER(ci)]
     L.cohost_rep3_session_destroy.argtypes = [vp]
     L.cohost_rep3_session_destroy.restype = None
     L.cohost_rep3_prove_begin.argtypes = [vp, vp, pvp, pvp, ctypes.POINTER(Rep3Randomness)]
@@ -260,6 +267,14 @@ def plonk_zkey_header(path: str) -> dict:
     return out
 
 
+def block_plan(world: int) -> dict:
+    """The block-mode work distribution for `world` ranks: {"wm": [3 ranks], "g1": [[a, b] x 3], "g2": [[a, b] x 3]}."""
+    out = (ci * 15)()
+    _ck(load_host().cohost_block_plan(world, out))
+    v = [int(x) for x in out]
+    return {"wm": v[:3], "g1": [v[3 + 2 * q:5 + 2 * q] for q in range(3)], "g2": [v[9 + 2 * q:11 + 2 * q] for q in range(3)]}
+
+
 def r1cs_info(path: str) -> dict:
     info = (sz * 6)()
     _ck(load_host().cohost_r1cs_info(path.encode(), info))
@@ -285,9 +300,12 @@ class Groth16ZKey:
     def __init__(self, curve: int, n_public: int, n_vars: int, pow_: int, num_constraints: int, a_csr, b_csr,
                  a_query=None, b_g1_query=None, b_g2_query=None, h_query=None, l_query=None, alpha_g1=None, beta_g1=None,
                  delta_g1=None, beta_g2=None, delta_g2=None, device: int = 0, synthetic_seed: bytes | None = None, rank: int = 0,
-                 world: int = 1):
-        """Query / vk arrays left as None are generated in HBM from `synthetic_seed` (32 bytes).  world > 1: only rank's
-        index-range shard of every query becomes resident (host arrays are still passed whole)."""
+                 world: int = 1, shard_mode: str = "ranges"):
+        """Query / vk arrays left as None are generated in HBM from `synthetic_seed` (32 bytes).  world > 1: only rank's part of the
+        queries becomes resident (host arrays are still passed whole): shard_mode "ranges" = its index range of every query,
+        "blocks" = the whole queries of the blocks of the proof it runs (REP3; see block_plan)."""
+        _need(shard_mode in ("ranges", "blocks"), "zkey: shard_mode must be ranges or blocks")
+        self.shard_mode = shard_mode if world > 1 else "ranges"
         L = load_host()
         self.curve, self.lq = curve, (4 if curve == _lib.BN254 else 6)
         self.n_public, self.n_vars, self.pow, self.num_constraints = n_public, n_vars, pow_, num_constraints
@@ -302,6 +320,7 @@ class Groth16ZKey:
         d = ZKeyDesc()
         d.curve, d.device, d.n_public, d.n_vars, d.pow, d.num_constraints = curve, device, n_public, n_vars, pow_, num_constraints
         d.rank, d.world = rank, world
+        d.shard_mode = 1 if shard_mode == "blocks" else 0
         d.a_rowptr, d.a_col, d.a_coeff, d.a_nnz = P(a_csr[0], np.uint32), P(a_csr[1], np.uint32), P(a_csr[2]), len(a_csr[1])
         d.b_rowptr, d.b_col, d.b_coeff, d.b_nnz = P(b_csr[0], np.uint32), P(b_csr[1], np.uint32), P(b_csr[2]), len(b_csr[1])
         _need(len(a_csr[0]) == num_constraints + 1 and len(b_csr[0]) == num_constraints + 1, "zkey: rowptr must hold num_constraints + 1 entries")
@@ -333,6 +352,7 @@ class Groth16ZKey:
         _ck(L.cohost_zkey_load_file(path.encode(), device, ctypes.byref(h)))
         self = cls.__new__(cls)
         self.h = h
+        self.shard_mode = "ranges"
         info = ZKeyInfo()
         _ck(L.cohost_zkey_get_info(h, ctypes.byref(info)))
         self.curve, self.lq = info.curve, (4 if info.curve == _lib.BN254 else 6)
@@ -411,8 +431,10 @@ class PlainSession:
 class Rep3Session:
     """Three CoGroth16<Rep3Protocol> provers on three threads over an in-process network (one GPU, or one MSM shard of `world`)."""
 
-    def __init__(self, zkey: Groth16ZKey, seeds: bytes | None = None, rank: int = 0, world: int = 1):
-        """seeds: 3 x 32 bytes, the parties' PRF seeds (Rep3Protocol::new draws them from entropy, rep3.rs:343-349).  Every mask and
+    def __init__(self, zkey: Groth16ZKey, seeds: bytes | None = None, rank: int = 0, world: int = 1, comm=None):
+        """comm (zkeys made with shard_mode="blocks" only): f(ops) performing the cross-GPU transfers of one mul_vec round, ops = list of
+        (dir, peer_rank, device_ptr, nbytes) with dir 0 = send / 1 = receive -- see distributed.make_p2p.
+        seeds: 3 x 32 bytes, the parties' PRF seeds (Rep3Protocol::new draws them from entropy, rep3.rs:343-349).  Every mask and
         the Groth16 blinders r, s derive from them, so the default is os.urandom; fixed seeds are for tests and the benchmark only.
         In a multi-GPU run every rank must pass the SAME seeds (the ranks replay the same three parties)."""
         seeds = os.urandom(96) if seeds is None else seeds
@@ -420,7 +442,23 @@ class Rep3Session:
         self.zkey, self.rank, self.world = zkey, rank, world
         self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
         h = vp()
-        _ck(load_host().cohost_rep3_session_create(zkey.h, self._seeds.ctypes.data, rank, world, ctypes.byref(h)))
+        self._comm_cb = None
+        if getattr(zkey, "shard_mode", "ranges") == "blocks":
+            _need(comm is not None, "Rep3Session: a block-mode zkey needs a comm function (distributed.make_p2p)")
+
+            def cb(_user, ops, nops):
+                try:
+                    comm([(ops[i].dir, ops[i].peer, ops[i].dptr, ops[i].bytes) for i in range(nops)])
+                    return 0
+                except Exception:  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+
+            self._comm_cb = COMM_CB(cb)
+            _ck(load_host().cohost_rep3_session_create_blocks(zkey.h, self._seeds.ctypes.data, rank, world, self._comm_cb, None, ctypes.byref(h)))
+        else:
+            _ck(load_host().cohost_rep3_session_create(zkey.h, self._seeds.ctypes.data, rank, world, ctypes.byref(h)))
         self.h = h
 
     def partial_bytes(self) -> int:

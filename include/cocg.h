@@ -125,6 +125,11 @@ COCG_API int cocg_ntt(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, c
  * mont = 1 if coordinates are Montgomery limbs, 0 if canonical. */
 COCG_API int cocg_bases_upload(cocg_ctx* ctx, int group, const void* pts, size_t n, size_t stride, int mont, uint64_t* handle);
 COCG_API int cocg_bases_free(cocg_ctx* ctx, uint64_t handle);
+/* Validates the resident points of `handle`: every point must satisfy the curve equation and, with check_subgroup != 0, lie in the
+ * prime-order subgroup ([r]P = O; (0, 0) = infinity passes).  Replaces the per-point `is_on_curve` / `is_in_correct_subgroup_assuming_
+ * on_curve` of the reference's zkey parser (circom-types/src/traits.rs:107-155, rayon loop :555-570).  *n_bad = number of offending
+ * points, *first_bad (may be NULL) = smallest offending index.  Synchronises. */
+COCG_API int cocg_bases_check(cocg_ctx* ctx, uint64_t handle, int check_subgroup, size_t* n_bad, size_t* first_bad);
 /* The window plan of the resident table built for a query of n points: signed digits of window_bits bits, `windows` of them per scalar
  * (= table rows = additions per scalar).  No GPU needed; bench.py reports the additions per MSM from it. */
 COCG_API int cocg_msm_plan(int curve, size_t n, int* window_bits, int* windows);

@@ -45,8 +45,10 @@ typedef struct cohost_zkey_desc {
   /* NULL, or 32 bytes: every query / vk pointer above that is NULL is filled with synthetic curve points generated in HBM
    * (cocg_bases_generate) -- the shape-faithful 2^20-constraint benchmark key, for which no zkey ships. */
   const void* synthetic_seed;
-  int rank, world;           /* world > 1: only this rank's index-range shard of every query becomes resident */
+  int rank, world;           /* world > 1: only this rank's part of the queries becomes resident */
   int coeff_form;            /* COCG_FORM_MONT (0, default) | COCG_FORM_R2 (as stored in a zkey) | COCG_FORM_CANONICAL */
+  int shard_mode;            /* world > 1: 0 = every MSM cut into `world` index ranges; 1 = whole blocks of the proof per rank (REP3):
+                                the witness map + h MSMs of a party, the {l, a, b_g1} MSMs or the b_g2 MSM of a (party, component) */
 } cohost_zkey_desc;
 
 typedef struct cohost_zkey_info {
@@ -90,6 +92,17 @@ COHOST_API int cohost_plain_prove(cohost_plain_session* s, const void* public_in
 /* Three CoGroth16<Rep3Protocol> provers.  seeds: 3 x 32 bytes (each party's PRF seed, rep3.rs:343-349).
  * rank/world: index-range sharding of every MSM over `world` GPUs (one process per GPU); world = 1 for a single GPU. */
 COHOST_API int cohost_rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_rep3_session** out);
+/* Block mode (zkey made with shard_mode = 1): a proof is 15 blocks of equal device time spread over the ranks; each block runs at full
+ * size with the single-GPU kernels.  The witness maps of the three parties then live on different GPUs and their two mul_vec payloads
+ * per proof travel GPU to GPU: `comm` receives the transfers of one round of this rank and must issue them as ONE grouped NCCL call
+ * (dir 0 = send, 1 = receive; dptr = device buffer of this rank) and return 0 once they have completed.  It is called from a party
+ * thread while the caller waits in cohost_rep3_prove_partials.  Partial sums still meet in one all-gather per proof (partials / combine). */
+typedef struct cohost_comm_op { int dir; int peer; void* dptr; size_t bytes; } cohost_comm_op;
+typedef int (*cohost_comm_cb)(void* user, const cohost_comm_op* ops, int nops);
+COHOST_API int cohost_rep3_session_create_blocks(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_comm_cb comm, void* user,
+                                                 cohost_rep3_session** out);
+/* The block plan for `world` ranks (no GPU needed): out[15] = wm[3] | g1[3][2] | g2[3][2] ranks. */
+COHOST_API int cohost_block_plan(int world, int* out);
 COHOST_API void cohost_rep3_session_destroy(cohost_rep3_session* s);
 /* One proof = begin [-> partials -> (caller all-gathers) -> combine] -> end.  wit_a[i] / wit_b[i]: party i's HOST share
  * components (m - l - 1 Fr each).  rnd: NULL for PRF-derived randomness. */

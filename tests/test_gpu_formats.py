@@ -94,3 +94,58 @@ def test_reader_rejects_malformed_files(cocg, tmp_path):
     # a plonk zkey (protocol id 2) is not a groth16 key
     with pytest.raises(cocg.CocgError, match="groth16"):
         cocg.Groth16ZKey.from_file(os.path.join(G, "plonk", "bn254", "multiplier2", "circuit.round1.zkey"))
+
+
+def test_zkey_load_rejects_points_off_curve_or_outside_the_subgroup(cocg, bn, bls, tmp_path):
+    """circom-types/src/traits.rs:107-155 (g1_from_bytes / g2_from_bytes): a point that is off the curve, or on it but outside the
+    prime-order subgroup, makes the parser fail.  Here the check is a kernel over the resident query (cocg_bases_check): the genuine
+    fixtures load, a corrupted coordinate is refused, and a curve point outside the subgroup is refused where a cofactor exists
+    (BLS12-381 G1: h = 0x396c8c005555e1568c00aaab0000aaab; BN254 G1 has cofactor 1)."""
+    from oracle import formats
+    for curve, c, ctx in (("bn254", BN254, bn), ("bls12_381", BLS12_381, bls)):
+        path = os.path.join(G, "groth16", curve, "multiplier2", "circuit.zkey")
+        raw = bytearray(open(path, "rb").read())
+        zk = cocg.Groth16ZKey.from_file(path)           # genuine file: accepted
+        zk.close()
+        ozk = formats.parse_groth16_zkey(bytes(raw))
+        # flip one byte inside the first point of the H section (section 9): almost surely off the curve
+        off = _section_offset(bytes(raw), 9)
+        bad = bytearray(raw)
+        bad[off + 3] ^= 0x55
+        p = tmp_path / f"bad_{curve}.zkey"
+        p.write_bytes(bytes(bad))
+        with pytest.raises(cocg.CocgError, match="InvalidData|not on the curve"):
+            cocg.Groth16ZKey.from_file(str(p))
+        # kernel-level: genuine points pass, a curve point of the wrong order fails where the group has a cofactor
+        pts = cref.g_to_mont(c, ozk.h_query, 1)
+        h = ctx.bases_upload(1, pts)
+        assert ctx.bases_check(h) == (0, None)
+        ctx.bases_free(h)
+        if c is BLS12_381:
+            x = 1
+            while True:  # a point of E(Fq) that is not in G1: take any curve point and keep it unless it happens to have order r
+                rhs = (x * x * x + 4) % c.q
+                y = pow(rhs, (c.q + 1) // 4, c.q)
+                if y * y % c.q == rhs and c.to_affine(c.jac_mul(c.to_jac((x, y), 1), c.r, 1), 1) is not None:  # (Curve.mul reduces the scalar mod r)
+                    break
+                x += 1
+            pts2 = pts.copy()
+            pts2[1] = cref.g_to_mont(c, [(x, y)], 1)[0]
+            h2 = ctx.bases_upload(1, pts2)
+            assert ctx.bases_check(h2, subgroup=True) == (1, 1)
+            assert ctx.bases_check(h2, subgroup=False) == (0, None)    # it IS on the curve
+            ctx.bases_free(h2)
+
+
+def _section_offset(data, want):
+    """byte offset of the payload of section `want` in a snarkjs binfile (circom-types/src/binfile.rs:52-105)"""
+    import struct
+    nsec = struct.unpack_from("<I", data, 8)[0]
+    off = 12
+    for _ in range(nsec):
+        sid, ln = struct.unpack_from("<IQ", data, off)
+        off += 12
+        if sid == want:
+            return off
+        off += ln
+    raise KeyError(want)
