@@ -14,6 +14,7 @@
 #include "serialize.hpp"
 #include "verify_json.hpp"
 #include "plonk_verify.hpp"
+#include "vm.hpp"
 
 using namespace cohost;
 
@@ -1190,6 +1191,114 @@ extern "C" int cohost_plonk_round1_rep3(cohost_plonk_zkey* z, const void* public
   cohost_plonk_session_destroy(s);
   if (rc) return rc;
   for (int i = 0; i < 3; i++) memcpy((uint64_t*)commits_out + (size_t)i * 6 * z->lq, pr.data() + (size_t)i * pl, 6 * z->lq * 8);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ batched witness-extension arithmetic
+struct cohost_vm {
+  int parties = 1;
+  size_t batch = 0;
+  std::unique_ptr<PlainDriver> plain;
+  std::unique_ptr<Rep3TestNetwork> net;
+  std::unique_ptr<Rep3Protocol> drv[3];
+  std::unique_ptr<BatchedWitnessVm<PlainDriver>> vm_plain;
+  std::unique_ptr<BatchedWitnessVm<Rep3Protocol>> vm_rep3[3];
+  bool failed = false;
+};
+extern "C" int cohost_vm_create(int curve, int device, int protocol, const uint8_t* seeds, size_t batch, int n_regs, cohost_vm** out) {
+  if (!out || !seeds) return fail("cohost_vm_create: null argument");
+  if (protocol != 0 && protocol != 1) return fail("cohost_vm_create: protocol must be 0 (plain) or 1 (REP3)");
+  if (n_regs <= 0 || n_regs > 65536) return fail("cohost_vm_create: bad register count");
+  *out = nullptr;
+  return guarded([&] {
+    std::unique_ptr<cohost_vm> v(new cohost_vm());
+    v->parties = protocol == 0 ? 1 : 3;
+    v->batch = batch;
+    if (protocol == 0) {
+      v->plain.reset(new PlainDriver(curve, device));
+      memcpy(v->plain->seed, seeds, 32);
+      v->vm_plain.reset(new BatchedWitnessVm<PlainDriver>(*v->plain, batch, n_regs));
+    } else {
+      v->net.reset(new Rep3TestNetwork());
+      v->net->device_exchange = true;  // the three parties of this process share the GPU
+      for (int i = 0; i < 3; i++) v->drv[i].reset(new Rep3Protocol(curve, device, v->net->party(i), seeds + 32 * i));
+      for (int i = 0; i < 3; i++) {
+        v->drv[i]->finish_setup();
+        v->vm_rep3[i].reset(new BatchedWitnessVm<Rep3Protocol>(*v->drv[i], batch, n_regs));
+      }
+    }
+    *out = v.release();
+  });
+}
+extern "C" void cohost_vm_destroy(cohost_vm* v) {
+  if (!v) return;
+  v->vm_plain.reset();
+  for (auto& m : v->vm_rep3) m.reset();  // registers go back to the drivers' pools before the drivers die
+  delete v;
+}
+extern "C" int cohost_vm_set_public(cohost_vm* v, int reg, const void* values) {
+  if (!v || !values) return fail("cohost_vm_set_public: null argument");
+  return guarded([&] {
+    if (v->parties == 1) v->vm_plain->set_public(reg, values);
+    else for (int i = 0; i < 3; i++) v->vm_rep3[i]->set_public(reg, values);
+  });
+}
+extern "C" int cohost_vm_set_shared(cohost_vm* v, int reg, int party, const void* a, const void* b) {
+  if (!v || !a || party < 0 || party >= v->parties || (v->parties == 3 && !b)) return fail("cohost_vm_set_shared: bad argument");
+  return guarded([&] {
+    if (v->parties == 1) v->vm_plain->set_shared(reg, a, nullptr);
+    else v->vm_rep3[party]->set_shared(reg, a, b);
+  });
+}
+extern "C" int cohost_vm_run(cohost_vm* v, const cohost_vm_instr* prog, size_t n) {
+  if (!v || (n && !prog)) return fail("cohost_vm_run: null argument");
+  if (v->failed) return fail("cohost_vm_run: the network is closed after an earlier failure");
+  static_assert(sizeof(cohost_vm_instr) == sizeof(VmInstr), "cohost_vm_instr must mirror VmInstr");
+  const VmInstr* p = reinterpret_cast<const VmInstr*>(prog);
+  return guarded([&] {
+    if (v->parties == 1) { v->vm_plain->run(p, n); return; }
+    std::thread th[3];
+    std::string errs[3];
+    for (int i = 0; i < 3; i++)
+      th[i] = std::thread([&, i] {
+        try {
+          v->vm_rep3[i]->run(p, n);
+        } catch (const std::exception& e) {
+          errs[i] = e.what();
+          v->net->close_all();
+        }
+      });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < 3; i++)
+      if (!errs[i].empty()) {
+        v->failed = true;
+        throw Error("party " + std::to_string(i) + ": " + errs[i]);
+      }
+  });
+}
+// kind: 1 public (a_out receives the values, b_out untouched), 2 shared (a_out | b_out: the party's components; b_out unused by plain)
+extern "C" int cohost_vm_get(cohost_vm* v, int reg, int party, int* kind, void* a_out, void* b_out) {
+  if (!v || !kind || party < 0 || party >= v->parties) return fail("cohost_vm_get: bad argument");
+  return guarded([&] {
+    auto get = [&](auto& vm) {
+      VmValue& val = vm.at(reg);
+      *kind = (int)val.kind;
+      if (val.kind == VmValue::PUBLIC && a_out) vm.driver.download(val.pub, a_out);
+      if (val.kind == VmValue::SHARED) {
+        if (a_out) vm.driver.download(val.sh.a, a_out);
+        if (b_out && val.sh.b.p) vm.driver.download(val.sh.b, b_out);
+      }
+    };
+    if (v->parties == 1) get(*v->vm_plain);
+    else get(*v->vm_rep3[party]);
+  });
+}
+// out[0] = kernel launches, out[1] = network rounds of party 0 (shared multiplications and inversions: ONE exchange each per batch)
+extern "C" int cohost_vm_stats(cohost_vm* v, uint64_t* out) {
+  if (!v || !out) return fail("cohost_vm_stats: null argument");
+  out[0] = 0;
+  if (v->parties == 1) { out[0] = cocg_launch_count(v->plain->ctx); out[1] = v->vm_plain->network_rounds; }
+  else { for (int i = 0; i < 3; i++) out[0] += cocg_launch_count(v->drv[i]->ctx); out[1] = v->vm_rep3[0]->network_rounds; }
   return 0;
 }
 

@@ -28,6 +28,7 @@ HOST_SYMBOLS = [
     "cohost_proof_to_json", "cohost_public_inputs_to_json", "cohost_shared_witness_encode", "cohost_shared_witness_decode",
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
     "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
+    "cohost_vm_create", "cohost_vm_destroy", "cohost_vm_set_public", "cohost_vm_set_shared", "cohost_vm_run", "cohost_vm_get", "cohost_vm_stats",
     "cohost_shamir_session_set_shard", "cohost_rep3_session_create_blocks", "cohost_block_plan", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
     "cohost_plonk_prove", "cohost_plonk_set_mpc_exchange", "cohost_plonk_launch_count", "cohost_plonk_profile_enable",
     "cohost_plonk_profile_reset", "cohost_plonk_profile_read", "cohost_plonk_round_times", "cohost_plonk_trace_enable",
@@ -82,6 +83,14 @@ def load_host():
     L.cohost_plain_session_destroy.restype = None
     L.cohost_plain_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.cohost_rep3_session_create.argtypes = [vp, vp, ci, ci, pvp]
+    L.cohost_vm_create.argtypes = [ci, ci, ci, vp, sz, ci, pvp]
+    L.cohost_vm_destroy.argtypes = [vp]
+    L.cohost_vm_destroy.restype = None
+    L.cohost_vm_set_public.argtypes = [vp, ci, vp]
+    L.cohost_vm_set_shared.argtypes = [vp, ci, ci, vp, vp]
+    L.cohost_vm_run.argtypes = [vp, vp, sz]
+    L.cohost_vm_get.argtypes = [vp, ci, ci, ctypes.POINTER(ci), vp, vp]
+    L.cohost_vm_stats.argtypes = [vp, ctypes.POINTER(u64)]
     L.cohost_rep3_session_create_blocks.argtypes = [vp, vp, ci, ci, COMM_CB, vp, pvp]
     L.cohost_block_plan.argtypes = [ci, ctypes.POINTER(ci)]
     L.cohost_rep3_session_destroy.argtypes = [vp]
@@ -753,4 +762,59 @@ class PlonkSession:
     def close(self):
         if self.h:
             load_host().cohost_plonk_session_destroy(self.h)
+            self.h = None
+
+
+VM_ADD, VM_SUB, VM_MUL, VM_NEG, VM_DIV = range(5)
+
+
+class BatchedVm:
+    """The field opcodes of the MPC witness-extension VM over a batch of independent inputs (host/vm.hpp)."""
+
+    def __init__(self, curve: int, protocol: str, batch: int, n_regs: int, seeds: bytes | None = None, device: int = 0):
+        _need(protocol in ("plain", "rep3"), "BatchedVm: protocol must be plain or rep3")
+        self.parties = 1 if protocol == "plain" else 3
+        self.batch = batch
+        seeds = os.urandom(32 * self.parties) if seeds is None else seeds
+        _need(len(seeds) == 32 * self.parties, "BatchedVm: seeds must be 32 bytes per party")
+        sd = np.frombuffer(seeds, dtype=np.uint8).copy()
+        h = vp()
+        _ck(load_host().cohost_vm_create(curve, device, 0 if protocol == "plain" else 1, sd.ctypes.data, batch, n_regs, ctypes.byref(h)))
+        self.h = h
+
+    def set_public(self, reg: int, values):
+        v = _c(values)
+        _need(v.size == 4 * self.batch, "set_public: one value per instance")
+        _ck(load_host().cohost_vm_set_public(self.h, reg, v.ctypes.data))
+
+    def set_shared(self, reg: int, party: int, a, b=None):
+        a = _c(a)
+        b = None if b is None else _c(b)
+        _need(a.size == 4 * self.batch and (b is None or b.size == 4 * self.batch), "set_shared: one share per instance")
+        _ck(load_host().cohost_vm_set_shared(self.h, reg, party, a.ctypes.data, None if b is None else b.ctypes.data))
+
+    def run(self, program):
+        """program: iterable of (op, dst, lhs, rhs)"""
+        prog = np.ascontiguousarray(np.array(list(program), dtype=np.int32).reshape(-1, 4))
+        _ck(load_host().cohost_vm_run(self.h, prog.ctypes.data, prog.shape[0]))
+
+    def get(self, reg: int, party: int = 0):
+        """-> ("public", values) or ("shared", a, b)"""
+        kind = ci(0)
+        a = np.zeros((self.batch, 4), dtype=np.uint64)
+        b = np.zeros((self.batch, 4), dtype=np.uint64)
+        _ck(load_host().cohost_vm_get(self.h, reg, party, ctypes.byref(kind), a.ctypes.data, b.ctypes.data))
+        if kind.value == 1:
+            return ("public", a)
+        _need(kind.value == 2, "get: empty register")
+        return ("shared", a, b)
+
+    def stats(self) -> dict:
+        out = (u64 * 2)()
+        _ck(load_host().cohost_vm_stats(self.h, out))
+        return {"launches": int(out[0]), "network_rounds": int(out[1])}
+
+    def close(self):
+        if self.h:
+            load_host().cohost_vm_destroy(self.h)
             self.h = None

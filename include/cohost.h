@@ -218,6 +218,23 @@ COHOST_API int cohost_plonk_verify_json(const char* vk_json, size_t vk_len, cons
  * tail, 2 = selector sections, 4 = sigma, 8 = Lagrange); k1k2: 2 Montgomery Fr; vk_g1: Qm Ql Qr Qo Qc S1 S2 S3 packed affine Montgomery;
  * x_2: G2 (circom-types/src/plonk/zkey.rs:329-420).  Output pointers may be NULL. */
 COHOST_API int cohost_plonk_zkey_header(const char* path, size_t* info, void* k1k2, void* vk_g1, void* x_2);
+/* Batched witness-extension arithmetic: the field opcodes of the reference's MPC VM (circom-mpc-vm/src/mpc_vm.rs:508-546:
+ * Add Sub Mul Neg Div, dispatched as Rep3VmType::{add, sub, mul, neg, div}, mpc-core/src/protocols/rep3/witness_extension_impl.rs:81-200)
+ * as SIMD over a batch of `batch` independent inputs of one circuit: every register holds `batch` Fr elements in HBM, public or
+ * secret-shared; one opcode = one kernel over the batch; a shared multiplication / inversion = ONE network round for the whole batch.
+ * protocol 0 = plain (seeds: 32 bytes), 1 = three REP3 parties on three threads (seeds: 3 x 32 bytes).  A straight-line program over
+ * registers stands in for the circom bytecode (no circom front end exists here). */
+typedef struct cohost_vm cohost_vm;
+typedef struct cohost_vm_instr { int op; int dst; int lhs; int rhs; } cohost_vm_instr;  /* op: 0 Add 1 Sub 2 Mul 3 Neg 4 Div */
+COHOST_API int cohost_vm_create(int curve, int device, int protocol, const uint8_t* seeds, size_t batch, int n_regs, cohost_vm** out);
+COHOST_API void cohost_vm_destroy(cohost_vm* v);
+COHOST_API int cohost_vm_set_public(cohost_vm* v, int reg, const void* values);                            /* batch Montgomery Fr */
+COHOST_API int cohost_vm_set_shared(cohost_vm* v, int reg, int party, const void* a, const void* b);       /* the party's components */
+COHOST_API int cohost_vm_run(cohost_vm* v, const cohost_vm_instr* prog, size_t n);
+/* *kind: 1 public (a_out), 2 shared (a_out | b_out = the party's components) */
+COHOST_API int cohost_vm_get(cohost_vm* v, int reg, int party, int* kind, void* a_out, void* b_out);
+/* out[0] = kernel launches so far, out[1] = network rounds so far */
+COHOST_API int cohost_vm_stats(cohost_vm* v, uint64_t* out);
 /* (offset, length) of the slice of an n-term MSM that `rank` of `world` accumulates (index-range sharding; needs no GPU). */
 COHOST_API int cohost_msm_shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 
