@@ -123,3 +123,26 @@ def test_cli_rejects_bad_arguments(cocg, tmp_path):
     with pytest.raises(SystemExit, match="does not exist"):
         cli.main(["split-witness", "--witness", os.path.join(d, "witness.wtns"), "--r1cs", os.path.join(d, "circuit.r1cs"), "--protocol", "REP3",
                   "--curve", "BN254", "--out-dir", str(tmp_path / "nope")])
+
+
+def test_plonk_files_to_verified_proof(cocg, tmp_path):
+    """`generate-proof plonk` (co-circom.rs:455-636 with the Plonk proof system): witness.wtns -> three REP3 share files -> CoPlonk::prove
+    on the GPU -> proof.json accepted by `verify plonk` with the fixture's snarkjs verification key; a changed public input is rejected."""
+    d = os.path.join(G, "plonk", "bn254", "multiplier2")
+    r1cs = os.path.join(G, "groth16", "bn254", "multiplier2", "circuit.r1cs")   # the same circuit; only its input counts are read
+    cli = _cli()
+    cli.main(["split-witness", "--witness", os.path.join(d, "witness.wtns"), "--r1cs", r1cs, "--protocol", "REP3", "--curve", "BN254",
+              "--out-dir", str(tmp_path)])
+    shares = [str(tmp_path / f"witness.wtns.{i}.shared") for i in range(3)]
+    out, pub_out = str(tmp_path / "proof.json"), str(tmp_path / "public.json")
+    cli.main(["generate-proof", "plonk", "--witness", *shares, "--zkey", os.path.join(d, "circuit.zkey"), "--protocol", "REP3", "--curve", "BN254",
+              "--out", out, "--public-input", pub_out])
+    assert json.load(open(pub_out)) == json.load(open(os.path.join(d, "public.json")))
+    assert json.load(open(out))["protocol"] == "plonk"
+    cli.main(["verify", "plonk", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", pub_out, "--curve", "BN254"])
+    public = json.load(open(pub_out))
+    bad_pub = str(tmp_path / "bad_public.json")
+    json.dump([str(int(public[0]) + 1)] + public[1:], open(bad_pub, "w"))
+    with pytest.raises(SystemExit) as e:
+        cli.main(["verify", "plonk", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", bad_pub, "--curve", "BN254"])
+    assert e.value.code == 1

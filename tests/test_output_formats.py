@@ -148,3 +148,32 @@ def test_plonk_zkey_header_reader_agrees_with_verification_key_json(cocg, curve)
     if curve == "bn254":
         t = cocg.plonk_zkey_header(os.path.join(d, "circuit.round1.zkey"))
         assert t["parts"] & 14 == 0 and t["n_constraints"] == h["n_constraints"]
+
+
+def test_shared_witness_bytes_hand_derived(cocg):
+    """A `.shared` file image derived BY HAND from the reference's code, as a literal -- not produced by any encoder:
+
+    * co-circom-snarks/src/lib.rs:24-41: `SharedWitness { public_inputs: Vec<F>, witness: FieldShareVec }`, both fields with
+      `serialize_with = ark_se`; files are written with `bincode::serialize_into(out_file, share)` (co-circom/src/bin/co-circom.rs:215, 244).
+    * serde_compat.rs:5-13 (ark_se): `a.serialize_with_mode(&mut bytes, Compress::Yes)` then `s.serialize_bytes(&bytes)`.
+    * bincode 1.x default options: fixed-width little-endian integers; a struct is its fields in order with no framing;
+      `serialize_bytes` = u64 length, then the bytes.
+    * ark-serialize 0.4: `Vec<T>` = u64 length (LE) then the elements; a prime-field element of a 254 / 255-bit modulus = 32 bytes,
+      little-endian, canonical (non-Montgomery) value; `#[derive(CanonicalSerialize)]` on `Rep3PrimeFieldShareVec { a, b }`
+      (mpc-core/src/protocols/rep3/fieldshare.rs:231-236) = a then b.
+
+    public_inputs = [1, 5], witness a = [7], b = [9] (BN254):
+      field 1: u64 72 | [u64 2 | 1 as 32 LE bytes | 5 as 32 LE bytes]                          (8 + 72 bytes)
+      field 2: u64 80 | [u64 1 | 7 as 32 LE bytes | u64 1 | 9 as 32 LE bytes]                   (8 + 80 bytes)"""
+    le32 = lambda v: "%02x" % v + "00" * 31
+    u64 = lambda v: "%02x" % v + "00" * 7
+    literal = bytes.fromhex(u64(72) + u64(2) + le32(1) + le32(5) + u64(80) + u64(1) + le32(7) + u64(1) + le32(9))
+    assert len(literal) == 168
+    c = BN254
+    img = cocg.shared_witness_encode(cocg.BN254, cref.fr_to_mont(c, [1, 5]), [cref.fr_to_mont(c, [7]), cref.fr_to_mont(c, [9])])
+    assert img == literal
+    pub, comps = cocg.shared_witness_decode(cocg.BN254, literal, 2)
+    assert cref.fr_from_mont(c, pub) == [1, 5] and cref.fr_from_mont(c, comps[0]) == [7] and cref.fr_from_mont(c, comps[1]) == [9]
+    # Shamir: ShamirPrimeFieldShareVec { a } (shamir/fieldshare.rs:152-155) -- one vector
+    literal_shamir = bytes.fromhex(u64(72) + u64(2) + le32(1) + le32(5) + u64(40) + u64(1) + le32(7))
+    assert cocg.shared_witness_encode(cocg.BN254, cref.fr_to_mont(c, [1, 5]), [cref.fr_to_mont(c, [7])]) == literal_shamir

@@ -4,8 +4,8 @@ sub-commands and flag names as /root/reference/co-circom/co-circom/src/lib.rs:10
 
   split-witness   --witness W.wtns --r1cs C.r1cs --protocol REP3|SHAMIR --curve BN254|BLS12-381 --out-dir DIR [-t T] [-n N]
                   -> DIR/<W>.<i>.shared                                   (co-circom.rs:160-256)
-  generate-proof  groth16 --witness S0.shared S1.shared S2.shared [...] --zkey K.zkey --protocol REP3|SHAMIR [-t T] --curve ...
-                  --out proof.json [--public-input public.json]             (co-circom.rs:455-636)
+  generate-proof  groth16|plonk --witness S0.shared S1.shared S2.shared [...] --zkey K.zkey --protocol REP3|SHAMIR [-t T] --curve ...
+                  --out proof.json [--public-input public.json]             (co-circom.rs:455-636; plonk: REP3)
   verify          groth16|plonk --proof proof.json --vk verification_key.json --public-input public.json --curve ...
                   exit code 0 = accepted, 1 = rejected                      (co-circom.rs:640-720; host pairing, no GPU)
 
@@ -32,9 +32,43 @@ def split_witness(a):
         print(f"Wrote witness share {i} to file {p}")
 
 
+def generate_proof_plonk(a):
+    """CoPlonk::prove over three REP3 parties (co-circom.rs:455-636 with proof system plonk)."""
+    if a.protocol != "REP3" or len(a.witness) != 3:
+        sys.exit("plonk: REP3 with the three parties' share files (one process plays all three parties)")
+    curve = CURVES[a.curve]
+    zk = cocg.PlonkZKey(a.zkey)
+    pubs, wa, wb = [], [], []
+    for path in a.witness:
+        pub, comps = cocg.shared_witness_decode(curve, open(path, "rb").read(), 2)
+        pubs.append(pub)
+        wa.append(comps[0])
+        wb.append(comps[1])
+    if any(p.shape != pubs[0].shape or not (p == pubs[0]).all() for p in pubs[1:]):
+        sys.exit("the share files disagree on the public inputs")
+    # a SharedWitness of the Groth16 flow carries every signal after the public ones; the Plonk prover reads the first
+    # n_vars - n_additions - n_public - 1 of them (the additions are recomputed, round1.rs:213-242)
+    need = zk.n_witness
+    if any(x.shape[0] < need for x in wa + wb):
+        sys.exit("the share files hold fewer witness elements than the zkey expects")
+    sess = cocg.PlonkSession(zk, "rep3", seeds=os.urandom(96))
+    proofs = sess.prove(pubs[0], [x[:need] for x in wa], [x[:need] for x in wb])
+    if any(not (p == proofs[0]).all() for p in proofs[1:]):
+        sys.exit("the parties opened different proofs")
+    with open(a.out, "w") as f:
+        f.write(cocg.plonk_proof_to_json(curve, proofs[0]))
+    print(f"Wrote proof to file {a.out}")
+    if a.public_input:
+        with open(a.public_input, "w") as f:
+            f.write(cocg.public_inputs_to_json(curve, pubs[0]))
+        print(f"Wrote public inputs to file {a.public_input}")
+    sess.close()
+    zk.close()
+
+
 def generate_proof(a):
-    if a.proof_system != "groth16":
-        sys.exit("only groth16 is built (CoPlonk: round 1 only, see DESIGN.md)")
+    if a.proof_system == "plonk":
+        return generate_proof_plonk(a)
     rep3 = a.protocol == "REP3"
     if rep3 and len(a.witness) != 3:
         sys.exit("REP3 needs the three parties' share files (one process plays all three parties)")
