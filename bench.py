@@ -92,7 +92,7 @@ class ClockSampler:
 def ncu_traffic(world):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (msm_accumulate_kernel, weighted 4 G1 : 1 G2
     like the launches of one share component) from the committed `ncu --set full` capture summary, single-GPU shape only."""
-    p = os.path.join(ROOT, "profiles", "r01_msm_accumulate_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_msm_accumulate_traffic.json")
     if world != 1 or not os.path.exists(p):
         return None
     t = json.load(open(p))

@@ -1,27 +1,26 @@
 #!/usr/bin/env python3
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel: launches, total, share, average."""
-import collections
+"""Condense `ncu -i X.ncu-rep --page raw --csv` into one JSON line per captured launch with the metrics DESIGN.md cites."""
 import csv
-import re
+import json
 import sys
 
-
-def main(path):
-    lines = [l for l in open(path) if not l.startswith("==")]
-    agg = collections.defaultdict(lambda: [0, 0.0])
-    for r in csv.DictReader(lines):
-        name = re.sub(r"^void ", "", r["Kernel Name"])
-        name = re.sub(r"\(.*", "", name)
-        v = float(r["Metric Value"].replace(",", ""))
-        v *= {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}[r["Metric Unit"]]
-        agg[name][0] += 1
-        agg[name][1] += v
-    tot = sum(v[1] for v in agg.values())
-    print(f"{'kernel':70s} {'n':>5s} {'total ms':>10s} {'share':>7s} {'avg us':>10s}")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{k[:70]:70s} {v[0]:5d} {v[1] / 1e6:10.3f} {100 * v[1] / tot:6.1f}% {v[1] / v[0] / 1e3:10.1f}")
-    print(f"{'total':70s} {sum(v[0] for v in agg.values()):5d} {tot / 1e6:10.3f}")
-
-
-if __name__ == "__main__":
-    main(sys.argv[1])
+KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "sm__icc_requests_lookup_hit.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "local_load_bytes", "smsp__cycles_active.avg"]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+names, units = rows[hdr], rows[hdr + 1]
+for r in rows[hdr + 2:]:
+    if len(r) != len(names):
+        continue
+    d = {"kernel": r[names.index("Kernel Name")][:90]}
+    for k in KEEP:
+        if k in names:
+            j = names.index(k)
+            d[k + (" [" + units[j] + "]" if units[j] else "")] = r[j]
+    print(json.dumps(d))
