@@ -647,6 +647,12 @@ extern "C" int cohost_shamir_session_set_shard(cohost_shamir_session* s, int ran
   }
   return 0;
 }
+// 0 = share vectors staged through pinned host memory (default), 1 = handed over in HBM (the parties share the session's GPU)
+extern "C" int cohost_shamir_set_mpc_exchange(cohost_shamir_session* s, int device) {
+  if (!s) return fail("cohost_shamir_set_mpc_exchange: null session");
+  s->net->device_exchange = device != 0;
+  return 0;
+}
 extern "C" void cohost_shamir_session_destroy(cohost_shamir_session* s) {
   if (!s) return;
   for (size_t i = 0; i < s->drv.size(); i++) s->drv[i]->release(s->prover[i]->last_h);

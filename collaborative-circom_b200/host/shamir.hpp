@@ -23,6 +23,9 @@ class ShamirNetwork {  // shamir/network.rs:14-59
   virtual int get_num_parties() const = 0;
   virtual void send(int target, Message m) = 0;
   virtual Message recv(int from) = 0;
+  // true when all parties live in one process on ONE GPU and the caller opted in: share vectors are then handed over as HBM buffers
+  // instead of being staged through pinned host memory (the default: what a party that has to reach a NIC does)
+  virtual bool device_exchange() const { return false; }
   void send_bytes(int target, const void* p, size_t n) {
     std::shared_ptr<void> buf(new uint8_t[n ? n : 1], [](void* q) { delete[] (uint8_t*)q; });
     memcpy(buf.get(), p, n);
@@ -52,6 +55,7 @@ class ShamirPartyTestNetwork : public ShamirNetwork {
   int get_num_parties() const override { return n_; }
   void send(int target, Message m) override;
   Message recv(int from) override;
+  bool device_exchange() const override;
 
  private:
   ShamirTestNetwork* net_;
@@ -65,6 +69,7 @@ class ShamirTestNetwork {
   ShamirPartyTestNetwork* party(int i) { return parties_[i].get(); }
   Channel& chan(int from, int to) { return ch_[(size_t)from * n_ + to]; }
   void close_all() { for (auto& c : ch_) c.close(); }
+  bool device_exchange = false;
 
  private:
   int n_;
@@ -73,6 +78,7 @@ class ShamirTestNetwork {
 };
 inline void ShamirPartyTestNetwork::send(int target, Message m) { net_->chan(id_, target).send(std::move(m)); }
 inline Message ShamirPartyTestNetwork::recv(int from) { return net_->chan(from, id_).recv(); }
+inline bool ShamirPartyTestNetwork::device_exchange() const { return net_->device_exchange; }
 
 class ShamirProtocol : public DeviceDriver {
  public:
@@ -144,6 +150,16 @@ class ShamirProtocol : public DeviceDriver {
     return out;
   }
   void send_vec(int target, const DevVec& v) {
+    if (net->device_exchange()) {  // co-located parties: the receiver adopts a copy in HBM
+      DevVec copy = alloc(v.n);
+      check(ctx, cocg_d2d(ctx, copy.p, v.p, v.n * 32), "cocg_d2d");
+      check(ctx, cocg_sync(ctx), "cocg_sync");
+      Message m;
+      m.bytes = v.n * 32;
+      m.device = copy.p;
+      net->send(target, std::move(m));
+      return;
+    }
     std::shared_ptr<void> buf = pinned(v.n * 32);
     check(ctx, cocg_d2h(ctx, buf.get(), v.p, v.n * 32), "cocg_d2h");
     net->send(target, Message{buf, v.n * 32});
@@ -151,6 +167,7 @@ class ShamirProtocol : public DeviceDriver {
   DevVec recv_vec(int from, size_t n, const char* what) {
     Message m = net->recv(from);
     if (m.bytes != n * 32) throw Error(std::string("During execution of ") + what + " in MPC: Invalid number of elements received");
+    if (m.device) return DevVec{m.device, n};
     return upload(m.data.get(), n);
   }
   // buffer_triples (shamir.rs:925-1010): every party shares `amount` random values with degree t and 2t, all parties apply the

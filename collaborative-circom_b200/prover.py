@@ -29,7 +29,7 @@ HOST_SYMBOLS = [
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
     "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
     "cohost_vm_create", "cohost_vm_destroy", "cohost_vm_set_public", "cohost_vm_set_shared", "cohost_vm_run", "cohost_vm_get", "cohost_vm_stats",
-    "cohost_shamir_session_set_shard", "cohost_rep3_session_create_blocks", "cohost_block_plan", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
+    "cohost_shamir_session_set_shard", "cohost_shamir_set_mpc_exchange", "cohost_rep3_session_create_blocks", "cohost_block_plan", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
     "cohost_plonk_prove", "cohost_plonk_set_mpc_exchange", "cohost_plonk_launch_count", "cohost_plonk_profile_enable",
     "cohost_plonk_profile_reset", "cohost_plonk_profile_read", "cohost_plonk_round_times", "cohost_plonk_trace_enable",
     "cohost_plonk_trace_get", "cohost_plonk_proof_to_json",
@@ -144,6 +144,7 @@ def load_host():
     L.cohost_shamir_session_destroy.restype = None
     L.cohost_shamir_prove.argtypes = [vp, vp, pvp, vp, vp]
     L.cohost_shamir_session_set_shard.argtypes = [vp, ci, ci, GATHER_CB, vp]
+    L.cohost_shamir_set_mpc_exchange.argtypes = [vp, ci]
     L.cohost_msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     L.cohost_proof_to_json.argtypes = [ci, vp, vp, sz, ctypes.POINTER(sz)]
     L.cohost_public_inputs_to_json.argtypes = [ci, vp, sz, vp, sz, ctypes.POINTER(sz)]
@@ -607,6 +608,11 @@ class ShamirSession:
 
             self._cb = GATHER_CB(cb)
             _ck(load_host().cohost_shamir_session_set_shard(self.h, rank, world, self._cb, None))
+
+    def set_mpc_exchange(self, mode: str):
+        """'host': share vectors staged through pinned host memory (default); 'device': handed over in HBM (co-located parties)."""
+        _need(mode in ("host", "device"), "set_mpc_exchange: mode must be host or device")
+        _ck(load_host().cohost_shamir_set_mpc_exchange(self.h, 1 if mode == "device" else 0))
 
     def prove(self, public_inputs, wit):
         """wit: n host share vectors.  Returns (proofs (n, A|B|C), rs (n, 2, 4): each party's shares of r and s)."""

@@ -134,6 +134,7 @@ COHOST_API int cohost_rep3_phase_times(cohost_rep3_session* s, double* out);
  * the caller supplies: gather(user, local, bytes, gathered) fills gathered[world x bytes] in rank order and returns 0. */
 typedef int (*cohost_gather_cb)(void* user, const void* local, size_t bytes, void* gathered);
 COHOST_API int cohost_shamir_session_set_shard(cohost_shamir_session* s, int rank, int world, cohost_gather_cb gather, void* user);
+COHOST_API int cohost_shamir_set_mpc_exchange(cohost_shamir_session* s, int device);  /* as cohost_rep3_set_mpc_exchange */
 COHOST_API int cohost_shamir_session_create(cohost_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_shamir_session** out);
 COHOST_API void cohost_shamir_session_destroy(cohost_shamir_session* s);
 COHOST_API int cohost_shamir_prove(cohost_shamir_session* s, const void* public_inputs, const void* const* wit, void* proofs_out, void* rs_out);
