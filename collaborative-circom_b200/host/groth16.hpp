@@ -13,6 +13,7 @@
 #pragma once
 #include <chrono>
 #include <functional>
+#include <future>
 
 #include "driver.hpp"
 
@@ -121,16 +122,27 @@ class CoGroth16 {
                      const FieldShareVec& private_witness) {
     driver.release(last_h);
     const double t0 = now();
-    FieldShareVec h;
-    if (!blocks || blocks->wm[party_id()] == block_rank) h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
-    else skip_witness_map();  // another rank runs this party's witness map: stay in step with its randomness
-    check(driver.ctx, cocg_sync(driver.ctx), "cocg_sync");
-    phase_s[0] = now() - t0;
+    // r, s and r*s are drawn FIRST (the reference draws them after the witness map, groth16.rs:128-131; they are independent of it):
+    // every group operation of create_proof_with_assignment that depends only on them and on the key -- 8 G1 and 3 G2 scalar
+    // multiplications of delta and of the public-input part of the queries, ~2 ms of host arithmetic -- then runs on a helper thread
+    // WHILE the GPU computes the witness map and the MSMs, instead of after them
     FieldShare r = driver.rand();
     FieldShare s = driver.rand();
     last_r = r;
     last_s = s;
-    Groth16Proof p = create_proof_with_assignment(zkey, hd, r, s, h, public_inputs_host, private_witness);
+    FieldShare rs = driver.mul(r, s);
+    std::future<Precomputed> pre = std::async(std::launch::async, [this, &zkey, r, s, rs, &public_inputs_host] { return precompute(zkey, r, s, rs, public_inputs_host); });
+    FieldShareVec h;
+    try {
+      if (!blocks || blocks->wm[party_id()] == block_rank) h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
+      else skip_witness_map();  // another rank runs this party's witness map: stay in step with its randomness
+      check(driver.ctx, cocg_sync(driver.ctx), "cocg_sync");
+    } catch (...) {
+      pre.wait();
+      throw;
+    }
+    phase_s[0] = now() - t0;
+    Groth16Proof p = create_proof_with_assignment(zkey, hd, r, s, h, public_inputs_host, private_witness, &pre);
     last_h = h;
     return p;
   }
@@ -166,12 +178,34 @@ class CoGroth16 {
     return ab;
   }
 
-  PointShare calculate_coeff(int g, const PointShare& initial, const std::vector<Point>& query_head, const Point& vk_param,
-                             const std::vector<Fr>& input_assignment, const PointShare& priv_acc) {
-    // pub_acc = msm_unchecked(query[1..=l], input_assignment): l is tiny, done on the host
+  // pub_acc = msm_unchecked(query[1..=l], input_assignment): l is tiny, done on the host
+  Point public_acc(int g, const std::vector<Point>& query_head, const std::vector<Fr>& input_assignment) {
     Point pub_acc = driver.infinity(g);
     for (size_t i = 0; i < input_assignment.size(); i++)
       pub_acc = driver.ec_add(g, pub_acc, driver.ec_mul(g, driver.from_affine(g, query_head[1 + i]), input_assignment[i]));
+    return pub_acc;
+  }
+  // what create_proof_with_assignment needs from (r, s, r*s, the key, the public inputs) alone: host arithmetic, no device, no network
+  struct Precomputed {
+    Point delta_g1, delta_g2, pub_a, pub_b1, pub_b2;
+    PointShare r_s_delta_g1, r_g1, s_g1, s_g2;
+  };
+  Precomputed precompute(const ZKey& zkey, const FieldShare& r, const FieldShare& s, const FieldShare& rs, const std::vector<Fr>& public_inputs_host) {
+    std::vector<Fr> input_assignment(public_inputs_host.begin() + 1, public_inputs_host.end());
+    Precomputed p;
+    p.delta_g1 = driver.from_affine(1, zkey.delta_g1);
+    p.delta_g2 = driver.from_affine(2, zkey.delta_g2);
+    p.r_s_delta_g1 = driver.scalar_mul_public_point(1, p.delta_g1, rs);
+    p.r_g1 = driver.scalar_mul_public_point(1, p.delta_g1, r);
+    p.s_g1 = driver.scalar_mul_public_point(1, p.delta_g1, s);
+    p.s_g2 = driver.scalar_mul_public_point(2, p.delta_g2, s);
+    p.pub_a = public_acc(1, zkey.a_head, input_assignment);
+    p.pub_b1 = public_acc(1, zkey.b_g1_head, input_assignment);
+    p.pub_b2 = public_acc(2, zkey.b_g2_head, input_assignment);
+    return p;
+  }
+  PointShare calculate_coeff(int g, const PointShare& initial, const std::vector<Point>& query_head, const Point& vk_param, const Point& pub_acc,
+                             const PointShare& priv_acc) {
     PointShare res = initial;
     driver.add_assign_points_public_affine(g, res, query_head[0]);
     driver.add_assign_points_public_affine(g, res, vk_param);
@@ -181,9 +215,9 @@ class CoGroth16 {
   }
 
   Groth16Proof create_proof_with_assignment(const ZKey& zkey, const Handles& hd, const FieldShare& r, const FieldShare& s, const FieldShareVec& h,
-                                            const std::vector<Fr>& public_inputs_host, const FieldShareVec& aux_assignment) {
+                                            const std::vector<Fr>& public_inputs_host, const FieldShareVec& aux_assignment,
+                                            std::future<Precomputed>* pre_async = nullptr) {
     const double t_start = now();
-    std::vector<Fr> input_assignment(public_inputs_host.begin() + 1, public_inputs_host.end());
     const size_t l = zkey.n_public, n_aux = zkey.n_aux();
     // ---- all secret-scalar MSMs first (msm_public_points at groth16.rs:248, 251-255 and inside calculate_coeff :221-225)
     MsmPartials m;
@@ -211,26 +245,22 @@ class CoGroth16 {
     const double t_comb = now();
     phase_s[2] = t_comb - t_msm;
 
-    Point delta_g1 = driver.from_affine(1, zkey.delta_g1);
-    FieldShare rs = driver.mul(r, s);
-    PointShare r_s_delta_g1 = driver.scalar_mul_public_point(1, delta_g1, rs);
+    Precomputed pc;
+    if (pre_async) pc = pre_async->get();
+    else pc = precompute(zkey, r, s, driver.mul(r, s), public_inputs_host);
 
-    PointShare r_g1 = driver.scalar_mul_public_point(1, delta_g1, r);
-    PointShare g_a = calculate_coeff(1, r_g1, zkey.a_head, zkey.alpha_g1, input_assignment, m.a_acc);
+    PointShare g_a = calculate_coeff(1, pc.r_g1, zkey.a_head, zkey.alpha_g1, pc.pub_a, m.a_acc);
     Point g_a_opened = driver.open_point(1, g_a);
     PointShare s_g_a = driver.scalar_mul_public_point(1, g_a_opened, s);
 
-    PointShare s_g1 = driver.scalar_mul_public_point(1, delta_g1, s);
-    PointShare g1_b = calculate_coeff(1, s_g1, zkey.b_g1_head, zkey.beta_g1, input_assignment, m.b1_acc);
+    PointShare g1_b = calculate_coeff(1, pc.s_g1, zkey.b_g1_head, zkey.beta_g1, pc.pub_b1, m.b1_acc);
     PointShare r_g1_b = driver.scalar_mul(1, g1_b, r);
 
-    Point delta_g2 = driver.from_affine(2, zkey.delta_g2);
-    PointShare s_g2 = driver.scalar_mul_public_point(2, delta_g2, s);
-    PointShare g2_b = calculate_coeff(2, s_g2, zkey.b_g2_head, zkey.beta_g2, input_assignment, m.b2_acc);
+    PointShare g2_b = calculate_coeff(2, pc.s_g2, zkey.b_g2_head, zkey.beta_g2, pc.pub_b2, m.b2_acc);
 
     PointShare g_c = s_g_a;
     driver.add_assign_points(1, g_c, r_g1_b);
-    driver.sub_assign_points(1, g_c, r_s_delta_g1);
+    driver.sub_assign_points(1, g_c, pc.r_s_delta_g1);
     driver.add_assign_points(1, g_c, m.l_acc);
     driver.add_assign_points(1, g_c, m.h_acc);
 

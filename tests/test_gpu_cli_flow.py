@@ -129,7 +129,7 @@ def test_plonk_files_to_verified_proof(cocg, tmp_path):
     """`generate-proof plonk` (co-circom.rs:455-636 with the Plonk proof system): witness.wtns -> three REP3 share files -> CoPlonk::prove
     on the GPU -> proof.json accepted by `verify plonk` with the fixture's snarkjs verification key; a changed public input is rejected."""
     d = os.path.join(G, "plonk", "bn254", "multiplier2")
-    r1cs = os.path.join(G, "groth16", "bn254", "multiplier2", "circuit.r1cs")   # the same circuit; only its input counts are read
+    r1cs = os.path.join(d, "circuit.r1cs")
     cli = _cli()
     cli.main(["split-witness", "--witness", os.path.join(d, "witness.wtns"), "--r1cs", r1cs, "--protocol", "REP3", "--curve", "BN254",
               "--out-dir", str(tmp_path)])

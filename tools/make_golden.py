@@ -125,7 +125,7 @@ def plonk_round2():
     out["verifier_challenges"] = {k: v for k, v in vals}
     src = os.path.join(REF, "test_vectors", "Plonk", "bn254", "multiplier2")
     dst = os.path.join(OUT, "plonk", "bn254", "multiplier2")
-    for f in ("circuit.zkey", "circom.proof", "public.json"):
+    for f in ("circuit.zkey", "circom.proof", "public.json", "circuit.r1cs"):
         shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
         os.chmod(os.path.join(dst, f), 0o644)
     # snarkjs Plonk proofs + keys of all four fixtures: the known-answer test of the verifier (co-plonk/src/lib.rs:255-275)
