@@ -405,8 +405,12 @@ def run_own(args):
             "e2e": {"value": e2e, "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": 3 * 2 * n_aux * 32 + 3 * 2 * 32, "d2h_bytes_per_step": 3 * 8 * 4 * 8,
                     "mpc_exchange_bytes_per_step": 2 * 3 * 2 * n * 32,
-                    "note": "witness shares in pinned host memory uploaded every step, proofs read back, and the two mul_vec rounds of each "
-                            "party (n x 32 B out + in per round) staged through pinned host memory; the `value` leg keeps all of that in HBM"},
+                    "note": ("witness shares in pinned host memory uploaded every step, proofs read back, and the two mul_vec rounds of each "
+                             "party (n x 32 B out + in per round) staged through pinned host memory; the `value` leg keeps all of that in HBM")
+                            if world == 1 or mode != "blocks" else
+                            ("witness share components in pinned host memory uploaded every step by the ranks whose blocks read them, proofs read "
+                             "back; the parties' witness maps run on different GPUs, so their mul_vec payloads travel GPU to GPU over NVLink "
+                             "(NCCL send / recv) in both legs; the `value` leg keeps the witness in HBM")},
             "gpu_launches": int(launches),
             "proof_sha256": proof_sha256,
             "proof_sha256_of": f"proof number {args.warmup + args.steps} of the value leg (A | B | C packed affine Montgomery limbs), fixed PRF seeds",

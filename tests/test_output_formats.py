@@ -177,3 +177,30 @@ def test_shared_witness_bytes_hand_derived(cocg):
     # Shamir: ShamirPrimeFieldShareVec { a } (shamir/fieldshare.rs:152-155) -- one vector
     literal_shamir = bytes.fromhex(u64(72) + u64(2) + le32(1) + le32(5) + u64(40) + u64(1) + le32(7))
     assert cocg.shared_witness_encode(cocg.BN254, cref.fr_to_mont(c, [1, 5]), [cref.fr_to_mont(c, [7])]) == literal_shamir
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bls12_381"])
+def test_plonk_proof_json_writer_reproduces_snarkjs_fixture(cocg, curve):
+    """PlonkProof serde layout (circom-types/src/plonk/proof.rs:7-87; its own test reads the same fixtures, :97-190): the product's writer,
+    fed the points and evaluations of the snarkjs `circom.proof`, reproduces the fixture's JSON value."""
+    c = BN254 if curve == "bn254" else BLS12_381
+    want = json.load(open(os.path.join(G, "plonk", curve, "multiplier2", "circom.proof")))
+    pts = [None if want[k][2] == "0" else (int(want[k][0]), int(want[k][1])) for k in ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")]
+    evs = [int(want[k]) for k in ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw")]
+    block = np.concatenate([cref.g_to_mont(c, pts, 1).reshape(-1), cref.fr_to_mont(c, evs).reshape(-1)])
+    got = json.loads(cocg.plonk_proof_to_json(_cid(cocg, c), block))
+    assert got == want
+
+
+def test_block_plan_covers_every_block_once(cocg):
+    """Multi-GPU block mode (host/types.hpp BlockPlan): all 15 blocks of a proof are placed, on valid ranks, as evenly as 15 blocks
+    allow; with three or more ranks the three witness maps run on three different GPUs."""
+    for world in (1, 2, 3, 4, 5, 8, 16):
+        p = cocg.block_plan(world)
+        ranks = p["wm"] + [r for pair in p["g1"] for r in pair] + [r for pair in p["g2"] for r in pair]
+        assert len(ranks) == 15 and all(0 <= r < world for r in ranks)
+        load = [ranks.count(r) for r in range(world)]
+        assert max(load) - min(load) <= 1 or world > 15
+        assert max(load) == -(-15 // world) if world <= 15 else max(load) == 1
+        if world >= 3:
+            assert len(set(p["wm"])) == 3
