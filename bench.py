@@ -602,7 +602,7 @@ def plonk_config(args, world):
             "curve": "bn254", "protocol": "rep3", "domain_size": n, "extended_domain": 4 * n, "n_public": 1,
             "per_party": "2 components x (4 iNTT(n) + 4 NTT(4n) + 2 iNTT(4n) + 9 G1 MSMs of ~n over p_tau), 2 fused quotient kernels on 4n, "
                          "prefix-product / inverse / Horner scans on n",
-            "mpc_exchanges_per_party": "12 vectors of 4n (round 3, two rounds) + ~16 vectors of n (round 2)",
+            "mpc_exchanges_per_party": "8 vectors of 4n (round 3, two rounds) + ~16 vectors of n (round 2)",
             "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one proof per GPU per step, no collective)",
             "l2_policy": "inputs_exceed_l2 (>= 1.5 GB of evaluation vectors and tables streamed per proof vs 126 MB L2)"}
 
@@ -775,7 +775,7 @@ def run_own_plonk(args):
         dom_ms = prof[dom][0] / args.steps
         achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
         value = world * args.steps / (ms / 1e3)
-        exch = 3 * (12 * 4 * n + 16 * n) * 32
+        exch = 3 * (8 * 4 * n + 16 * n) * 32
         o = {
             "metric": "plonk_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <array>
 #include <deque>
@@ -157,7 +158,12 @@ inline int msm_plan_window_bits(size_t n, int scalar_bits) {
   while (((size_t)1 << (lg + 1)) <= v) lg++;
   int c = lg;
   if (c < 4) c = 4;
-  if (c > 20) c = 20;
+  int cap = 20;
+  if (const char* e = getenv("COCG_MSM_MAX_WINDOW")) {  // experiment knob: cap of the window width, 8..22
+    int v2 = atoi(e);
+    if (v2 >= 8 && v2 <= 22) cap = v2;
+  }
+  if (c > cap) c = cap;
   while (c > 4 && (scalar_bits + c - 1) / (c - 1) == (scalar_bits + c) / c) c--;
   return c;
 }

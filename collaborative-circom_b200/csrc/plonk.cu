@@ -9,7 +9,7 @@
 //   level 1:  x * y           of wire / permutation evaluations and the blinding polynomials,
 //   level 2:  (x * y) * (u * v) of two level-1 results,
 // and everything else is linear.  A REP3 product is local up to a re-sharing of ONE additive value per element, and sums of products
-// may be re-shared together, so the quotient needs exactly two exchanges: after `plonk_quotient_l1_kernel` (10 vectors of 4n) and after
+// may be re-shared together, so the quotient needs exactly two exchanges: after `plonk_quotient_l1_kernel` (6 vectors of 4n) and after
 // `plonk_quotient_l2_kernel` (2 vectors: t and tz).  Products of two BLINDING polynomials (ap*bp, cp*zp, cp*zwp) are polynomials in w
 // whose coefficients are products of the shared blinders b_i -- ten scalar multiplications done once on the host driver.
 // With Z = Z_H(w^i) in {0, zeta_1, zeta_2, zeta_3} (get_z1..3: z1[m] = zeta_m, z2[m] = zeta_m^2, z3[m] = zeta_m^3) the five outputs of
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) plonk_z_factors_kernel(ZFactorArgs g, siz
 }
 
 // ---------------------------------------------------------------------------------------------- round 3
-constexpr int kQuotL1Outs = 10;
+constexpr int kQuotL1Outs = 6;
 struct QuotArgs {  // mirrors cocg_plonk_quotient_args (include/cocg.h), device pointers resolved
   const void* ea[2]; const void* eb[2]; const void* ec[2]; const void* ez[2];
   const void* s1; const void* s2; const void* s3;
@@ -111,8 +111,8 @@ struct QuotArgs {  // mirrors cocg_plonk_quotient_args (include/cocg.h), device 
   const void* lagrange;      // n_lagrange polynomials of 4n evaluations, contiguous
   const void* wpow;          // w^i, i < 4n (w = generator of the 4n domain)
   const void* buf_a[2];      // wire buffer a (first n_lagrange elements are the public-input gates)
-  const void* l1[2];         // level-1 results: 10 vectors of 4n, contiguous, per component
-  void* out;                 // l1: 10 x 4n; l2: 2 x 4n (t | tz)
+  const void* l1[2];         // level-1 results: 6 vectors of 4n, contiguous, per component
+  void* out;                 // l1: 6 x 4n; l2: 2 x 4n (t | tz)
 };
 template <class P>
 struct QuotScalars {
@@ -162,28 +162,16 @@ __global__ void __launch_bounds__(128) plonk_quotient_l1_kernel(QuotArgs g, Quot
   const Sh<P, K> a = sh_load<P, K>(g.ea, i), b = sh_load<P, K>(g.eb, i), c = sh_load<P, K>(g.ec, i), z = sh_load<P, K>(g.ez, i);
   const Sh<P, K> zw = sh_load<P, K>(g.ez, (i + 4) & (n4 - 1));
   const Blind<P, K> bl = blinding_evals<P, K>(s, w);
+  // The wire factors of the permutation products differ from a, b, c by PUBLIC addends only (A = a + (beta w + gamma), ...), so
+  // A*B = a*b + cb*a + ca*b + ca*cb and Ap*B + A*Bp = (ap*b + a*bp) + cb*ap + ca*bp are linear in the two gate products below:
+  // six products are re-shared, not ten (level 2 rebuilds X0, X1, Y0, Y1 of both permutation terms from them).
   Fp<P> o[kQuotL1Outs];
   o[0] = sh_lmul(a, b);                                    // a*b
   o[1] = fp_add(sh_lmul(a, bl.bp), sh_lmul(bl.ap, b));     // a*bp + ap*b
-  const Fp<P> betaw = fmul<P>(s.beta, w);
-  {
-    const Sh<P, K> A = sh_add_pub(a, fp_add(betaw, s.gamma), pub_comp);
-    const Sh<P, K> B = sh_add_pub(b, fp_add(fmul<P>(betaw, s.k1), s.gamma), pub_comp);
-    const Sh<P, K> C = sh_add_pub(c, fp_add(fmul<P>(betaw, s.k2), s.gamma), pub_comp);
-    o[2] = sh_lmul(A, B);
-    o[3] = fp_add(sh_lmul(bl.ap, B), sh_lmul(A, bl.bp));
-    o[4] = sh_lmul(C, z);
-    o[5] = fp_add(sh_lmul(bl.cp, z), sh_lmul(C, bl.zp));
-  }
-  {
-    const Sh<P, K> A = sh_add_pub(a, fp_add(fmul<P>(load_fp_ro<P>(g.s1, i), s.beta), s.gamma), pub_comp);
-    const Sh<P, K> B = sh_add_pub(b, fp_add(fmul<P>(load_fp_ro<P>(g.s2, i), s.beta), s.gamma), pub_comp);
-    const Sh<P, K> C = sh_add_pub(c, fp_add(fmul<P>(load_fp_ro<P>(g.s3, i), s.beta), s.gamma), pub_comp);
-    o[6] = sh_lmul(A, B);
-    o[7] = fp_add(sh_lmul(bl.ap, B), sh_lmul(A, bl.bp));
-    o[8] = sh_lmul(C, zw);
-    o[9] = fp_add(sh_lmul(bl.cp, zw), sh_lmul(C, bl.zwp));
-  }
+  o[2] = sh_lmul(c, z);                                    // c*z
+  o[3] = fp_add(sh_lmul(bl.cp, z), sh_lmul(c, bl.zp));     // cp*z + c*zp
+  o[4] = sh_lmul(c, zw);                                   // c*zw
+  o[5] = fp_add(sh_lmul(bl.cp, zw), sh_lmul(c, bl.zwp));   // cp*zw + c*zwp
 #pragma unroll 1
   for (int j = 0; j < kQuotL1Outs; j++) {  // rolled: one copy of the PRF call in the instruction stream
     Fp<P> v = o[j];
@@ -235,9 +223,29 @@ __global__ void __launch_bounds__(128) plonk_quotient_l2_kernel(QuotArgs g, Quot
   }
   // ---- bilinear parts
   Fp<P> e23 = Fp<P>::zero(), e23z = Fp<P>::zero();
+  const Sh<P, K> av = sh_load<P, K>(g.ea, i), bv = sh_load<P, K>(g.eb, i);
+  const Sh<P, K> zv = sh_load<P, K>(g.ez, i), zwv = sh_load<P, K>(g.ez, (i + 4) & (n4 - 1));
+  const Sh<P, K> P1 = L1(0), P23 = L1(1);
+  const Fp<P> betaw = fmul<P>(s.beta, w);
 #pragma unroll
   for (int grp = 0; grp < 2; grp++) {
-    const Sh<P, K> X0 = L1(2 + 4 * grp), X1 = L1(3 + 4 * grp), Y0 = L1(4 + 4 * grp), Y1 = L1(5 + 4 * grp);
+    // public addends of the three wire factors of this permutation term (round3.rs:397-409)
+    Fp<P> ca, cb, cc;
+    if (grp == 0) {
+      ca = fp_add(betaw, s.gamma);
+      cb = fp_add(fmul<P>(betaw, s.k1), s.gamma);
+      cc = fp_add(fmul<P>(betaw, s.k2), s.gamma);
+    } else {
+      ca = fp_add(fmul<P>(load_fp_ro<P>(g.s1, i), s.beta), s.gamma);
+      cb = fp_add(fmul<P>(load_fp_ro<P>(g.s2, i), s.beta), s.gamma);
+      cc = fp_add(fmul<P>(load_fp_ro<P>(g.s3, i), s.beta), s.gamma);
+    }
+    const Sh<P, K>& D = grp ? zwv : zv;
+    const Sh<P, K>& Dp = grp ? bl.zwp : bl.zp;
+    const Sh<P, K> X0 = sh_add_pub(sh_add(P1, sh_add(sh_scale(av, cb), sh_scale(bv, ca))), fmul<P>(ca, cb), pub_comp);
+    const Sh<P, K> X1 = sh_add(P23, sh_add(sh_scale(bl.ap, cb), sh_scale(bl.bp, ca)));
+    const Sh<P, K> Y0 = sh_add(L1(2 + 2 * grp), sh_scale(D, cc));
+    const Sh<P, K> Y1 = sh_add(L1(3 + 2 * grp), sh_scale(Dp, cc));
     const Sh<P, K>& Y2g = grp ? Y2w : Y2;
     const Fp<P> r = sh_lmul(X0, Y0);
     Fp<P> post;

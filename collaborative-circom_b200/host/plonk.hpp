@@ -428,9 +428,9 @@ class CoPlonk {
     qa.scalar_products = sprod;
     qa.seed_own = driver.seed_own();
     qa.seed_prev = driver.seed_prev();
-    // level 1: ten product vectors, one exchange
-    DevVec l1 = driver.alloc(10 * n4);
-    qa.ctr = driver.take_ctr(10);
+    // level 1: six product vectors, one exchange
+    DevVec l1 = driver.alloc(6 * n4);
+    qa.ctr = driver.take_ctr(6);
     qa.out = l1.p;
     check(driver.ctx, cocg_plonk_quotient_l1(driver.ctx, &qa), "cocg_plonk_quotient_l1");
     FieldShareVec l1s = driver.reshare(l1);

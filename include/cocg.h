@@ -209,7 +209,7 @@ typedef struct cocg_plonk_z_args {
 } cocg_plonk_z_args;
 COCG_API int cocg_plonk_z_factors(cocg_ctx* ctx, const cocg_plonk_z_args* args, size_t n, int add_public);
 /* Round 3, compute_t (round3.rs:237-471) in two levels (see csrc/plonk.cu for the algebra): level 1 writes the party's additive, masked
- * shares of 10 product vectors (out: 10 x n4), level 2 those of t and tz (out: 2 x n4).  The caller re-shares after each level. */
+ * shares of 6 product vectors (out: 6 x n4), level 2 those of t and tz (out: 2 x n4).  The caller re-shares after each level. */
 typedef struct cocg_plonk_quotient_args {
   int components;                        /* 1 plain, 2 REP3 (a | b) */
   int pub_comp;                          /* component that receives public addends: 0 plain / party 0, 1 party 1, -1 party 2 */
@@ -219,12 +219,12 @@ typedef struct cocg_plonk_quotient_args {
   const void* buffer_a[2];               /* DEVICE: wire buffer a (its first n_public elements feed PI) */
   const void *sigma1, *sigma2, *sigma3, *qm, *ql, *qr, *qo, *qc;  /* DEVICE: n4 public evaluations each */
   const void* lagrange;                  /* DEVICE: n_lagrange x n4 evaluations, contiguous */
-  const void* level1[2];                 /* DEVICE (level 2 only): the re-shared level-1 vectors, 10 x n4 per component */
+  const void* level1[2];                 /* DEVICE (level 2 only): the re-shared level-1 vectors, 6 x n4 per component */
   const void *beta, *gamma, *alpha, *k1, *k2, *omega_n, *omega_4n;  /* HOST Fr */
   const void* blinders;                  /* HOST: b0..b8 as 9 x 2 Fr (component a | b; b ignored when components = 1) */
   const void* scalar_products;           /* HOST (level 2): shares of b1b3 b0b3 b1b2 b0b2 b5b8 b5b7 b5b6 b4b8 b4b7 b4b6, 10 x 2 Fr */
   const void *seed_own, *seed_prev;      /* HOST: 32-byte PRF seeds (REP3 zero-masks; csrc/prf.cuh) */
-  uint32_t ctr;                          /* first PRF vector counter; level 1 consumes 10, level 2 consumes 2 */
+  uint32_t ctr;                          /* first PRF vector counter; level 1 consumes 6, level 2 consumes 2 */
   void* out;                             /* DEVICE */
 } cocg_plonk_quotient_args;
 COCG_API int cocg_plonk_quotient_l1(cocg_ctx* ctx, const cocg_plonk_quotient_args* args);
