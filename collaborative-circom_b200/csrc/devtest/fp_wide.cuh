@@ -9,7 +9,7 @@
 // to (e[c], e[c+1]) when c is even and to (o[c-1], o[c]) when c is odd, so every product lands on an aligned (lo, hi) register
 // pair and a row of products of one parity is a single carry chain (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32.X).
 #pragma once
-#include "fp.cuh"
+#include "../fp.cuh"
 
 #if defined(__CUDA_ARCH__)
 namespace cocg {

@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../fp_wide.cuh"
+#include "fp_wide.cuh"
 
 using namespace cocg;
 
