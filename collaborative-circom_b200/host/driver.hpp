@@ -239,6 +239,19 @@ class PlainDriver : public DeviceDriver {
 
   // ---- CoPlonk (co-plonk/src/round*.rs) driver surface: plain.rs:111-285
   int pub_comp() const { return 0; }
+  // several scalar vectors against the SAME bases in one call (the commitments of one Plonk round over p_tau): their bucket sets are
+  // reduced together and the call synchronises once
+  std::vector<PointShare> msm_public_points_many(int group, uint64_t bases, size_t n, const std::vector<const FieldShareVec*>& scalars) {
+    const size_t m = scalars.size(), nl = 3 * group * lq;
+    std::vector<const void*> sc(m);
+    for (size_t j = 0; j < m; j++) sc[j] = scalars[j]->a.p;
+    std::vector<uint64_t> packed(m * nl);
+    check(ctx, cocg_msm(ctx, bases, 0, n, sc.data(), (int)m, 1, packed.data()), "cocg_msm");
+    std::vector<PointShare> r(m);
+    for (size_t j = 0; j < m; j++) memcpy(r[j].a.l, packed.data() + j * nl, nl * 8);
+    return r;
+  }
+  std::vector<Point> open_point_many(int, const std::vector<PointShare>& a) { std::vector<Point> r; for (auto& x : a) r.push_back(x.a); return r; }
   std::vector<FieldShare> mul_many(const std::vector<FieldShare>& a, const std::vector<FieldShare>& b) {  // plain.rs:123-131
     std::vector<FieldShare> r(a.size());
     for (size_t i = 0; i < a.size(); i++) r[i] = mul(a[i], b[i]);
@@ -468,6 +481,35 @@ class Rep3Protocol : public DeviceDriver {
 
   // ---- CoPlonk (co-plonk/src/round*.rs) driver surface: rep3.rs:503-760
   int pub_comp() const { return id() == 0 ? 0 : id() == 1 ? 1 : -1; }
+  // several share vectors against the SAME bases in one call (k = 2 components each, at most 4 vectors): one launch sequence, one sync
+  std::vector<PointShare> msm_public_points_many(int group, uint64_t bases, size_t n, const std::vector<const FieldShareVec*>& scalars) {
+    const size_t m = scalars.size(), nl = 3 * group * lq;
+    if (2 * m > 8) throw Error("msm_public_points_many: at most 4 share vectors per call");
+    std::vector<const void*> sc(2 * m);
+    for (size_t j = 0; j < m; j++) { sc[2 * j] = scalars[j]->a.p; sc[2 * j + 1] = scalars[j]->b.p; }
+    std::vector<uint64_t> packed(2 * m * nl);
+    check(ctx, cocg_msm(ctx, bases, 0, n, sc.data(), (int)(2 * m), 1, packed.data()), "cocg_msm");
+    std::vector<PointShare> r(m);
+    for (size_t j = 0; j < m; j++) {
+      memcpy(r[j].a.l, packed.data() + 2 * j * nl, nl * 8);
+      memcpy(r[j].b.l, packed.data() + (2 * j + 1) * nl, nl * 8);
+    }
+    return r;
+  }
+  std::vector<Point> open_point_many(int g, const std::vector<PointShare>& a) {  // rep3.rs:855-861: one message for all of them
+    const size_t nb = 3 * g * lq * 8;
+    std::vector<uint8_t> snd(a.size() * nb), rcv(a.size() * nb);
+    for (size_t j = 0; j < a.size(); j++) memcpy(snd.data() + j * nb, a[j].b.l, nb);
+    net->send_next_bytes(snd.data(), snd.size());
+    net->recv_prev_bytes(rcv.data(), rcv.size());
+    std::vector<Point> r(a.size());
+    for (size_t j = 0; j < a.size(); j++) {
+      Point c;
+      memcpy(c.l, rcv.data() + j * nb, nb);
+      r[j] = ec_add(g, ec_add(g, a[j].a, a[j].b), c);
+    }
+    return r;
+  }
   const uint8_t* seed_own() const { return seed1; }
   const uint8_t* seed_prev() const { return seed2; }
   uint32_t take_ctr(uint32_t k) { uint32_t c = ctr; ctr += k; return c; }

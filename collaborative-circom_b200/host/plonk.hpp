@@ -264,6 +264,19 @@ class CoPlonk {
     PointShare c = driver.msm_public_points(1, p_tau_, 0, len, poly);
     return driver.to_affine(1, driver.open_point(1, c));
   }
+  // The commitments of one round (round1.rs:276-292, round3.rs:498-517, round5.rs:351-358): the polynomials are multiplied against
+  // the same p_tau, so ONE MSM call takes them as extra scalar vectors (their bucket sets are reduced together, one synchronisation)
+  // and open_point_many opens them with one message.  `len` covers the longest; every vector must hold zeros from its own end to len.
+  std::vector<Point> commit_many(const std::vector<const FieldShareVec*>& polys, size_t len) {
+    std::vector<PointShare> c = driver.msm_public_points_many(1, p_tau_, len, polys);
+    std::vector<Point> opened = driver.open_point_many(1, c);
+    for (auto& p : opened) p = driver.to_affine(1, p);
+    return opened;
+  }
+  void zero_tail(FieldShareVec& v, size_t from, size_t to) {
+    if (to <= from) return;
+    for (int k = 0; k < K; k++) check(driver.ctx, cocg_memset0(driver.ctx, comp(v, k).at(from), (to - from) * 32), "cocg_memset0");
+  }
 
   // ------------------------------------------------------------------------------------------------ round 1
   void round1(const Fr* public_inputs, const void* wit_a, const void* wit_b, bool deterministic, bool wit_on_device, PlonkProof& pr) {
@@ -315,7 +328,6 @@ class CoPlonk {
       if (K == 2) check(driver.ctx, cocg_h2d(driver.ctx, sig.b.at(base), hb.data(), hb.size() * 32), "cocg_h2d");
     }
     // ---- compute_wire_polynomials (round1.rs:121-209)
-    Point commits[3];
     for (int w = 0; w < 3; w++) {
       buf_[w] = driver.alloc_share(n);
       for (int k = 0; k < K; k++)
@@ -327,9 +339,9 @@ class CoPlonk {
       poly_[w] = extend(poly, n + 2, n);
       driver.release(poly);
       blind(poly_[w], n, {b_[2 * w + 1], b_[2 * w]});  // coeff_rev = b[2w .. 2w + 2]
-      commits[w] = commit(poly_[w], n + 2);
     }
     driver.release(sig);
+    std::vector<Point> commits = commit_many({&poly_[0], &poly_[1], &poly_[2]}, n + 2);
     pr.a = commits[0];
     pr.b = commits[1];
     pr.c = commits[2];
@@ -446,9 +458,11 @@ class CoPlonk {
     if (trace) { record("t_evals", t.a, n4); record("tz_evals", tz.a, n4); }
     driver.ifft_in_place(t, ext_);
     driver.ifft_in_place(tz, ext_);
-    t_[0] = driver.alloc_share(n + 1);
-    t_[1] = driver.alloc_share(n + 1);
+    t_[0] = driver.alloc_share(n + 6);  // t1, t2 hold n + 1 coefficients; zero up to n + 6 so that one MSM call commits all three
+    t_[1] = driver.alloc_share(n + 6);
     t_[2] = driver.alloc_share(n + 6);
+    zero_tail(t_[0], n, n + 6);
+    zero_tail(t_[1], n, n + 6);
     for (int k = 0; k < K; k++)
       check(driver.ctx, cocg_plonk_t_finish(driver.ctx, comp(t, k).p, comp(tz, k).p, n, comp(t_[0], k).p, comp(t_[1], k).p, comp(t_[2], k).p), "cocg_plonk_t_finish");
     driver.release(tt);
@@ -457,9 +471,10 @@ class CoPlonk {
     set_share_at(t_[1], n, b_[10]);  // t2.push(b[10])
     sub_share_at0(t_[2], b_[10]);    // t3[0] -= b[10]
     if (trace) { record("t1", t_[0].a, n + 1); record("t2", t_[1].a, n + 1); record("t3", t_[2].a, n + 6); }
-    pr.t1 = commit(t_[0], n + 1);
-    pr.t2 = commit(t_[1], n + 1);
-    pr.t3 = commit(t_[2], n + 6);
+    std::vector<Point> ct = commit_many({&t_[0], &t_[1], &t_[2]}, n + 6);
+    pr.t1 = ct[0];
+    pr.t2 = ct[1];
+    pr.t3 = ct[2];
   }
 
   // ------------------------------------------------------------------------------------------------ round 4
@@ -567,11 +582,13 @@ class CoPlonk {
     div_by_linear(wxi, len, xi_);
     if (trace) record("wxi", wxi.a, len - 1);
     // ---- compute_wxiw (round5.rs:315-330)
-    FieldShareVec wxiw = extend(poly_z_, n + 3, n + 3);
+    FieldShareVec wxiw = extend(poly_z_, len, n + 3);
     add_public_at0(wxiw, fr.neg(pr.eval_zw));
     div_by_linear(wxiw, n + 3, fr.mul(xi_, dom_.group_gen));
-    pr.wxi = commit(wxi, len - 1);
-    pr.wxiw = commit(wxiw, n + 2);
+    zero_tail(wxiw, n + 2, len);  // the quotient has n + 2 coefficients; slot n + 2 holds the (vanishing) remainder term
+    std::vector<Point> cw = commit_many({&wxi, &wxiw}, len - 1);
+    pr.wxi = cw[0];
+    pr.wxiw = cw[1];
     driver.release(wxi);
     driver.release(wxiw);
   }
