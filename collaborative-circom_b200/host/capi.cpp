@@ -3,6 +3,7 @@
 // Rep3TestNetwork, exactly how /root/reference/tests/tests/circom/e2e_tests/mod.rs:55-70 and
 // tests/benches/poseidon_hash2.rs:197-222 run it) on top of libcocg.so.  Declared in include/cohost.h.
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <thread>
 
@@ -1021,26 +1022,39 @@ extern "C" int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info) {
 // in-process network (tests/tests/circom/e2e_tests/mod.rs:55-70 runs the reference's Plonk provers the same way).
 struct cohost_plonk_session {
   cohost_plonk_zkey* zkey = nullptr;
-  int parties = 1;
+  int parties = 1, protocol = 0;
   std::unique_ptr<PlainDriver> plain;
   std::unique_ptr<Rep3TestNetwork> net;
   std::unique_ptr<Rep3Protocol> drv[3];
-  uint64_t h_tau[3] = {0, 0, 0};
+  std::unique_ptr<ShamirTestNetwork> snet;  // protocol 2: `parties` CoPlonk<ShamirProtocol> provers
+  std::vector<std::unique_ptr<ShamirProtocol>> sdrv;
+  std::vector<uint64_t> h_tau;
   bool trace_on = false;
-  std::map<std::string, std::vector<Fr>> traces[3];
-  double round_s[3][5] = {};
+  std::vector<std::map<std::string, std::vector<Fr>>> traces;
+  std::vector<std::array<double, 5>> round_s;
   bool failed = false;
-  DeviceDriver* driver(int i) { return parties == 1 ? (DeviceDriver*)plain.get() : (DeviceDriver*)drv[i].get(); }
+  DeviceDriver* driver(int i) { return protocol == 0 ? (DeviceDriver*)plain.get() : protocol == 1 ? (DeviceDriver*)drv[i].get() : (DeviceDriver*)sdrv[i].get(); }
+  void size_for(int n) {
+    parties = n;
+    h_tau.assign(n, 0);
+    traces.assign(n, {});
+    round_s.assign(n, std::array<double, 5>{});
+  }
+  void close_all() {
+    if (net) net->close_all();
+    if (snet) snet->close_all();
+  }
 };
 
 extern "C" int cohost_plonk_session_create(cohost_plonk_zkey* z, int protocol, const uint8_t* seeds, cohost_plonk_session** out) {
   if (!z || !out || !seeds) return fail("cohost_plonk_session_create: null argument");
-  if (protocol != 0 && protocol != 1) return fail("cohost_plonk_session_create: protocol must be 0 (plain) or 1 (REP3)");
+  if (protocol != 0 && protocol != 1) return fail("cohost_plonk_session_create: protocol must be 0 (plain) or 1 (REP3); Shamir sessions come from cohost_plonk_session_create_shamir");
   *out = nullptr;
   return guarded([&] {
     std::unique_ptr<cohost_plonk_session> s(new cohost_plonk_session());
     s->zkey = z;
-    s->parties = protocol == 0 ? 1 : 3;
+    s->protocol = protocol;
+    s->size_for(protocol == 0 ? 1 : 3);
     if (protocol == 0) {
       s->plain.reset(new PlainDriver(z->zk.curve, z->zk.device));
       memcpy(s->plain->seed, seeds, 32);
@@ -1058,52 +1072,86 @@ extern "C" int cohost_plonk_session_create(cohost_plonk_zkey* z, int protocol, c
     *out = s.release();
   });
 }
+// CoPlonk over Shamir (num_parties, threshold) shares: ShamirProtocol implements the same driver surface (co-plonk is generic over
+// PrimeFieldMpcProtocol + ..., plonk.rs:50-77; mpc-core/src/protocols/shamir.rs:459-712).  seeds: num_parties x 32 bytes.
+extern "C" int cohost_plonk_session_create_shamir(cohost_plonk_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_plonk_session** out) {
+  if (!z || !out || !seeds) return fail("cohost_plonk_session_create_shamir: null argument");
+  if (num_parties < 3 || num_parties > 64) return fail("Shamir protocol requires at least 3 parties");  // shamir/network.rs:75-77
+  *out = nullptr;
+  return guarded([&] {
+    std::unique_ptr<cohost_plonk_session> s(new cohost_plonk_session());
+    s->zkey = z;
+    s->protocol = 2;
+    s->size_for(num_parties);
+    s->snet.reset(new ShamirTestNetwork(num_parties));
+    const char* ex = getenv("COHOST_MPC_EXCHANGE");
+    s->snet->device_exchange = ex && std::string(ex) == "device";
+    for (int i = 0; i < num_parties; i++) {
+      s->sdrv.emplace_back(new ShamirProtocol(z->zk.curve, z->zk.device, threshold, s->snet->party(i), seeds + 32 * i));
+      check(s->sdrv[i]->ctx, cocg_bases_share(s->sdrv[i]->ctx, z->zk.owner, z->zk.p_tau, &s->h_tau[i]), "share p_tau");
+    }
+    *out = s.release();
+  });
+}
 extern "C" void cohost_plonk_session_destroy(cohost_plonk_session* s) { delete s; }
+extern "C" int cohost_plonk_session_parties(cohost_plonk_session* s) { return s ? s->parties : 0; }
 
-// One proof.  public_inputs: n_public + 1 Fr; wit_a / wit_b: `parties` pointers each (wit_b may be NULL for the plain driver) to the
-// parties' share components of the private witness, HOST memory or -- wit_on_device -- HBM of the session's device.
+// One proof.  public_inputs: n_public + 1 Fr; wit_a / wit_b: `parties` pointers each (wit_b may be NULL for the one-component plain and
+// Shamir drivers) to the parties' share components of the private witness, HOST memory or -- wit_on_device -- HBM of the session's device.
 // proofs_out: parties x cohost_plonk_proof_limbs() u64.  rounds = 1 stops after round 1 (commitments a, b, c only).
+template <class T, class GetDriver>
+static void plonk_prove_parties(cohost_plonk_session* s, GetDriver get, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
+                                bool deterministic, bool wit_on_device, bool round1_only, uint64_t* proofs_out) {
+  const PlonkZKey& zk = s->zkey->zk;
+  const size_t lq = s->zkey->lq, pl = 18 * lq + 24;
+  const int n = s->parties;
+  std::vector<std::thread> th(n);
+  std::vector<std::string> errs(n);
+  std::vector<PlonkProof> proofs(n);
+  for (int i = 0; i < n; i++) {
+    const void* a = wit_a[i];
+    const void* b = wit_b ? wit_b[i] : nullptr;
+    th[i] = std::thread([&, i, a, b] {
+      try {
+        CoPlonk<T> pv(*get(i));
+        if (s->trace_on) { s->traces[i].clear(); pv.trace = &s->traces[i]; }
+        proofs[i] = pv.prove(zk, s->h_tau[i], (const Fr*)public_inputs, a, b, deterministic, wit_on_device, round1_only);
+        memcpy(s->round_s[i].data(), pv.round_s, sizeof(pv.round_s));
+      } catch (const std::exception& e) {
+        errs[i] = e.what();
+        s->close_all();
+      }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; i++)
+    if (!errs[i].empty()) {
+      s->failed = true;
+      throw Error("party " + std::to_string(i) + ": " + errs[i]);
+    }
+  for (int i = 0; i < n; i++) plonk_proof_pack(proofs[i], lq, proofs_out + (size_t)i * pl);
+}
 static int plonk_prove_impl(cohost_plonk_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b, int deterministic,
                             int wit_on_device, int rounds, void* proofs_out) {
   if (!s || !public_inputs || !wit_a || !proofs_out) return fail("cohost_plonk_prove: null argument");
-  if (s->parties == 3 && !wit_b) return fail("cohost_plonk_prove: REP3 needs both share components");
+  if (s->protocol == 1 && !wit_b) return fail("cohost_plonk_prove: REP3 needs both share components");
   if (s->failed) return fail("cohost_plonk_prove: the session's network is closed after an earlier failure");
   return guarded([&] {
     const PlonkZKey& zk = s->zkey->zk;
-    const size_t lq = s->zkey->lq, pl = 18 * lq + 24;
-    if (s->parties == 1) {
+    const size_t lq = s->zkey->lq;
+    if (s->protocol == 0) {
       CoPlonk<PlainDriver> pv(*s->plain);
       if (s->trace_on) { s->traces[0].clear(); pv.trace = &s->traces[0]; }
       PlonkProof p = pv.prove(zk, s->h_tau[0], (const Fr*)public_inputs, wit_a[0], nullptr, deterministic != 0, wit_on_device != 0, rounds == 1);
-      memcpy(s->round_s[0], pv.round_s, sizeof(pv.round_s));
+      memcpy(s->round_s[0].data(), pv.round_s, sizeof(pv.round_s));
       plonk_proof_pack(p, lq, (uint64_t*)proofs_out);
-      return;
+    } else if (s->protocol == 1) {
+      plonk_prove_parties<Rep3Protocol>(s, [s](int i) { return s->drv[i].get(); }, public_inputs, wit_a, wit_b, deterministic != 0, wit_on_device != 0, rounds == 1,
+                                        (uint64_t*)proofs_out);
+    } else {
+      plonk_prove_parties<ShamirProtocol>(s, [s](int i) { return s->sdrv[i].get(); }, public_inputs, wit_a, nullptr, deterministic != 0, wit_on_device != 0,
+                                          rounds == 1, (uint64_t*)proofs_out);
     }
-    std::thread th[3];
-    std::string errs[3];
-    PlonkProof proofs[3];
-    for (int i = 0; i < 3; i++) {
-      const void* a = wit_a[i];
-      const void* b = wit_b[i];
-      th[i] = std::thread([&, i, a, b] {
-        try {
-          CoPlonk<Rep3Protocol> pv(*s->drv[i]);
-          if (s->trace_on) { s->traces[i].clear(); pv.trace = &s->traces[i]; }
-          proofs[i] = pv.prove(zk, s->h_tau[i], (const Fr*)public_inputs, a, b, deterministic != 0, wit_on_device != 0, rounds == 1);
-          memcpy(s->round_s[i], pv.round_s, sizeof(pv.round_s));
-        } catch (const std::exception& e) {
-          errs[i] = e.what();
-          s->net->close_all();
-        }
-      });
-    }
-    for (auto& t : th) t.join();
-    for (int i = 0; i < 3; i++)
-      if (!errs[i].empty()) {
-        s->failed = true;
-        throw Error("party " + std::to_string(i) + ": " + errs[i]);
-      }
-    for (int i = 0; i < 3; i++) plonk_proof_pack(proofs[i], lq, (uint64_t*)proofs_out + (size_t)i * pl);
   });
 }
 extern "C" int cohost_plonk_prove(cohost_plonk_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b, int deterministic,
@@ -1114,6 +1162,7 @@ extern "C" size_t cohost_plonk_proof_limbs(cohost_plonk_zkey* z) { return z ? 18
 extern "C" int cohost_plonk_set_mpc_exchange(cohost_plonk_session* s, int device) {
   if (!s) return fail("cohost_plonk_set_mpc_exchange: null session");
   if (s->net) s->net->device_exchange = device != 0;
+  if (s->snet) s->snet->device_exchange = device != 0;
   return 0;
 }
 extern "C" uint64_t cohost_plonk_launch_count(cohost_plonk_session* s) {
@@ -1150,7 +1199,7 @@ extern "C" int cohost_plonk_profile_read(cohost_plonk_session* s, int cls, doubl
 // Host wall-clock per round of the last proof, seconds: out[party * 5 + round].
 extern "C" int cohost_plonk_round_times(cohost_plonk_session* s, double* out) {
   if (!s || !out) return fail("cohost_plonk_round_times: null argument");
-  for (int i = 0; i < s->parties; i++) memcpy(out + 5 * i, s->round_s[i], 5 * sizeof(double));
+  for (int i = 0; i < s->parties; i++) memcpy(out + 5 * i, s->round_s[i].data(), 5 * sizeof(double));
   return 0;
 }
 // Test hook: keep component a of named intermediate vectors of the next proofs (buffer_z, poly_z, t_evals, tz_evals, t1, t2, t3, poly_r,

@@ -16,6 +16,7 @@
 #include "formats.hpp"
 #include "groth16.hpp"
 #include "plonk_verify.hpp"
+#include "shamir.hpp"
 
 namespace cohost {
 
@@ -149,6 +150,10 @@ template <> struct ShareOps<Rep3Protocol> {
   static FieldShare promote(Rep3Protocol& d, const Fr& v) {  // fieldshare.rs:55-79: (v, 0) / (0, v) / (0, 0)
     return FieldShare{d.id() == 0 ? v : d.fr.zero(), d.id() == 1 ? v : d.fr.zero()};
   }
+};
+
+template <> struct ShareOps<ShamirProtocol> {
+  static FieldShare promote(ShamirProtocol& d, const Fr& v) { return FieldShare{v, d.fr.zero()}; }  // shamir.rs:625-627: every party holds the value
 };
 
 template <class T>

@@ -94,6 +94,9 @@ class ShamirProtocol : public DeviceDriver {
     for (int i = 0; i <= threshold; i++) pts.push_back((id + np - i) % np + 1);  // we send in circles: receive from the previous parties
     open_lagrange_t = lagrange_from_coeff(pts);
     pts.clear();
+    for (int i = 0; i <= 2 * threshold; i++) pts.push_back((id + np - i) % np + 1);  // open of a degree-2t sharing (mul_open, shamir.rs:676-712)
+    open_lagrange_2t = lagrange_from_coeff(pts);
+    pts.clear();
     for (int i = 1; i <= 2 * threshold + 1; i++) pts.push_back(i);
     mul_lagrange_2t = lagrange_from_coeff(pts);
   }
@@ -105,7 +108,7 @@ class ShamirProtocol : public DeviceDriver {
   ShamirNetwork* net;
   uint8_t seed[32];
   uint32_t ctr = 0;
-  std::vector<Fr> open_lagrange_t, mul_lagrange_2t;
+  std::vector<Fr> open_lagrange_t, open_lagrange_2t, mul_lagrange_2t;
   int id() const { return net->get_id(); }
 
   // ---- ShamirCore (shamir/shamir_core.rs)
@@ -408,7 +411,142 @@ class ShamirProtocol : public DeviceDriver {
     return res;
   }
 
+  // ---- CoPlonk (co-plonk/src/round*.rs) driver surface: shamir.rs:459-712, 865-871
+  int pub_comp() const { return 0; }  // add_with_public: every party adds the constant (shamir.rs:471-473)
+  const uint8_t* seed_own() const { return seed; }
+  const uint8_t* seed_prev() const { return seed; }
+  uint32_t take_ctr(uint32_t k) { uint32_t c = ctr; ctr += k; return c; }
+  FieldShareVec alloc_share(size_t n) { return FieldShareVec{alloc(n), DevVec{}}; }
+  std::vector<FieldShare> mul_many(const std::vector<FieldShare>& a, const std::vector<FieldShare>& b) {  // :490-502
+    std::vector<Fr> prod(a.size());
+    for (size_t i = 0; i < a.size(); i++) prod[i] = fr.mul(a[i].a, b[i].a);
+    FieldShareVec red = degree_reduce_vec(upload(prod.data(), prod.size()));
+    download(red.a, prod.data());
+    release(red);
+    std::vector<FieldShare> r(a.size());
+    for (size_t i = 0; i < a.size(); i++) r[i] = FieldShare{prod[i], fr.zero()};
+    return r;
+  }
+  std::vector<Fr> open_many(const std::vector<FieldShare>& a) {  // :581-607
+    std::vector<Fr> mine(a.size());
+    for (size_t i = 0; i < a.size(); i++) mine[i] = a[i].a;
+    auto rcv = net->broadcast_next(mine.data(), mine.size() * 32, threshold + 1);
+    std::vector<Fr> res(a.size(), fr.zero());
+    for (size_t j = 0; j < rcv.size(); j++)
+      for (size_t i = 0; i < a.size(); i++) {
+        Fr s;
+        memcpy(s.l, rcv[j].data() + 32 * i, 32);
+        res[i] = fr.add(res[i], fr.mul(s, open_lagrange_t[j]));
+      }
+    return res;
+  }
+  FieldShareVec rand_vec(size_t n) {  // n x rand(): the degree-t halves of fresh double-random pairs (:570-573)
+    auto pr = get_pairs(n);
+    FieldShareVec o = alloc_share(n);
+    check(ctx, cocg_d2d(ctx, o.a.p, pr.first.p, n * 32), "cocg_d2d");
+    return o;
+  }
+  FieldShareVec reshare(DevVec local) { return degree_reduce_vec(local); }  // a degree-2t local result back to degree t
+  // several independent products, ONE degree reduction (one king round) for all of them
+  std::vector<FieldShareVec> mul_vec_many(const std::vector<std::pair<const FieldShareVec*, const FieldShareVec*>>& ops) {
+    size_t total = 0;
+    for (auto& o : ops) { if (o.first->len() != o.second->len()) throw Error("mul_vec: length mismatch"); total += o.first->len(); }
+    DevVec loc = alloc(total);
+    size_t off = 0;
+    for (auto& o : ops) {
+      check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, o.first->a.p, o.second->a.p, loc.at(off), o.first->len()), "cocg_vec_op");
+      off += o.first->len();
+    }
+    FieldShareVec red = degree_reduce_vec(loc);
+    std::vector<FieldShareVec> r;
+    off = 0;
+    for (auto& o : ops) {
+      r.push_back(FieldShareVec{slice(red.a, off, o.first->len()), DevVec{}});
+      off += o.first->len();
+    }
+    many_owned_.push_back({r.empty() ? nullptr : r[0].a.p, red.a});
+    return r;
+  }
+  void release_many(std::vector<FieldShareVec>& v) {
+    if (!v.empty())
+      for (size_t k = 0; k < many_owned_.size(); k++)
+        if (many_owned_[k].first == v[0].a.p) {
+          release(many_owned_[k].second);
+          many_owned_.erase(many_owned_.begin() + k);
+          break;
+        }
+    v.clear();
+  }
+  // mul_open_many (:684-712): the degree-2t products go to the next 2t parties, each reconstructs from its own and the 2t it receives
+  DevVec mul_open_many(const FieldShareVec& a, const FieldShareVec& b) {
+    const size_t n = a.len();
+    const int np = net->get_num_parties(), me = id(), cnt = 2 * threshold + 1;
+    DevVec mul = alloc(n);
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.a.p, b.a.p, mul.p, n), "cocg_vec_op");
+    for (int s = 1; s < cnt; s++) send_vec((me + s) % np, mul);
+    DevVec res = alloc(n);
+    check(ctx, cocg_vec_axpy(ctx, open_lagrange_2t[0].l, mul.p, nullptr, res.p, n), "cocg_vec_axpy");
+    for (int r = 1; r < cnt; r++) {
+      DevVec v = recv_vec((me + np - r) % np, n, "mul_open_many");
+      check(ctx, cocg_vec_axpy(ctx, open_lagrange_2t[r].l, v.p, res.p, res.p, n), "cocg_vec_axpy");
+      release(v);
+    }
+    release(mul);
+    return res;
+  }
+  void mul_assign_public_vec(FieldShareVec& a, const DevVec& pub) { check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, a.a.p, pub.p, a.a.p, a.len()), "cocg_vec_op"); }
+  FieldShareVec inv_many(const FieldShareVec& a) {  // :521-535
+    FieldShareVec r = rand_vec(a.len());
+    DevVec y = mul_open_many(a, r);
+    pub_inv(y);
+    mul_assign_public_vec(r, y);
+    release(y);
+    return r;
+  }
+  FieldShareVec array_prod_mul(const FieldShareVec& inp) {  // round2.rs:17-42
+    const size_t len = inp.len();
+    FieldShareVec r = rand_vec(len + 1);
+    FieldShareVec r_inv = inv_many(r);
+    Fr h;
+    check(ctx, cocg_d2h(ctx, h.l, r_inv.a.p, 32), "cocg_d2h");
+    FieldShareVec r_inv0 = alloc_share(len);
+    check(ctx, cocg_vec_fill(ctx, r_inv0.a.p, len, h.l), "cocg_vec_fill");
+    const FieldShareVec r_tail = slice(r, 1, len), r_head = slice(r, 0, len), r_inv_tail = slice(r_inv, 1, len);
+    std::vector<FieldShareVec> pr = mul_vec_many({{&r_inv0, &r_tail}, {&r_head, &inp}});
+    DevVec open = mul_open_many(pr[1], r_inv_tail);
+    pub_scan_mul(open);
+    FieldShareVec unblind = alloc_share(len);
+    check(ctx, cocg_vec_op(ctx, COCG_OP_MUL, pr[0].a.p, open.p, unblind.a.p, len), "cocg_vec_op");
+    release(open);
+    release_many(pr);
+    release(r_inv0);
+    release(r);
+    release(r_inv);
+    return unblind;
+  }
+  FieldShare evaluate_poly_public(const FieldShareVec& poly, size_t n, const Fr& point) { return FieldShare{eval_public(poly.a, n, point), fr.zero()}; }  // :865-871
+  std::vector<PointShare> msm_public_points_many(int group, uint64_t bases, size_t n, const std::vector<const FieldShareVec*>& scalars) {
+    const size_t m = scalars.size(), nl = 3 * group * lq;
+    std::vector<const void*> sc(m);
+    for (size_t j = 0; j < m; j++) sc[j] = scalars[j]->a.p;
+    std::vector<uint64_t> packed(m * nl);
+    check(ctx, cocg_msm(ctx, bases, 0, n, sc.data(), (int)m, 1, packed.data()), "cocg_msm");
+    std::vector<PointShare> r(m);
+    for (size_t j = 0; j < m; j++) memcpy(r[j].a.l, packed.data() + j * nl, nl * 8);
+    return r;
+  }
+  std::vector<Point> open_point_many(int g, const std::vector<PointShare>& a) {  // :784-806
+    const size_t nb = 3 * g * lq * 8;
+    std::vector<uint8_t> buf(a.size() * nb);
+    for (size_t j = 0; j < a.size(); j++) memcpy(buf.data() + j * nb, a[j].a.l, nb);
+    auto rcv = net->broadcast_next(buf.data(), buf.size(), threshold + 1);
+    std::vector<Point> r(a.size());
+    for (size_t j = 0; j < a.size(); j++) r[j] = reconstruct_point(g, rcv, j * nb, nb);
+    return r;
+  }
+
  private:
+  std::vector<std::pair<void*, DevVec>> many_owned_;
   void ntt(FieldShareVec& v, const Domain& d, int inverse, const Fr* coset_g) {
     if (v.len() != d.size()) throw Error("fft: vector length != domain size");
     void* vecs[1] = {v.a.p};

@@ -29,7 +29,7 @@ HOST_SYMBOLS = [
     "cohost_split_witness_rep3", "cohost_r1cs_info", "cohost_split_witness_files",
     "cohost_groth16_verify", "cohost_groth16_verify_json", "cohost_plonk_verify_json", "cohost_plonk_zkey_header",
     "cohost_vm_create", "cohost_vm_destroy", "cohost_vm_set_public", "cohost_vm_set_shared", "cohost_vm_run", "cohost_vm_get", "cohost_vm_stats",
-    "cohost_shamir_session_set_shard", "cohost_shamir_set_mpc_exchange", "cohost_rep3_session_create_blocks", "cohost_block_plan", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_destroy",
+    "cohost_shamir_session_set_shard", "cohost_shamir_set_mpc_exchange", "cohost_rep3_session_create_blocks", "cohost_block_plan", "cohost_plonk_zkey_create_synthetic", "cohost_plonk_proof_limbs", "cohost_plonk_session_create", "cohost_plonk_session_create_shamir", "cohost_plonk_session_parties", "cohost_plonk_session_destroy",
     "cohost_plonk_prove", "cohost_plonk_set_mpc_exchange", "cohost_plonk_launch_count", "cohost_plonk_profile_enable",
     "cohost_plonk_profile_reset", "cohost_plonk_profile_read", "cohost_plonk_round_times", "cohost_plonk_trace_enable",
     "cohost_plonk_trace_get", "cohost_plonk_proof_to_json",
@@ -124,6 +124,8 @@ def load_host():
     L.cohost_plonk_proof_limbs.argtypes = [vp]
     L.cohost_plonk_proof_limbs.restype = sz
     L.cohost_plonk_session_create.argtypes = [vp, ci, vp, pvp]
+    L.cohost_plonk_session_create_shamir.argtypes = [vp, ci, ci, vp, pvp]
+    L.cohost_plonk_session_parties.argtypes = [vp]
     L.cohost_plonk_session_destroy.argtypes = [vp]
     L.cohost_plonk_session_destroy.restype = None
     L.cohost_plonk_prove.argtypes = [vp, vp, pvp, pvp, ci, ci, vp]
@@ -695,16 +697,21 @@ class PlonkZKey:
 
 
 class PlonkSession:
-    """CoPlonk::prove: protocol 'plain' (one party) or 'rep3' (three parties on three threads, in-process network)."""
+    """CoPlonk::prove: protocol 'plain' (one party), 'rep3' (three parties on three threads, in-process network) or 'shamir'
+    (num_parties parties, threshold t; one share component per party)."""
 
-    def __init__(self, zkey: PlonkZKey, protocol: str = "plain", seeds: bytes | None = None):
-        _need(protocol in ("plain", "rep3"), "PlonkSession: protocol must be plain or rep3")
-        self.zkey, self.parties = zkey, (1 if protocol == "plain" else 3)
+    def __init__(self, zkey: PlonkZKey, protocol: str = "plain", seeds: bytes | None = None, num_parties: int = 3, threshold: int = 1):
+        _need(protocol in ("plain", "rep3", "shamir"), "PlonkSession: protocol must be plain, rep3 or shamir")
+        self.zkey, self.protocol = zkey, protocol
+        self.parties = 1 if protocol == "plain" else 3 if protocol == "rep3" else num_parties
         seeds = os.urandom(32 * self.parties) if seeds is None else seeds  # blinders and masks derive from these: entropy by default
         _need(len(seeds) == 32 * self.parties, "PlonkSession: seeds must be 32 bytes per party")
         self._seeds = np.frombuffer(seeds, dtype=np.uint8).copy()
         h = vp()
-        _ck(load_host().cohost_plonk_session_create(zkey.h, 0 if protocol == "plain" else 1, self._seeds.ctypes.data, ctypes.byref(h)))
+        if protocol == "shamir":
+            _ck(load_host().cohost_plonk_session_create_shamir(zkey.h, num_parties, threshold, self._seeds.ctypes.data, ctypes.byref(h)))
+        else:
+            _ck(load_host().cohost_plonk_session_create(zkey.h, 0 if protocol == "plain" else 1, self._seeds.ctypes.data, ctypes.byref(h)))
         self.h = h
 
     def prove(self, public_inputs, wit_a, wit_b=None, deterministic=False, device_ptrs=False) -> np.ndarray:
@@ -722,7 +729,9 @@ class PlonkSession:
             keep.append(a)
             return a.ctypes.data
 
-        _need(len(wit_a) == self.parties and (self.parties == 1 or (wit_b is not None and len(wit_b) == 3)), "prove: one share per party")
+        _need(len(wit_a) == self.parties and (self.protocol != "rep3" or (wit_b is not None and len(wit_b) == 3)), "prove: one share per party")
+        if self.protocol != "rep3":
+            wit_b = None
         A = (vp * self.parties)(*[addr(x) for x in wit_a])
         B = None if wit_b is None else (vp * self.parties)(*[addr(x) for x in wit_b])
         out = np.zeros((self.parties, zk.proof_limbs), dtype=np.uint64)
@@ -751,9 +760,9 @@ class PlonkSession:
         return out
 
     def round_times(self) -> np.ndarray:
-        out = (ctypes.c_double * 15)()
+        out = (ctypes.c_double * (5 * self.parties))()
         _ck(load_host().cohost_plonk_round_times(self.h, out))
-        return np.array(out).reshape(3, 5)[:self.parties]
+        return np.array(out).reshape(self.parties, 5)
 
     def trace(self, on: bool = True):
         _ck(load_host().cohost_plonk_trace_enable(self.h, 1 if on else 0))

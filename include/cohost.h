@@ -161,6 +161,10 @@ COHOST_API void cohost_plonk_zkey_destroy(cohost_plonk_zkey* z);
 COHOST_API int cohost_plonk_zkey_get_info(cohost_plonk_zkey* z, size_t* info);
 COHOST_API size_t cohost_plonk_proof_limbs(cohost_plonk_zkey* z);
 COHOST_API int cohost_plonk_session_create(cohost_plonk_zkey* z, int protocol, const uint8_t* seeds, cohost_plonk_session** out);
+/* CoPlonk over Shamir (num_parties, threshold) shares -- co-plonk is generic over the MPC protocol (co-plonk/src/plonk.rs:50-77); the
+ * driver surface is mpc-core/src/protocols/shamir.rs:459-712.  seeds: num_parties x 32 bytes; prove() takes one share per party in wit_a. */
+COHOST_API int cohost_plonk_session_create_shamir(cohost_plonk_zkey* z, int num_parties, int threshold, const uint8_t* seeds, cohost_plonk_session** out);
+COHOST_API int cohost_plonk_session_parties(cohost_plonk_session* s);
 COHOST_API void cohost_plonk_session_destroy(cohost_plonk_session* s);
 COHOST_API int cohost_plonk_prove(cohost_plonk_session* s, const void* public_inputs, const void* const* wit_a, const void* const* wit_b,
                                   int deterministic, int wit_on_device, void* proofs_out);

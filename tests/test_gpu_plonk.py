@@ -142,6 +142,69 @@ def test_plonk_random_blinders_verify(cocg, tmp_path, curve, circ):
     zk.close()
 
 
+def _shamir_shares(c, wit, n, t, seed):
+    """shamir/utils share_field_elements: party i holds p(i + 1), p random of degree t with p(0) = value."""
+    rng = random.Random(seed)
+    out = [[] for _ in range(n)]
+    for v in wit:
+        coeffs = [rng.randrange(c.r) for _ in range(t)]
+        for p in range(n):
+            out[p].append((v + sum(cf * pow(p + 1, k + 1, c.r) for k, cf in enumerate(coeffs))) % c.r)
+    return [cref.fr_to_mont(c, o) for o in out]
+
+
+@pytest.mark.parametrize("n,t", [(3, 1), (5, 2), (4, 1)])
+def test_plonk_shamir_reproduces_reference_round_kats(cocg, tmp_path, n, t):
+    """CoPlonk<ShamirProtocol> (co-plonk is generic over the MPC protocol, plonk.rs:50-77; driver mpc-core/src/protocols/shamir.rs):
+    with the deterministic blinders every party of a (n, t) sharing outputs the reference's round KATs literally."""
+    path, ozk, wt = _full_fixture("bn254", "multiplier2", tmp_path)
+    c = ozk.curve
+    k1 = json.load(open(os.path.join(G, "plonk_round1_kats.json")))["bn254/multiplier2"]
+    kat = json.load(open(os.path.join(G, "plonk_round2_kats.json")))
+    pt = lambda v: (int(v[0]), int(v[1]))
+    want = {"A": pt(k1["commit_a"]), "B": pt(k1["commit_b"]), "C": pt(k1["commit_c"]), "Z": pt(kat["commit_z"]),
+            "T1": pt(kat["commit_t"][0]), "T2": pt(kat["commit_t"][1]), "T3": pt(kat["commit_t"][2]),
+            "Wxi": pt(kat["commit_w"][0]), "Wxiw": pt(kat["commit_w"][1])}
+    want.update({k: int(v) for k, v in kat["evals"].items()})
+    zk = cocg.PlonkZKey(path)
+    ell = zk.n_public
+    pub = cref.fr_to_mont(c, wt[:ell + 1])
+    wit = [v % c.r for v in wt[ell + 1:]]
+    sh = cocg.PlonkSession(zk, "shamir", seeds=bytes(range(32 * n)), num_parties=n, threshold=t)
+    for mode in ("host", "device"):
+        sh.set_mpc_exchange(mode)
+        out = sh.prove(pub, _shamir_shares(c, wit, n, t, 9), deterministic=True)
+        for party in range(n):
+            assert _proof_dict(c, zk, out[party]) == want, (mode, party)
+    sh.close()
+    zk.close()
+
+
+@pytest.mark.parametrize("curve,circ,n,t", [("bn254", "poseidon", 3, 1), ("bls12_381", "multiplier2", 5, 2)])
+def test_plonk_shamir_random_blinders_verify(cocg, tmp_path, curve, circ, n, t):
+    """Random blinders (degree-t halves of the double-random pairs): all parties open the same proof, it verifies, a second proof differs."""
+    path, ozk, wt = _full_fixture(curve, circ, tmp_path)
+    c = ozk.curve
+    d = os.path.join(G, "plonk", curve, circ)
+    vk = open(os.path.join(d, "verification_key.json")).read()
+    public = json.load(open(os.path.join(d, "public.json")))
+    zk = cocg.PlonkZKey(path)
+    ell = zk.n_public
+    pub = cref.fr_to_mont(c, wt[:ell + 1])
+    wit = [v % c.r for v in wt[ell + 1:]]
+    sh = cocg.PlonkSession(zk, "shamir", num_parties=n, threshold=t)
+    shares = _shamir_shares(c, wit, n, t, 10)
+    prev = None
+    for _ in range(2):
+        out = sh.prove(pub, shares)
+        assert all(np.array_equal(out[0], out[i]) for i in range(1, n))
+        assert cocg.plonk_verify_json(vk, cocg.plonk_proof_to_json(zk.curve, out[0]), json.dumps(public)) is True
+        assert prev is None or not np.array_equal(prev, out[0])
+        prev = out[0]
+    sh.close()
+    zk.close()
+
+
 def test_plonk_poseidon_intermediates_match_oracle(cocg, tmp_path):
     """n = 4096, 2228 additions (multi-block scans, multi-pass NTTs): every intermediate vector of rounds 2-5 -- the rotated grand
     product, z(X), the quotient evaluations t / tz on the 4n domain, t1 t2 t3, r(X), W_xi -- equals the oracle's (which reproduces the
