@@ -381,30 +381,41 @@ struct ReduceSets {
   uint32_t slot[kMaxSets];  // result slot (kResultSlot bytes each) of every set
 };
 static inline uint32_t marg_stride(uint32_t nmarg) { return nmarg + (nmarg + 31) / 32 + 2; }  // partial marginals | weighted warp sums
+// The 32 lane sums of a marginal are folded through SHARED memory, not by a shuffle tree: slot = lane * 4 + warp, so that level
+// after level the surviving additions sit in whole warps (2, 1, 1, 1, 1 warp-additions per block instead of 5 x 4 with 16, 8, 4, 2, 1
+// lanes active -- the tree was 24 % of the kernel's issue slots, profiles/r01_ncu_msm_marginals*).
 template <class F>
 __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
                                                              XYZZ<F>* __restrict__ out, uint32_t mstride) {
+  __shared__ __align__(16) unsigned char fold_raw[128 * sizeof(XYZZ<F>)];
+  XYZZ<F>* fold = reinterpret_cast<XYZZ<F>*>(fold_raw);
   const uint32_t H = 1u << logH, L = 1u << logL;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= H + L * kColSeg) return;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * 4 + wib;
+  const uint32_t nmarg = H + L * kColSeg;
   buckets += (size_t)blockIdx.y << (logH + logL);
   out += (size_t)blockIdx.y * mstride;
   XYZZ<F> acc = xyzz_inf<F>();
   if (warp < H) {
     const XYZZ<F>* r = buckets + ((size_t)warp << logL);
     for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add_inline(acc, r[lo]);
-  } else {
+  } else if (warp < nmarg) {
     const uint32_t w = warp - H;
     const uint32_t col = w / kColSeg, seg = w % kColSeg;
     const uint32_t hi0 = (uint32_t)((uint64_t)seg * H / kColSeg), hi1 = (uint32_t)((uint64_t)(seg + 1) * H / kColSeg);
     for (uint32_t hi = hi0 + lane; hi < hi1; hi += 32) xyzz_add_inline(acc, buckets[((size_t)hi << logL) + col]);
   }
-  for (int delta = 16; delta >= 1; delta >>= 1) {
-    XYZZ<F> other = warp_shfl_down(acc, delta);
-    if (lane < (uint32_t)delta) xyzz_add(acc, other);
+  fold[lane * 4 + wib] = acc;
+  __syncthreads();
+  for (uint32_t active = 64; active >= 4; active >>= 1) {
+    if (threadIdx.x < active) {
+      XYZZ<F> a = fold[threadIdx.x];
+      xyzz_add(a, fold[threadIdx.x + active]);
+      fold[threadIdx.x] = a;
+    }
+    __syncthreads();
   }
-  if (lane == 0) out[warp] = acc;
+  if (threadIdx.x < 4 && blockIdx.x * 4 + threadIdx.x < nmarg) out[blockIdx.x * 4 + threadIdx.x] = fold[threadIdx.x];
 }
 // weights: one THREAD per partial marginal (all lanes busy, unlike a multiply on the reducing lane), then a warp tree
 template <class F>
@@ -546,7 +557,7 @@ int msm_reduce_impl(cocg_ctx* ctx, int group, int c, const ReduceSets& sets, voi
   COCG_TRY(scratch_get(ctx, 8, (size_t)sets.n * mstride * sizeof(X), &p)); marg = (X*)p;
   cudaStream_t st = ctx->stream;
   ProfScope prof(ctx, COCG_PROF_MSM_REDUCE);
-  msm_marginals_kernel<F><<<dim3((nmarg * 32 + 127) / 128, sets.n), 128, 0, st>>>(buckets, logH, logL, marg, mstride);
+  msm_marginals_kernel<F><<<dim3((nmarg + 3) / 4, sets.n), 128, 0, st>>>(buckets, logH, logL, marg, mstride);
   COCG_LAUNCH_CHECK(ctx);
   const uint32_t nwarps = (nmarg + 31) / 32;
   msm_weigh_kernel<F><<<dim3((nmarg + 127) / 128, sets.n), 128, 0, st>>>(marg, logH, logL, marg + nmarg, mstride);

@@ -18,15 +18,23 @@
 //     store, which makes the transform in-order without a separate permutation pass.
 // Twiddles come from one table w^k, k < n/2, cached per (n, w) in HBM and hot in L2.
 // Data moves data -> scratch (pass 0) -> ... -> data (last pass): 32*n bytes read + written per pass.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.cuh"
 
 namespace cocg {
 
-constexpr int kNttMaxStages = 8;    // stages per pass
+#ifndef COCG_NTT_CALL
+#define COCG_NTT_CALL __forceinline__
+#endif
+#ifndef COCG_NTT_MIN_BLOCKS
+#define COCG_NTT_MIN_BLOCKS 4
+#endif
+constexpr int kNttMaxStages = 8;    // stages per pass (COCG_NTT_MAX_STAGES overrides, <= 10)
 constexpr int kNttTile = 1024;      // elements per CTA tile
-constexpr int kNttThreads = 256;
+constexpr int kNttThreads = 128;    // one thread per 8 tile elements: a radix-8 round keeps every thread busy
+constexpr int kNttMaxLogC = 4;      // columns per tile: global runs of up to 16 x 32 B
 constexpr int kNttMaxVecs = 8;
 
 struct NttVecs {
@@ -36,8 +44,142 @@ struct NttVecs {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return bits == 0 ? 0u : (__brev(x) >> (32 - bits)); }
 
+// The product is CALLED (operands and result in registers): a radix-8 round holds 12 of them, inlined they are ~50 KB of SASS per
+// round shape and the instruction cache, not the multiplier, sets the pace (the same effect as in plonk.cu).
+template <class P>
+__device__ COCG_NTT_CALL Fp<P> ntt_fmul(Fp<P> a, Fp<P> b) { return fp_mul(a, b); }
+// two independent products per call: the two carry chains interleave inside the callee (one chain per warp leaves the multiplier
+// waiting on its own latency at the 12-16 warps per SM this kernel's register budget allows)
+template <class P>
+struct FpPair {
+  Fp<P> a, b;
+};
+template <class P>
+__device__ COCG_NTT_CALL FpPair<P> ntt_fmul2(Fp<P> a, Fp<P> wa, Fp<P> b, Fp<P> wb) {
+  FpPair<P> r;
+  r.a = fp_mul(a, wa);
+  r.b = fp_mul(b, wb);
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> lds_fp(const uint4* plane_lo, const uint4* plane_hi, int m) {
+  const uint4 lo = plane_lo[m], hi = plane_hi[m];
+  Fp<P> x;
+  x.l[0] = lo.x; x.l[1] = lo.y; x.l[2] = lo.z; x.l[3] = lo.w; x.l[4] = hi.x; x.l[5] = hi.y; x.l[6] = hi.z; x.l[7] = hi.w;
+  return x;
+}
+template <class P>
+__device__ __forceinline__ void sts_fp(uint4* plane_lo, uint4* plane_hi, int m, const Fp<P>& x) {
+  plane_lo[m] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+  plane_hi[m] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+}
+
+// The twiddles of a round are known before its input is: their cache lines are requested (prefetch.global.L1, no registers) before the
+// barrier the round waits on, so the loads inside the round hit L1 instead of stalling on L2 / DRAM (ncu: long_scoreboard was the
+// second stall reason; the first stage of pass 0 reads n/2 distinct twiddles, one per butterfly).
+template <class P, int G, bool LAST>
+__device__ __forceinline__ void ntt_prefetch_twiddles(int tile_elems, int s, int logC, int kk, int k0, int L, int logQ, uint32_t col0,
+                                                      const void* __restrict__ tw) {
+  const int C = 1 << logC;
+  const int d = s - kk - G;
+  const int items = tile_elems >> G;
+  for (int it = threadIdx.x; it < items; it += kNttThreads) {
+    const int c = it & (C - 1);
+    const int low = (it >> logC) & ((1 << d) - 1);
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      const int k = k0 + kk + t;
+      if (k == L - 1) continue;
+#pragma unroll
+      for (int q = 0; q < (1 << (G - 1 - t)); q++) {
+        const int lo_i = (q << d) + low;
+        const size_t ex = LAST ? (size_t)lo_i : (((size_t)lo_i << logQ) + col0 + c);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)tw + ((ex << k) * sizeof(Fp<P>))));
+      }
+    }
+  }
+}
 template <class P, bool LAST>
-__global__ void __launch_bounds__(kNttThreads) ntt_pass_kernel(NttVecs vecs, int L, int k0, int s, int logC,
+__device__ __forceinline__ void ntt_prefetch_round(int g, int tile_elems, int s, int logC, int kk, int k0, int L, int logQ, uint32_t col0,
+                                                   const void* __restrict__ tw) {
+  if (g == 3) ntt_prefetch_twiddles<P, 3, LAST>(tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+  else if (g == 2) ntt_prefetch_twiddles<P, 2, LAST>(tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+  else if (g == 1) ntt_prefetch_twiddles<P, 1, LAST>(tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+}
+// stages of the round that starts at local stage kk: 3 while more than 4 remain (or exactly 3), else 2, else 1 -- 2, 2 instead of 3, 1
+__device__ __forceinline__ int ntt_round_stages(int s, int kk) {
+  const int rem = s - kk;
+  return rem <= 0 ? 0 : (rem > 4 || rem == 3) ? 3 : rem >= 2 ? 2 : 1;
+}
+
+// One round = G consecutive butterfly stages (local stages kk .. kk+G-1 of the pass) on 2^G elements held in REGISTERS: the tile is
+// read and written once per round instead of once per stage, one barrier per round, 2^G - 1 twiddle loads per 2^G elements.
+// DIF stage: (x, y) -> (x + y, (x - y) * w^((e mod 2^logh) * Q' << k)).  The 2^G elements of a work item differ in bits
+// d .. d+G-1 of the group index e (d = s - kk - G); stage t pairs elements whose j differ in bit G-1-t.
+template <class P, int G, bool LAST>
+__device__ __forceinline__ void ntt_round(uint4* plane_lo, uint4* plane_hi, int tile_elems, int s, int logC, int kk, int k0, int L, int logQ,
+                                          uint32_t col0, const void* __restrict__ tw) {
+  constexpr int R = 1 << G;
+  const int C = 1 << logC;
+  const int d = s - kk - G;
+  const int items = tile_elems >> G;
+  for (int it = threadIdx.x; it < items; it += kNttThreads) {
+    const int c = it & (C - 1);
+    const int p = it >> logC;
+    const int low = p & ((1 << d) - 1);
+    const int e_base = ((p >> d) << (d + G)) + low;
+    Fp<P> x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) x[j] = lds_fp<P>(plane_lo, plane_hi, ((e_base + (j << d)) << logC) + c);
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      const int k = k0 + kk + t;
+      constexpr int kPairs = R / 2;
+      const int half = 1 << (G - 1 - t);
+      const bool unit = (k == L - 1);  // last global stage: every twiddle is 1
+      // butterfly b of this stage: q = b mod half (position below the pairing bit -> its twiddle), elements j = (b / half) * 2 half + q, j + half
+      Fp<P> wa, wb;           // the (at most two) twiddles in use; reloaded only when the pair of butterflies needs other ones
+      int held_a = -1, held_b = -1;  // compile-time after unrolling
+      auto twiddle = [&](int q) {
+        const int lo_i = (q << d) + low;
+        const size_t ex = LAST ? (size_t)lo_i : (((size_t)lo_i << logQ) + col0 + c);
+        return load_fp_ro<P>(tw, ex << k);
+      };
+#pragma unroll
+      for (int b = 0; b < kPairs; b += 2) {
+        const int q0 = b & (half - 1), j0 = ((b & ~(half - 1)) << 1) + q0;
+        if (!unit && held_a != q0) { wa = twiddle(q0); held_a = q0; }
+        if (kPairs == 1) {
+          const Fp<P> u = fp_add(x[j0], x[j0 + half]);
+          Fp<P> v = fp_sub(x[j0], x[j0 + half]);
+          if (!unit) v = ntt_fmul<P>(v, wa);
+          x[j0] = u;
+          x[j0 + half] = v;
+        } else {
+          const int b1 = b + 1, q1 = b1 & (half - 1), j1 = ((b1 & ~(half - 1)) << 1) + q1;
+          if (!unit && q1 != q0 && held_b != q1) { wb = twiddle(q1); held_b = q1; }
+          const Fp<P> u0 = fp_add(x[j0], x[j0 + half]), u1 = fp_add(x[j1], x[j1 + half]);
+          Fp<P> v0 = fp_sub(x[j0], x[j0 + half]), v1 = fp_sub(x[j1], x[j1 + half]);
+          if (!unit) {
+            const FpPair<P> pr = ntt_fmul2<P>(v0, wa, v1, q1 != q0 ? wb : wa);
+            v0 = pr.a;
+            v1 = pr.b;
+          }
+          x[j0] = u0; x[j0 + half] = v0;
+          x[j1] = u1; x[j1 + half] = v1;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) sts_fp<P>(plane_lo, plane_hi, ((e_base + (j << d)) << logC) + c, x[j]);
+  }
+  ntt_prefetch_round<P, LAST>(ntt_round_stages(s, kk + G), tile_elems, s, logC, kk + G, k0, L, logQ, col0, tw);
+  __syncthreads();
+}
+
+template <class P, bool LAST>
+__global__ void __launch_bounds__(kNttThreads, COCG_NTT_MIN_BLOCKS) ntt_pass_kernel(NttVecs vecs, int L, int k0, int s, int logC,
                                                                 const void* __restrict__ tw, const void* __restrict__ pre,
                                                                 const void* __restrict__ post, Fp<P> post_const, int use_post_const) {
   __shared__ uint4 plane_lo[kNttTile];
@@ -68,6 +210,8 @@ __global__ void __launch_bounds__(kNttThreads) ntt_pass_kernel(NttVecs vecs, int
     stride_c = ((size_t)1 << (L - s - logC)) << s;
   }
 
+  ntt_prefetch_round<P, LAST>(ntt_round_stages(s, 0), tile_elems, s, logC, 0, k0, L, logQ, col0, tw);
+
   // ---- load (optionally pre-scaled by pre[global index])
   for (int t = threadIdx.x; t < tile_elems; t += kNttThreads) {
     int e, c;
@@ -77,7 +221,7 @@ __global__ void __launch_bounds__(kNttThreads) ntt_pass_kernel(NttVecs vecs, int
     if (pre) {
       Fp<P> x;
       x.l[0] = lo.x; x.l[1] = lo.y; x.l[2] = lo.z; x.l[3] = lo.w; x.l[4] = hi.x; x.l[5] = hi.y; x.l[6] = hi.z; x.l[7] = hi.w;
-      x = fp_mul(x, load_fp_ro<P>(pre, g));
+      x = ntt_fmul<P>(x, load_fp_ro<P>(pre, g));
       lo = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
       hi = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
     }
@@ -87,36 +231,11 @@ __global__ void __launch_bounds__(kNttThreads) ntt_pass_kernel(NttVecs vecs, int
   }
   __syncthreads();
 
-  // ---- s butterfly stages: (x, y) -> (x + y, (x - y) * w^((j mod 2^(L-1-k)) * 2^k))
-  const int nbf = tile_elems >> 1;
-  for (int kk = 0; kk < s; kk++) {
-    const int k = k0 + kk;
-    const int logh = s - 1 - kk;
-    const bool unit = (k == L - 1);  // last global stage: twiddle is 1
-    for (int b = threadIdx.x; b < nbf; b += kNttThreads) {
-      int c = b & (C - 1);
-      int p = b >> logC;
-      int lo_i = p & ((1 << logh) - 1);
-      int hi_i = p >> logh;
-      int e0 = (hi_i << (logh + 1)) + lo_i;
-      int m0 = (e0 << logC) + c;
-      int m1 = m0 + ((1 << logh) << logC);
-      uint4 xl = plane_lo[m0], xh = plane_hi[m0], yl = plane_lo[m1], yh = plane_hi[m1];
-      Fp<P> x, y;
-      x.l[0] = xl.x; x.l[1] = xl.y; x.l[2] = xl.z; x.l[3] = xl.w; x.l[4] = xh.x; x.l[5] = xh.y; x.l[6] = xh.z; x.l[7] = xh.w;
-      y.l[0] = yl.x; y.l[1] = yl.y; y.l[2] = yl.z; y.l[3] = yl.w; y.l[4] = yh.x; y.l[5] = yh.y; y.l[6] = yh.z; y.l[7] = yh.w;
-      Fp<P> u = fp_add(x, y);
-      Fp<P> v = fp_sub(x, y);
-      if (!unit) {
-        size_t ex = LAST ? (size_t)lo_i : (((size_t)lo_i << logQ) + col0 + c);
-        v = fp_mul(v, load_fp_ro<P>(tw, ex << k));
-      }
-      plane_lo[m0] = make_uint4(u.l[0], u.l[1], u.l[2], u.l[3]);
-      plane_hi[m0] = make_uint4(u.l[4], u.l[5], u.l[6], u.l[7]);
-      plane_lo[m1] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-      plane_hi[m1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-    }
-    __syncthreads();
+  // ---- s butterfly stages in register rounds
+  for (int kk = 0, g; (g = ntt_round_stages(s, kk)) != 0; kk += g) {
+    if (g == 3) ntt_round<P, 3, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+    else if (g == 2) ntt_round<P, 2, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+    else ntt_round<P, 1, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
   }
 
   // ---- store
@@ -143,7 +262,7 @@ __global__ void __launch_bounds__(kNttThreads) ntt_pass_kernel(NttVecs vecs, int
       if (post || use_post_const) {
         Fp<P> x;
         x.l[0] = lo.x; x.l[1] = lo.y; x.l[2] = lo.z; x.l[3] = lo.w; x.l[4] = hi.x; x.l[5] = hi.y; x.l[6] = hi.z; x.l[7] = hi.w;
-        x = fp_mul(x, post ? load_fp_ro<P>(post, i) : post_const);
+        x = ntt_fmul<P>(x, post ? load_fp_ro<P>(post, i) : post_const);
         lo = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
         hi = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
       }
@@ -183,7 +302,12 @@ static int ntt_impl(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, con
   int use_post_const = (inverse && !coset_g) ? 1 : 0;
 
   // pass plan
-  int np = (L + kNttMaxStages - 1) / kNttMaxStages;
+  static const int max_stages = [] {
+    const char* e = getenv("COCG_NTT_MAX_STAGES");
+    int v = e ? atoi(e) : kNttMaxStages;
+    return v < 1 ? 1 : v > 10 ? 10 : v;
+  }();
+  int np = (L + max_stages - 1) / max_stages;
   int sbase = L / np, extra = L % np;
   void* scratch = nullptr;
   if (np > 1) COCG_TRY(scratch_get(ctx, 0, (size_t)k * n * sizeof(F), &scratch));
@@ -193,8 +317,8 @@ static int ntt_impl(cocg_ctx* ctx, void* const* vecs, int k, unsigned log_n, con
     int s = sbase + (p < extra ? 1 : 0);
     bool last = (p == np - 1);
     int logC = 0;
-    if (!last) { logC = L - k0 - s; if (logC > 2) logC = 2; }
-    else { logC = L - s; if (logC > 2) logC = 2; }
+    if (!last) { logC = L - k0 - s; if (logC > kNttMaxLogC) logC = kNttMaxLogC; }
+    else { logC = L - s; if (logC > kNttMaxLogC) logC = kNttMaxLogC; }
     while ((1 << (s + logC)) > kNttTile) logC--;
     for (int v0 = 0; v0 < k; v0 += kNttMaxVecs) {
       int kv = k - v0 < kNttMaxVecs ? k - v0 : kNttMaxVecs;

@@ -146,3 +146,20 @@ def test_plonk_files_to_verified_proof(cocg, tmp_path):
     with pytest.raises(SystemExit) as e:
         cli.main(["verify", "plonk", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", bad_pub, "--curve", "BN254"])
     assert e.value.code == 1
+
+
+def test_plonk_shamir_files_to_verified_proof(cocg, tmp_path):
+    """The same flow over Shamir (5, 2) share files (`--protocol SHAMIR -t 2 -n 5`, co-circom.rs:455-636)."""
+    d = os.path.join(G, "plonk", "bn254", "multiplier2")
+    cli = _cli()
+    cli.main(["split-witness", "--witness", os.path.join(d, "witness.wtns"), "--r1cs", os.path.join(d, "circuit.r1cs"), "--protocol", "SHAMIR",
+              "--curve", "BN254", "--out-dir", str(tmp_path), "-t", "2", "-n", "5"])
+    shares = [str(tmp_path / f"witness.wtns.{i}.shared") for i in range(5)]
+    out, pub_out = str(tmp_path / "proof.json"), str(tmp_path / "public.json")
+    cli.main(["generate-proof", "plonk", "--witness", *shares, "--zkey", os.path.join(d, "circuit.zkey"), "--protocol", "SHAMIR", "-t", "2",
+              "--curve", "BN254", "--out", out, "--public-input", pub_out])
+    assert json.load(open(pub_out)) == json.load(open(os.path.join(d, "public.json")))
+    cli.main(["verify", "plonk", "--proof", out, "--vk", os.path.join(d, "verification_key.json"), "--public-input", pub_out, "--curve", "BN254"])
+    with pytest.raises(SystemExit, match="n > 2t"):
+        cli.main(["generate-proof", "plonk", "--witness", *shares[:4], "--zkey", os.path.join(d, "circuit.zkey"), "--protocol", "SHAMIR", "-t", "2",
+                  "--curve", "BN254", "--out", out])

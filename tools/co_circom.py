@@ -33,17 +33,20 @@ def split_witness(a):
 
 
 def generate_proof_plonk(a):
-    """CoPlonk::prove over three REP3 parties (co-circom.rs:455-636 with proof system plonk)."""
-    if a.protocol != "REP3" or len(a.witness) != 3:
-        sys.exit("plonk: REP3 with the three parties' share files (one process plays all three parties)")
+    """CoPlonk::prove over three REP3 parties or n Shamir parties (co-circom.rs:455-636 with proof system plonk)."""
+    rep3 = a.protocol == "REP3"
+    if rep3 and len(a.witness) != 3:
+        sys.exit("REP3 needs the three parties' share files (one process plays all three parties)")
+    if not rep3 and len(a.witness) <= 2 * a.threshold:
+        sys.exit("Shamir needs the share files of all n > 2t parties (one process plays all of them)")
     curve = CURVES[a.curve]
     zk = cocg.PlonkZKey(a.zkey)
     pubs, wa, wb = [], [], []
     for path in a.witness:
-        pub, comps = cocg.shared_witness_decode(curve, open(path, "rb").read(), 2)
+        pub, comps = cocg.shared_witness_decode(curve, open(path, "rb").read(), 2 if rep3 else 1)
         pubs.append(pub)
         wa.append(comps[0])
-        wb.append(comps[1])
+        wb.append(comps[-1])
     if any(p.shape != pubs[0].shape or not (p == pubs[0]).all() for p in pubs[1:]):
         sys.exit("the share files disagree on the public inputs")
     # a SharedWitness of the Groth16 flow carries every signal after the public ones; the Plonk prover reads the first
@@ -51,8 +54,12 @@ def generate_proof_plonk(a):
     need = zk.n_witness
     if any(x.shape[0] < need for x in wa + wb):
         sys.exit("the share files hold fewer witness elements than the zkey expects")
-    sess = cocg.PlonkSession(zk, "rep3", seeds=os.urandom(96))
-    proofs = sess.prove(pubs[0], [x[:need] for x in wa], [x[:need] for x in wb])
+    if rep3:
+        sess = cocg.PlonkSession(zk, "rep3", seeds=os.urandom(96))
+        proofs = sess.prove(pubs[0], [x[:need] for x in wa], [x[:need] for x in wb])
+    else:
+        sess = cocg.PlonkSession(zk, "shamir", seeds=os.urandom(32 * len(a.witness)), num_parties=len(a.witness), threshold=a.threshold)
+        proofs = sess.prove(pubs[0], [x[:need] for x in wa])
     if any(not (p == proofs[0]).all() for p in proofs[1:]):
         sys.exit("the parties opened different proofs")
     with open(a.out, "w") as f:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Short workloads for `ncu --set full -k regex:<kernel>` captures (B200_PROFILING.md): each mode launches the named kernels a few
 times at the benchmark's size and nothing else heavy.
-  python tools/ncu_targets.py msm_g1 | msm_g2 | ntt | plonk"""
+  python tools/ncu_targets.py msm_g1 | msm_g2 | msm_multi | ntt | plonk"""
 import os
 import sys
 
@@ -20,6 +20,13 @@ if mode in ("msm_g1", "msm_g2"):
     s = ctx.upload(bench.rand_fr(n, rng))
     for _ in range(3):
         ctx.msm(h, [s])
+elif mode == "msm_multi":  # the Groth16 aux shape: 3 G1 queries + 1 G2 query x 2 share components, one call
+    ctx = cocg.Context(cocg.BN254, 0)
+    n = 1 << 20
+    hs = [ctx.bases_generate(1, n, bytes([10 + i] * 32)) for i in range(3)] + [ctx.bases_generate(2, n, bytes([13] * 32))]
+    sc = [ctx.upload(bench.rand_fr(n, rng)) for _ in range(2)]
+    for _ in range(2):
+        ctx.msm_multi(hs, [0, 0, 0, 0], sc)
 elif mode == "ntt":
     from oracle import ntt as ontt, cref
     from oracle.curves import BN254
