@@ -287,6 +287,81 @@ constexpr int kAccumulateThreads = 128;
 // After the Fq2 product became a call (ec.cuh) the BN254 G2 instantiation is occupancy-limited rather than fetch-limited: capping it at
 // 128 registers (4 blocks per SM, 456 B of L1-resident spills) measured 7.01 -> 6.52 ms at 2^20 terms; 3 blocks 6.67, 5 blocks 6.82.
 template <class F> constexpr int kAccumulateMinBlocks = sizeof(F) == 64 ? 4 : 1;
+// Fq2 (BN254 G2): the bucket accumulator lives in SHARED memory, 16 B words interleaved over the block's threads (conflict-free),
+// and each coordinate is read where it is used and written back as soon as its new value exists.  In registers the accumulator is
+// 64 of the 128 the 4-blocks-per-SM cap allows, the Fq2 product is a call that values cannot be moved across, and ptxas answered
+// with 456 B of spills per thread (ncu: ~0.95 GB of spill traffic reaching DRAM per 2^20-term launch).
+template <class F> constexpr int kAccSmemWords = sizeof(F) == 64 ? (int)(sizeof(XYZZ<F>) / 16) * kAccumulateThreads : 1;
+template <class F>
+__device__ __forceinline__ F sm_get(const uint4* sm, int comp) {  // coordinate `comp` (0 X, 1 Y, 2 ZZ, 3 ZZZ) of this thread's accumulator
+  constexpr int W = sizeof(F) / 16;
+  F r;
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < W; k++) {
+    const uint4 v = sm[(comp * W + k) * kAccumulateThreads + threadIdx.x];
+    d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+  }
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void sm_put(uint4* sm, int comp, const F& x) {
+  constexpr int W = sizeof(F) / 16;
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(&x);
+#pragma unroll
+  for (int k = 0; k < W; k++) sm[(comp * W + k) * kAccumulateThreads + threadIdx.x] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+}
+// acc += q with the accumulator in shared memory (the formulas and the special cases of xyzz_madd, ec.cuh); inf = accumulator is O
+template <class F>
+__device__ __forceinline__ void xyzz_madd_sm(uint4* sm, bool& inf, const Affine<F>& q) {
+  if (q.is_inf()) return;
+  if (inf) {
+    sm_put<F>(sm, 0, q.x); sm_put<F>(sm, 1, q.y); sm_put<F>(sm, 2, F::one()); sm_put<F>(sm, 3, F::one());
+    inf = false;
+    return;
+  }
+  const F Pd = f_sub(f_mul(q.x, sm_get<F>(sm, 2)), sm_get<F>(sm, 0));
+  const F R = f_sub(f_mul(q.y, sm_get<F>(sm, 3)), sm_get<F>(sm, 1));
+  if (Pd.is_zero()) {
+    if (R.is_zero()) {
+      const XYZZ<F> d = xyzz_dbl_affine(q);
+      sm_put<F>(sm, 0, d.x); sm_put<F>(sm, 1, d.y); sm_put<F>(sm, 2, d.zz); sm_put<F>(sm, 3, d.zzz);
+    } else {
+      inf = true;
+    }
+    return;
+  }
+  const F PP = f_sqr(Pd);
+  sm_put<F>(sm, 2, f_mul(sm_get<F>(sm, 2), PP));
+  const F Q = f_mul(sm_get<F>(sm, 0), PP);
+  const F PPP = f_mul(Pd, PP);
+  sm_put<F>(sm, 3, f_mul(sm_get<F>(sm, 3), PPP));
+  const F T = f_mul(sm_get<F>(sm, 1), PPP);
+  const F X3 = f_sub(f_sub(f_sqr(R), PPP), f_dbl(Q));
+  sm_put<F>(sm, 0, X3);
+  sm_put<F>(sm, 1, f_sub(f_mul(R, f_sub(Q, X3)), T));
+}
+template <class F>
+__device__ __forceinline__ void accumulate_run_sm(uint4* sm, bool& inf, const void* table, size_t tstride, const uint32_t* sorted, uint32_t beg,
+                                                  uint32_t end) {
+  auto entry_index = [&](uint32_t v) { return (size_t)((v >> kIdxBits) & 63u) * tstride + (v & ((1u << kIdxBits) - 1)); };
+  if (beg >= end) return;
+  uint32_t v = sorted[beg];
+  for (uint32_t e = beg; e < end; e++) {
+    const size_t idx = entry_index(v);
+    uint32_t vn = 0;
+    if (e + 1 < end) {
+      vn = sorted[e + 1];
+      const char* nxt = reinterpret_cast<const char*>(table) + entry_index(vn) * sizeof(Affine<F>);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+      if (128 % sizeof(Affine<F>) != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + sizeof(Affine<F>) - 16));
+    }
+    Affine<F> p = load_affine<F>(table, idx);
+    if (v >> 31) p.y = f_neg(p.y);
+    xyzz_madd_sm<F>(sm, inf, p);
+    v = vn;
+  }
+}
 // One thread per bucket, buckets taken in descending size order so that the lanes of a warp finish together (ncu: 31.7 of 32
 // lanes active, fmaheavy pipe 90 % busy at 2^19 buckets of ~26 points).
 struct HeavyRec {
@@ -310,9 +385,18 @@ __global__ void __launch_bounds__(kAccumulateThreads, kAccumulateMinBlocks<F>) m
     for (uint32_t q = 0; q < nch; q++) chunk_owner[first + q] = h;
     return;
   }
-  XYZZ<F> acc = xyzz_inf<F>();
-  accumulate_run<F>(acc, table, tstride, sorted, beg, end, 1);
-  buckets[gb] = acc;
+  if constexpr (sizeof(F) == 64) {
+    __shared__ uint4 acc_sm[kAccSmemWords<F>];
+    bool inf = true;
+    accumulate_run_sm<F>(acc_sm, inf, table, tstride, sorted, beg, end);
+    XYZZ<F> acc = xyzz_inf<F>();
+    if (!inf) acc = XYZZ<F>{sm_get<F>(acc_sm, 0), sm_get<F>(acc_sm, 1), sm_get<F>(acc_sm, 2), sm_get<F>(acc_sm, 3)};
+    buckets[gb] = acc;
+  } else {
+    XYZZ<F> acc = xyzz_inf<F>();
+    accumulate_run<F>(acc, table, tstride, sorted, beg, end, 1);
+    buckets[gb] = acc;
+  }
 }
 // skewed scalars (plain-driver witnesses, or a top window narrower than c bits): a warp per kHeavy-entry chunk ...
 template <class F>
@@ -384,8 +468,9 @@ static inline uint32_t marg_stride(uint32_t nmarg) { return nmarg + (nmarg + 31)
 // The 32 lane sums of a marginal are folded through SHARED memory, not by a shuffle tree: slot = lane * 4 + warp, so that level
 // after level the surviving additions sit in whole warps (2, 1, 1, 1, 1 warp-additions per block instead of 5 x 4 with 16, 8, 4, 2, 1
 // lanes active -- the tree was 24 % of the kernel's issue slots, profiles/r01_ncu_msm_marginals*).
+template <class F> constexpr int kMarginalsMinBlocks = sizeof(F) == 32 ? 4 : 1;  // BN254 G1: 4 blocks of 128 threads per SM (300 B of spills; 3 blocks without spills measured slower)
 template <class F>
-__global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
+__global__ void __launch_bounds__(128, kMarginalsMinBlocks<F>) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
                                                              XYZZ<F>* __restrict__ out, uint32_t mstride) {
   __shared__ __align__(16) unsigned char fold_raw[128 * sizeof(XYZZ<F>)];
   XYZZ<F>* fold = reinterpret_cast<XYZZ<F>*>(fold_raw);
@@ -398,19 +483,19 @@ __global__ void __launch_bounds__(128) msm_marginals_kernel(const XYZZ<F>* __res
   XYZZ<F> acc = xyzz_inf<F>();
   if (warp < H) {
     const XYZZ<F>* r = buckets + ((size_t)warp << logL);
-    for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add_inline(acc, r[lo]);
+    for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add_red(acc, r[lo]);
   } else if (warp < nmarg) {
     const uint32_t w = warp - H;
     const uint32_t col = w / kColSeg, seg = w % kColSeg;
     const uint32_t hi0 = (uint32_t)((uint64_t)seg * H / kColSeg), hi1 = (uint32_t)((uint64_t)(seg + 1) * H / kColSeg);
-    for (uint32_t hi = hi0 + lane; hi < hi1; hi += 32) xyzz_add_inline(acc, buckets[((size_t)hi << logL) + col]);
+    for (uint32_t hi = hi0 + lane; hi < hi1; hi += 32) xyzz_add_red(acc, buckets[((size_t)hi << logL) + col]);
   }
   fold[lane * 4 + wib] = acc;
   __syncthreads();
   for (uint32_t active = 64; active >= 4; active >>= 1) {
     if (threadIdx.x < active) {
       XYZZ<F> a = fold[threadIdx.x];
-      xyzz_add(a, fold[threadIdx.x + active]);
+      xyzz_add_red(a, fold[threadIdx.x + active]);
       fold[threadIdx.x] = a;
     }
     __syncthreads();
@@ -533,6 +618,10 @@ int msm_buckets_impl(cocg_ctx* ctx, const BasesEntry& be, size_t off, const MsmS
   ProfScope prof(ctx, COCG_PROF_MSM_ACCUMULATE);
   COCG_CUDA(ctx, cudaMemsetAsync(S.heavy, 0, 16, st));
   constexpr int kThreads = kAccumulateThreads;
+  if (sizeof(F) == 64) {  // 4 blocks x 32 KB of accumulators per SM: ask for the carve-out that holds them
+    static const cudaError_t carve = cudaFuncSetAttribute(msm_accumulate_kernel<F>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    (void)carve;
+  }
   msm_accumulate_kernel<F><<<(nb + kThreads - 1) / kThreads, kThreads, 0, st>>>(table, be.n, S.sorted, S.start, S.order, nb, buckets, S.heavy_list,
                                                                                   S.chunk_owner, S.heavy);
   COCG_LAUNCH_CHECK(ctx);

@@ -75,44 +75,6 @@ __device__ __forceinline__ void sts_fp(uint4* plane_lo, uint4* plane_hi, int m, 
   plane_hi[m] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
 }
 
-// The twiddles of a round are known before its input is: their cache lines are requested (prefetch.global.L1, no registers) before the
-// barrier the round waits on, so the loads inside the round hit L1 instead of stalling on L2 / DRAM (ncu: long_scoreboard was the
-// second stall reason; the first stage of pass 0 reads n/2 distinct twiddles, one per butterfly).
-template <class P, int G, bool LAST>
-__device__ __forceinline__ void ntt_prefetch_twiddles(int tile_elems, int s, int logC, int kk, int k0, int L, int logQ, uint32_t col0,
-                                                      const void* __restrict__ tw) {
-  const int C = 1 << logC;
-  const int d = s - kk - G;
-  const int items = tile_elems >> G;
-  for (int it = threadIdx.x; it < items; it += kNttThreads) {
-    const int c = it & (C - 1);
-    const int low = (it >> logC) & ((1 << d) - 1);
-#pragma unroll
-    for (int t = 0; t < G; t++) {
-      const int k = k0 + kk + t;
-      if (k == L - 1) continue;
-#pragma unroll
-      for (int q = 0; q < (1 << (G - 1 - t)); q++) {
-        const int lo_i = (q << d) + low;
-        const size_t ex = LAST ? (size_t)lo_i : (((size_t)lo_i << logQ) + col0 + c);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)tw + ((ex << k) * sizeof(Fp<P>))));
-      }
-    }
-  }
-}
-template <class P, bool LAST>
-__device__ __forceinline__ void ntt_prefetch_round(int g, int tile_elems, int s, int logC, int kk, int k0, int L, int logQ, uint32_t col0,
-                                                   const void* __restrict__ tw) {
-  if (g == 3) ntt_prefetch_twiddles<P, 3, LAST>(tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
-  else if (g == 2) ntt_prefetch_twiddles<P, 2, LAST>(tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
-  else if (g == 1) ntt_prefetch_twiddles<P, 1, LAST>(tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
-}
-// stages of the round that starts at local stage kk: 3 while more than 4 remain (or exactly 3), else 2, else 1 -- 2, 2 instead of 3, 1
-__device__ __forceinline__ int ntt_round_stages(int s, int kk) {
-  const int rem = s - kk;
-  return rem <= 0 ? 0 : (rem > 4 || rem == 3) ? 3 : rem >= 2 ? 2 : 1;
-}
-
 // One round = G consecutive butterfly stages (local stages kk .. kk+G-1 of the pass) on 2^G elements held in REGISTERS: the tile is
 // read and written once per round instead of once per stage, one barrier per round, 2^G - 1 twiddle loads per 2^G elements.
 // DIF stage: (x, y) -> (x + y, (x - y) * w^((e mod 2^logh) * Q' << k)).  The 2^G elements of a work item differ in bits
@@ -174,7 +136,6 @@ __device__ __forceinline__ void ntt_round(uint4* plane_lo, uint4* plane_hi, int 
 #pragma unroll
     for (int j = 0; j < R; j++) sts_fp<P>(plane_lo, plane_hi, ((e_base + (j << d)) << logC) + c, x[j]);
   }
-  ntt_prefetch_round<P, LAST>(ntt_round_stages(s, kk + G), tile_elems, s, logC, kk + G, k0, L, logQ, col0, tw);
   __syncthreads();
 }
 
@@ -210,8 +171,6 @@ __global__ void __launch_bounds__(kNttThreads, COCG_NTT_MIN_BLOCKS) ntt_pass_ker
     stride_c = ((size_t)1 << (L - s - logC)) << s;
   }
 
-  ntt_prefetch_round<P, LAST>(ntt_round_stages(s, 0), tile_elems, s, logC, 0, k0, L, logQ, col0, tw);
-
   // ---- load (optionally pre-scaled by pre[global index])
   for (int t = threadIdx.x; t < tile_elems; t += kNttThreads) {
     int e, c;
@@ -231,12 +190,19 @@ __global__ void __launch_bounds__(kNttThreads, COCG_NTT_MIN_BLOCKS) ntt_pass_ker
   }
   __syncthreads();
 
-  // ---- s butterfly stages in register rounds
-  for (int kk = 0, g; (g = ntt_round_stages(s, kk)) != 0; kk += g) {
-    if (g == 3) ntt_round<P, 3, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
-    else if (g == 2) ntt_round<P, 2, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
-    else ntt_round<P, 1, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+  // ---- s butterfly stages in register rounds of 3 (2, 2 instead of 3, 1, so that no round is a lone stage unless s == 1).
+  // Requesting a round's twiddle lines ahead of its barrier (prefetch.global.L1) was measured and made the pass slower
+  // (0.42 -> 0.46 ms for two 2^20 vectors): the extra address arithmetic and spills cost more than the L2 latency they hide.
+  int kk = 0;
+  while (s - kk > 4 || s - kk == 3) {
+    ntt_round<P, 3, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+    kk += 3;
   }
+  while (s - kk >= 2) {
+    ntt_round<P, 2, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
+    kk += 2;
+  }
+  if (s - kk == 1) ntt_round<P, 1, LAST>(plane_lo, plane_hi, tile_elems, s, logC, kk, k0, L, logQ, col0, tw);
 
   // ---- store
   if (!LAST) {

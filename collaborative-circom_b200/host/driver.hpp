@@ -208,6 +208,9 @@ class PlainDriver : public DeviceDriver {
   // follows ifft (precedes fft) in witness_map_from_matrices into the transform.
   void fft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 0, coset_g); }
   void ifft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 1, coset_g); }
+  // the same transform of several share vectors as ONE launch sequence (the grid of a single 2^20 transform is 3.5 waves)
+  void fft_many(const std::vector<FieldShareVec*>& vs, const Domain& d, const Fr* coset_g = nullptr) { ntt_many(vs, d, 0, coset_g); }
+  void ifft_many(const std::vector<FieldShareVec*>& vs, const Domain& d, const Fr* coset_g = nullptr) { ntt_many(vs, d, 1, coset_g); }
   // MSMProvider (plain.rs:408-416)
   PointShare msm_public_points(int group, uint64_t bases, size_t off, size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
     PointShare r;
@@ -296,6 +299,14 @@ class PlainDriver : public DeviceDriver {
     if (v.len() != d.size()) throw Error("fft: vector length != domain size");
     void* vecs[1] = {v.a.p};
     check(ctx, cocg_ntt(ctx, vecs, 1, d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
+  }
+  void ntt_many(const std::vector<FieldShareVec*>& vs, const Domain& d, int inverse, const Fr* coset_g) {
+    std::vector<void*> vecs;
+    for (FieldShareVec* v : vs) {
+      if (v->len() != d.size()) throw Error("fft: vector length != domain size");
+      vecs.push_back(v->a.p);
+    }
+    check(ctx, cocg_ntt(ctx, vecs.data(), (int)vecs.size(), d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
   }
 };
 
@@ -393,6 +404,8 @@ class Rep3Protocol : public DeviceDriver {
   // ---- FFTProvider (rep3.rs:880-921): both components in one launch sequence
   void fft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 0, coset_g); }
   void ifft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 1, coset_g); }
+  void fft_many(const std::vector<FieldShareVec*>& vs, const Domain& d, const Fr* coset_g = nullptr) { ntt_many(vs, d, 0, coset_g); }
+  void ifft_many(const std::vector<FieldShareVec*>& vs, const Domain& d, const Fr* coset_g = nullptr) { ntt_many(vs, d, 1, coset_g); }
   // ---- MSMProvider (rep3.rs:934-947): a and b components against the same resident bases
   PointShare msm_public_points(int group, uint64_t bases, size_t off, size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
     Point out[2];
@@ -718,6 +731,15 @@ class Rep3Protocol : public DeviceDriver {
     if (v.len() != d.size()) throw Error("fft: vector length != domain size");
     void* vecs[2] = {v.a.p, v.b.p};
     check(ctx, cocg_ntt(ctx, vecs, 2, d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
+  }
+  void ntt_many(const std::vector<FieldShareVec*>& vs, const Domain& d, int inverse, const Fr* coset_g) {
+    std::vector<void*> vecs;
+    for (FieldShareVec* v : vs) {
+      if (v->len() != d.size()) throw Error("fft: vector length != domain size");
+      vecs.push_back(v->a.p);
+      vecs.push_back(v->b.p);
+    }
+    check(ctx, cocg_ntt(ctx, vecs.data(), (int)vecs.size(), d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
   }
 };
 

@@ -163,16 +163,15 @@ class CoGroth16 {
     driver.clone_from_slice(a, promoted_public, num_constraints, 0, num_inputs);
     driver.release(promoted_public);
 
+    // The three [ifft, coset scale, fft] pipelines (groth16.rs:177-199) are independent: a, b and c (every share component) go
+    // through each transform as ONE launch sequence.  The order of the two mul_vec rounds -- and with it every PRF counter -- is
+    // the reference's, so the proof bytes do not depend on this batching.
     FieldShareVec c = driver.mul_vec(a, b);
-    driver.ifft_in_place(a, domain, &root_of_unity);  // + distribute_powers_and_mul_by_const(a, root_of_unity, 1)
-    driver.ifft_in_place(b, domain, &root_of_unity);
-    driver.fft_in_place(a, domain);
-    driver.fft_in_place(b, domain);
+    driver.ifft_many({&a, &b, &c}, domain, &root_of_unity);  // + distribute_powers_and_mul_by_const(., root_of_unity, 1)
+    driver.fft_many({&a, &b, &c}, domain);
     FieldShareVec ab = driver.mul_vec(a, b);
     driver.release(a);
     driver.release(b);
-    driver.ifft_in_place(c, domain, &root_of_unity);
-    driver.fft_in_place(c, domain);
     driver.sub_assign_vec(ab, c);
     driver.release(c);
     return ab;

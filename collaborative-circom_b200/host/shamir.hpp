@@ -351,6 +351,8 @@ class ShamirProtocol : public DeviceDriver {
   // ---- FFTProvider (:826-871), MSMProvider (:1027-1039)
   void fft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 0, coset_g); }
   void ifft_in_place(FieldShareVec& v, const Domain& d, const Fr* coset_g = nullptr) { ntt(v, d, 1, coset_g); }
+  void fft_many(const std::vector<FieldShareVec*>& vs, const Domain& d, const Fr* coset_g = nullptr) { ntt_many(vs, d, 0, coset_g); }
+  void ifft_many(const std::vector<FieldShareVec*>& vs, const Domain& d, const Fr* coset_g = nullptr) { ntt_many(vs, d, 1, coset_g); }
   PointShare msm_public_points(int, uint64_t bases, size_t off, size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
     PointShare r;
     const void* sc[1] = {scalars.a.at(scalar_off)};
@@ -547,6 +549,14 @@ class ShamirProtocol : public DeviceDriver {
 
  private:
   std::vector<std::pair<void*, DevVec>> many_owned_;
+  void ntt_many(const std::vector<FieldShareVec*>& vs, const Domain& d, int inverse, const Fr* coset_g) {
+    std::vector<void*> vecs;
+    for (FieldShareVec* v : vs) {
+      if (v->len() != d.size()) throw Error("fft: vector length != domain size");
+      vecs.push_back(v->a.p);
+    }
+    check(ctx, cocg_ntt(ctx, vecs.data(), (int)vecs.size(), d.log_n, d.group_gen.l, inverse, coset_g ? coset_g->l : nullptr), "cocg_ntt");
+  }
   void ntt(FieldShareVec& v, const Domain& d, int inverse, const Fr* coset_g) {
     if (v.len() != d.size()) throw Error("fft: vector length != domain size");
     void* vecs[1] = {v.a.p};
