@@ -173,11 +173,11 @@ COCG_HD void xyzz_add_inline(XYZZ<F>& acc, const XYZZ<F>& q) {
   acc.zzz = f_mul(f_mul(acc.zzz, q.zzz), PPP);
 }
 
-#if defined(__CUDA_ARCH__)
-// Bucket-reduction flavour of the addition.  Over Fq2 it is the inline body (its products are calls already).  Over Fq the 14 products
-// are issued as 7 CALLS of two independent products each: inlined, the addition is ~35 KB of SASS per call site and the marginal-sum
-// kernel, which has two of them and warps in both, ran at a 60 % instruction-cache hit rate with `no_instruction` as its first stall
-// reason (profiles/r02_ncu_msm_marginals_multi*); called one product at a time, a warp would have a single carry chain in flight.
+#if defined(__CUDACC__)
+// Two independent base-field products per CALL.  The bucket-reduction kernels (msm_impl.cuh) issue the 14 products of an addition over
+// Fq as 7 of these: inlined, the addition is ~35 KB of SASS per call site and the marginal-sum kernel ran at a 60 % instruction-cache
+// hit rate with `no_instruction` as its first stall reason (profiles/r02_ncu_msm_marginals_multi*); called one product at a time, a
+// warp would have a single carry chain in flight.
 template <class P>
 struct FqPair {
   Fp<P> a, b;
@@ -188,33 +188,6 @@ __device__ __noinline__ FqPair<P> fp_mul2_call(Fp<P> a0, Fp<P> b0, Fp<P> a1, Fp<
   r.a = fp_mul(a0, b0);
   r.b = fp_mul(a1, b1);
   return r;
-}
-template <class P>
-COCG_D void xyzz_add_red(XYZZ<Fp2<P>>& acc, const XYZZ<Fp2<P>>& q) { xyzz_add_inline(acc, q); }
-template <class P>
-COCG_D void xyzz_add_red(XYZZ<Fp<P>>& acc, const XYZZ<Fp<P>>& q) {
-  using F = Fp<P>;
-  if (q.is_inf()) return;
-  if (acc.is_inf()) { acc = q; return; }
-  const FqPair<P> u = fp_mul2_call<P>(acc.x, q.zz, q.x, acc.zz);    // U1, U2
-  const FqPair<P> s = fp_mul2_call<P>(acc.y, q.zzz, q.y, acc.zzz);  // S1, S2
-  const F Pd = fp_sub(u.b, u.a);
-  const F R = fp_sub(s.b, s.a);
-  if (Pd.is_zero()) {
-    if (R.is_zero()) acc = xyzz_dbl(acc);
-    else acc = xyzz_inf<F>();
-    return;
-  }
-  const FqPair<P> z = fp_mul2_call<P>(acc.zz, q.zz, acc.zzz, q.zzz);
-  const FqPair<P> sq = fp_mul2_call<P>(Pd, Pd, R, R);                // PP, R^2
-  const FqPair<P> pq = fp_mul2_call<P>(Pd, sq.a, u.a, sq.a);         // PPP, Q
-  const F X3 = fp_sub(fp_sub(sq.b, pq.a), fp_add(pq.b, pq.b));
-  const FqPair<P> t = fp_mul2_call<P>(R, fp_sub(pq.b, X3), s.a, pq.a);  // R (Q - X3), S1 PPP
-  const FqPair<P> zz = fp_mul2_call<P>(z.a, sq.a, z.b, pq.a);        // ZZ1 ZZ2 PP, ZZZ1 ZZZ2 PPP
-  acc.x = X3;
-  acc.y = fp_sub(t.a, t.b);
-  acc.zz = zz.a;
-  acc.zzz = zz.b;
 }
 #endif
 

@@ -465,42 +465,161 @@ struct ReduceSets {
   uint32_t slot[kMaxSets];  // result slot (kResultSlot bytes each) of every set
 };
 static inline uint32_t marg_stride(uint32_t nmarg) { return nmarg + (nmarg + 31) / 32 + 2; }  // partial marginals | weighted warp sums
-// The 32 lane sums of a marginal are folded through SHARED memory, not by a shuffle tree: slot = lane * 4 + warp, so that level
-// after level the surviving additions sit in whole warps (2, 1, 1, 1, 1 warp-additions per block instead of 5 x 4 with 16, 8, 4, 2, 1
-// lanes active -- the tree was 24 % of the kernel's issue slots, profiles/r01_ncu_msm_marginals*).
-template <class F> constexpr int kMarginalsMinBlocks = sizeof(F) == 32 ? 4 : 1;  // BN254 G1: 4 blocks of 128 threads per SM (300 B of spills; 3 blocks without spills measured slower)
+// Marginal sums with the accumulators in SHARED memory.  A block of 128 threads owns 4 marginals; thread T sums part T / 4 (of 32)
+// of marginal T mod 4 into its own accumulator slot (16-byte words interleaved over the block: conflict-free), reading each
+// coordinate of the accumulator and of the addend where the formula uses it -- no XYZZ value is ever held in registers as a whole,
+// which is what lets the Fq2 instantiation run 4 blocks per SM instead of 2 (250 registers before).  The 32 partial sums of a
+// marginal are then folded in place: T < 64 adds slot T + 64, T < 32 adds slot T + 32, ... -- whole warps drop out level after level
+// (2, 1, 1, 1, 1 warp-additions per block) where a shuffle tree kept 16, 8, 4, 2, 1 lanes of EVERY warp busy.
+// Over Fq the 14 products of an addition are 7 calls of two independent products (instruction cache, see fp_mul2_call in ec.cuh).
+template <class F>
+struct Mul2 {
+  F a, b;
+};
+template <class P>
+__device__ __forceinline__ Mul2<Fp<P>> f_mul2(const Fp<P>& a0, const Fp<P>& b0, const Fp<P>& a1, const Fp<P>& b1) {
+  const FqPair<P> r = fp_mul2_call<P>(a0, b0, a1, b1);
+  return Mul2<Fp<P>>{r.a, r.b};
+}
+template <class P>
+__device__ __forceinline__ Mul2<Fp2<P>> f_mul2(const Fp2<P>& a0, const Fp2<P>& b0, const Fp2<P>& a1, const Fp2<P>& b1) {
+  return Mul2<Fp2<P>>{f_mul(a0, b0), f_mul(a1, b1)};
+}
+template <class F>
+struct GlobalXyzz {  // coordinate getter of a bucket in global memory
+  const uint4* p;
+  __device__ __forceinline__ F operator()(int comp) const {
+    constexpr int W = sizeof(F) / 16;
+    F r;
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      const uint4 v = __ldg(p + comp * W + k);
+      d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+    }
+    return r;
+  }
+};
+template <class F>
+struct SlotXyzz {  // coordinate getter of another thread's accumulator slot
+  const uint4* sm;
+  uint32_t slot;
+  __device__ __forceinline__ F operator()(int comp) const {
+    constexpr int W = sizeof(F) / 16;
+    F r;
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      const uint4 v = sm[(comp * W + k) * 128 + slot];
+      d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+    }
+    return r;
+  }
+};
+template <class F>
+__device__ __forceinline__ F slot_get(const uint4* sm, int comp) {
+  return SlotXyzz<F>{sm, threadIdx.x}(comp);
+}
+template <class F>
+__device__ __forceinline__ void slot_put(uint4* sm, int comp, const F& x) {
+  constexpr int W = sizeof(F) / 16;
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(&x);
+#pragma unroll
+  for (int k = 0; k < W; k++) sm[(comp * W + k) * 128 + threadIdx.x] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+}
+// own slot += q (add-2008-s, the special cases of xyzz_add).  The accumulator is overwritten before P == Q is known; in that case
+// it equals q, which is intact, and is doubled from there.
+template <class F, class Q>
+__device__ __forceinline__ void xyzz_add_slot(uint4* sm, bool& inf, const Q& q) {
+  const F zz2 = q(2);
+  if (zz2.is_zero()) return;
+  if (inf) {
+    slot_put<F>(sm, 0, q(0)); slot_put<F>(sm, 1, q(1)); slot_put<F>(sm, 2, zz2); slot_put<F>(sm, 3, q(3));
+    inf = false;
+    return;
+  }
+  F U1, U2, S1, Pd, R;
+  {
+    const F zz1 = slot_get<F>(sm, 2);
+    const Mul2<F> m = f_mul2(zz1, zz2, q(0), zz1);  // ZZ1 ZZ2, U2
+    slot_put<F>(sm, 2, m.a);
+    U2 = m.b;
+  }
+  {
+    const F zzz1 = slot_get<F>(sm, 3), zzz2 = q(3);
+    const Mul2<F> m = f_mul2(slot_get<F>(sm, 0), zz2, zzz1, zzz2);  // U1, ZZZ1 ZZZ2
+    U1 = m.a;
+    slot_put<F>(sm, 3, m.b);
+    const Mul2<F> s = f_mul2(q(1), zzz1, slot_get<F>(sm, 1), zzz2);  // S2, S1
+    S1 = s.b;
+    R = f_sub(s.a, s.b);
+  }
+  Pd = f_sub(U2, U1);
+  if (Pd.is_zero()) {
+    if (R.is_zero()) {
+      const XYZZ<F> d = xyzz_dbl(XYZZ<F>{q(0), q(1), q(2), q(3)});
+      slot_put<F>(sm, 0, d.x); slot_put<F>(sm, 1, d.y); slot_put<F>(sm, 2, d.zz); slot_put<F>(sm, 3, d.zzz);
+    } else {
+      inf = true;
+    }
+    return;
+  }
+  const Mul2<F> sq = f_mul2(Pd, Pd, R, R);      // PP, R^2
+  const Mul2<F> pq = f_mul2(Pd, sq.a, U1, sq.a);  // PPP, Q
+  const F X3 = f_sub(f_sub(sq.b, pq.a), f_dbl(pq.b));
+  slot_put<F>(sm, 0, X3);
+  {
+    const Mul2<F> z = f_mul2(slot_get<F>(sm, 2), sq.a, slot_get<F>(sm, 3), pq.a);
+    slot_put<F>(sm, 2, z.a);
+    slot_put<F>(sm, 3, z.b);
+  }
+  const Mul2<F> t = f_mul2(R, f_sub(pq.b, X3), S1, pq.a);  // R (Q - X3), S1 PPP
+  slot_put<F>(sm, 1, f_sub(t.a, t.b));
+}
+template <class F> constexpr int kMarginalsMinBlocks = sizeof(F) == 32 ? 4 : sizeof(F) == 64 ? 3 : sizeof(F) == 48 ? 3 : 1;  // blocks of 128 threads per SM
 template <class F>
 __global__ void __launch_bounds__(128, kMarginalsMinBlocks<F>) msm_marginals_kernel(const XYZZ<F>* __restrict__ buckets, uint32_t logH, uint32_t logL,
                                                              XYZZ<F>* __restrict__ out, uint32_t mstride) {
-  __shared__ __align__(16) unsigned char fold_raw[128 * sizeof(XYZZ<F>)];
-  XYZZ<F>* fold = reinterpret_cast<XYZZ<F>*>(fold_raw);
+  __shared__ uint4 acc_sm[sizeof(XYZZ<F>) / 16 * 128];
   const uint32_t H = 1u << logH, L = 1u << logL;
-  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * 4 + wib;
+  const uint32_t part = threadIdx.x >> 2;
+  const uint32_t marg = blockIdx.x * 4 + (threadIdx.x & 3);
   const uint32_t nmarg = H + L * kColSeg;
   buckets += (size_t)blockIdx.y << (logH + logL);
   out += (size_t)blockIdx.y * mstride;
-  XYZZ<F> acc = xyzz_inf<F>();
-  if (warp < H) {
-    const XYZZ<F>* r = buckets + ((size_t)warp << logL);
-    for (uint32_t lo = lane; lo < L; lo += 32) xyzz_add_red(acc, r[lo]);
-  } else if (warp < nmarg) {
-    const uint32_t w = warp - H;
+  bool inf = true;
+  constexpr int kLines = (sizeof(XYZZ<F>) + 127) / 128;
+  auto add_bucket = [&](const XYZZ<F>* b, const XYZZ<F>* next) {
+    if (next) {
+#pragma unroll
+      for (int l = 0; l < kLines; l++) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(next) + 128 * l));
+    }
+    xyzz_add_slot<F>(acc_sm, inf, GlobalXyzz<F>{reinterpret_cast<const uint4*>(b)});
+  };
+  if (marg < H) {
+    const XYZZ<F>* r = buckets + ((size_t)marg << logL);
+    for (uint32_t lo = part; lo < L; lo += 32) add_bucket(r + lo, lo + 32 < L ? r + lo + 32 : nullptr);
+  } else if (marg < nmarg) {
+    const uint32_t w = marg - H;
     const uint32_t col = w / kColSeg, seg = w % kColSeg;
     const uint32_t hi0 = (uint32_t)((uint64_t)seg * H / kColSeg), hi1 = (uint32_t)((uint64_t)(seg + 1) * H / kColSeg);
-    for (uint32_t hi = hi0 + lane; hi < hi1; hi += 32) xyzz_add_red(acc, buckets[((size_t)hi << logL) + col]);
+    for (uint32_t hi = hi0 + part; hi < hi1; hi += 32)
+      add_bucket(buckets + ((size_t)hi << logL) + col, hi + 32 < hi1 ? buckets + ((size_t)(hi + 32) << logL) + col : nullptr);
   }
-  fold[lane * 4 + wib] = acc;
+  if (inf) slot_put<F>(acc_sm, 2, F::zero());  // the fold reads other threads' slots: mark O the way XYZZ does (ZZ = 0)
   __syncthreads();
   for (uint32_t active = 64; active >= 4; active >>= 1) {
     if (threadIdx.x < active) {
-      XYZZ<F> a = fold[threadIdx.x];
-      xyzz_add_red(a, fold[threadIdx.x + active]);
-      fold[threadIdx.x] = a;
+      xyzz_add_slot<F>(acc_sm, inf, SlotXyzz<F>{acc_sm, threadIdx.x + active});
+      if (inf) slot_put<F>(acc_sm, 2, F::zero());
     }
     __syncthreads();
   }
-  if (threadIdx.x < 4 && blockIdx.x * 4 + threadIdx.x < nmarg) out[blockIdx.x * 4 + threadIdx.x] = fold[threadIdx.x];
+  if (threadIdx.x < 4 && marg < nmarg) {
+    XYZZ<F> r = xyzz_inf<F>();
+    if (!inf) r = XYZZ<F>{slot_get<F>(acc_sm, 0), slot_get<F>(acc_sm, 1), slot_get<F>(acc_sm, 2), slot_get<F>(acc_sm, 3)};
+    out[marg] = r;
+  }
 }
 // weights: one THREAD per partial marginal (all lanes busy, unlike a multiply on the reducing lane), then a warp tree
 template <class F>
