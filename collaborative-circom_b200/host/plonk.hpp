@@ -333,16 +333,20 @@ class CoPlonk {
       if (K == 2) check(driver.ctx, cocg_h2d(driver.ctx, sig.b.at(base), hb.data(), hb.size() * 32), "cocg_h2d");
     }
     // ---- compute_wire_polynomials (round1.rs:121-209)
+    // the three wires go through each transform as one launch sequence (a 2^18 transform alone is less than one wave of blocks)
+    FieldShareVec wire_poly[3];
     for (int w = 0; w < 3; w++) {
       buf_[w] = driver.alloc_share(n);
       for (int k = 0; k < K; k++)
         check(driver.ctx, cocg_vec_gather(driver.ctx, comp(sig, k).p, zk.n_vars, zk.d_map[w], comp(buf_[w], k).p, n), "cocg_vec_gather");
-      FieldShareVec poly = extend(buf_[w], n, n);
-      driver.ifft_in_place(poly, dom_);
-      eval_[w] = extend(poly, 4 * n, n);
-      driver.fft_in_place(eval_[w], ext_);
-      poly_[w] = extend(poly, n + 2, n);
-      driver.release(poly);
+      wire_poly[w] = extend(buf_[w], n, n);
+    }
+    driver.ifft_many({&wire_poly[0], &wire_poly[1], &wire_poly[2]}, dom_);
+    for (int w = 0; w < 3; w++) eval_[w] = extend(wire_poly[w], 4 * n, n);
+    driver.fft_many({&eval_[0], &eval_[1], &eval_[2]}, ext_);
+    for (int w = 0; w < 3; w++) {
+      poly_[w] = extend(wire_poly[w], n + 2, n);
+      driver.release(wire_poly[w]);
       blind(poly_[w], n, {b_[2 * w + 1], b_[2 * w]});  // coeff_rev = b[2w .. 2w + 2]
     }
     driver.release(sig);
@@ -461,8 +465,7 @@ class CoPlonk {
     driver.release(l1s);
     FieldShareVec t = driver.slice(tt, 0, n4), tz = driver.slice(tt, n4, n4);
     if (trace) { record("t_evals", t.a, n4); record("tz_evals", tz.a, n4); }
-    driver.ifft_in_place(t, ext_);
-    driver.ifft_in_place(tz, ext_);
+    driver.ifft_many({&t, &tz}, ext_);
     t_[0] = driver.alloc_share(n + 6);  // t1, t2 hold n + 1 coefficients; zero up to n + 6 so that one MSM call commits all three
     t_[1] = driver.alloc_share(n + 6);
     t_[2] = driver.alloc_share(n + 6);
