@@ -222,8 +222,8 @@ def workload_config(args, world):
             "curve": args.curve, "protocol": args.protocol, "domain_size": n, "n_vars": n, "n_public": 1, "nnz_per_row": 2,
             "msm_per_proof": f"3 parties x {comps} components x (4 G1 + 1 G2)", "ntt_per_proof": 18 * comps,
             "parallelism": "single GPU" if world == 1 else (
-                f"15 equal blocks of the proof (per party: witness map + h MSMs; per party and share component: the l/a/b_g1 MSMs, the b_g2 MSM) "
-                f"spread over {world} GPUs at full size, mul_vec payloads GPU to GPU over NCCL, 1 all-gather/proof"
+                f"27 units of the proof (per party: witness map + h MSMs; per party and share component: the b_g2 MSM and each of the l / a / b_g1 "
+                f"MSMs) placed largest-first on {world} GPUs at full size, mul_vec payloads GPU to GPU over NCCL, 1 all-gather/proof"
                 if args.protocol == "rep3" and getattr(args, "shard_mode", "blocks") == "blocks" else
                 f"MSM bases sharded by index range over {world} GPUs, NTT replicated, 1 all-gather/proof"),
             "l2_policy": "inputs_exceed_l2 (>= 0.9 GB of bases + share vectors streamed per proof vs 126 MB L2)"}

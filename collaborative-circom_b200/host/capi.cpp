@@ -135,12 +135,13 @@ extern "C" int cohost_zkey_create(const cohost_zkey_desc* d, cohost_zkey** out) 
     }
     const size_t len_q = (zk.world > 1 && !zk.blocks) ? len_x : m;  // a / b queries: whole (heads included) or the aux slice
     // block mode: whole queries, but only those of the blocks this rank runs (types.hpp BlockPlan)
-    const bool want_g1 = !zk.blocks || zk.plan.has_g1(zk.rank), want_g2 = !zk.blocks || zk.plan.has_g2(zk.rank), want_h = !zk.blocks || zk.plan.has_wm(zk.rank);
-    if (want_g1) bases(COCG_G1, d->a_query, zk.a_first, len_q, 1, &zk.a_query, "a_query");
-    if (want_g1) bases(COCG_G1, d->b_g1_query, zk.b_g1_first, len_q, 2, &zk.b_g1_query, "b_g1_query");
+    const bool want_l = !zk.blocks || zk.plan.has_g1(zk.rank, 0), want_a = !zk.blocks || zk.plan.has_g1(zk.rank, 1), want_b1 = !zk.blocks || zk.plan.has_g1(zk.rank, 2);
+    const bool want_g2 = !zk.blocks || zk.plan.has_g2(zk.rank), want_h = !zk.blocks || zk.plan.has_wm(zk.rank);
+    if (want_a) bases(COCG_G1, d->a_query, zk.a_first, len_q, 1, &zk.a_query, "a_query");
+    if (want_b1) bases(COCG_G1, d->b_g1_query, zk.b_g1_first, len_q, 2, &zk.b_g1_query, "b_g1_query");
     if (want_g2) bases(COCG_G2, d->b_g2_query, zk.b_g2_first, len_q, 3, &zk.b_g2_query, "b_g2_query");
     if (want_h) bases(COCG_G1, d->h_query, zk.h_first, len_h, 4, &zk.h_query, "h_query");
-    if (want_g1) bases(COCG_G1, d->l_query, zk.l_first, len_x, 5, &zk.l_query, "l_query");
+    if (want_l) bases(COCG_G1, d->l_query, zk.l_first, len_x, 5, &zk.l_query, "l_query");
     check(c, cocg_csr_upload_form(c, d->a_rowptr, d->a_col, d->a_coeff, zk.num_constraints, d->a_nnz, d->coeff_form, &zk.csr_a), "csr_a");
     check(c, cocg_csr_upload_form(c, d->b_rowptr, d->b_col, d->b_coeff, zk.num_constraints, d->b_nnz, d->coeff_form, &zk.csr_b), "csr_b");
     zk.a_head.resize(l + 1);
@@ -405,7 +406,7 @@ static int rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, c
         FieldShareVec wit;
         bool need[2] = {true, true};  // block mode: only the components of this party that a block of this rank reads
         if (zk.blocks)
-          for (int c = 0; c < 2; c++) need[c] = zk.plan.wm[i] == s->rank || zk.plan.g1[i][c] == s->rank || zk.plan.g2[i][c] == s->rank;
+          for (int c = 0; c < 2; c++) need[c] = zk.plan.reads_witness(s->rank, i, c);
         if (wit_on_device) {  // borrowed: the caller keeps ownership
           wit.a = DevVec{const_cast<void*>(wit_a_i), zk.n_aux()};
           wit.b = DevVec{const_cast<void*>(wit_b_i), zk.n_aux()};
@@ -538,7 +539,10 @@ extern "C" int cohost_block_plan(int world, int* out) {
   BlockPlan p = BlockPlan::make(world);
   for (int q = 0; q < 3; q++) out[q] = p.wm[q];
   for (int q = 0; q < 3; q++)
-    for (int c = 0; c < 2; c++) { out[3 + 2 * q + c] = p.g1[q][c]; out[9 + 2 * q + c] = p.g2[q][c]; }
+    for (int c = 0; c < 2; c++) {
+      out[3 + 2 * q + c] = p.g2[q][c];
+      for (int k = 0; k < 3; k++) out[9 + 6 * q + 3 * c + k] = p.g1[q][c][k];
+    }
   return 0;
 }
 // The index-range partition of an n-term MSM over `world` ranks (MsmShard::range); no GPU needed.

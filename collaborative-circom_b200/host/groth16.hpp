@@ -287,16 +287,19 @@ class CoGroth16 {
     m.h_acc = m.l_acc = m.a_acc = m.b1_acc = PointShare{inf1, inf1};
     m.b2_acc = PointShare{inf2, inf2};
     if (blocks->wm[p] == block_rank) m.h_acc = driver.msm_public_points(1, hd.h_query, 0, std::min(h.len(), zkey.domain_size()), h, 0);
-    for (int c = 0; c < 2; c++) {
-      if (blocks->g1[p][c] == block_rank) {  // l, a, b_g1 of one component: one digit sort
-        std::vector<Point> r = driver.msm_public_points_multi_comp({1, 1, 1}, {hd.l_query, hd.a_query, hd.b_g1_query}, {0, 1 + l, 1 + l}, n_aux, aux, c);
-        (c ? m.l_acc.b : m.l_acc.a) = r[0];
-        (c ? m.a_acc.b : m.a_acc.a) = r[1];
-        (c ? m.b1_acc.b : m.b1_acc.a) = r[2];
-      }
-      if (blocks->g2[p][c] == block_rank) {
-        std::vector<Point> r = driver.msm_public_points_multi_comp({2}, {hd.b_g2_query}, {1 + l}, n_aux, aux, c);
-        (c ? m.b2_acc.b : m.b2_acc.a) = r[0];
+    for (int c = 0; c < 2; c++) {  // the MSMs of one share component that run here share one digit sort
+      std::vector<int> groups, which;
+      std::vector<uint64_t> bases;
+      std::vector<size_t> offs;
+      const uint64_t handle[3] = {hd.l_query, hd.a_query, hd.b_g1_query};
+      for (int k = 0; k < 3; k++)
+        if (blocks->g1[p][c][k] == block_rank) { groups.push_back(1); bases.push_back(handle[k]); offs.push_back(k == 0 ? 0 : 1 + l); which.push_back(k); }
+      if (blocks->g2[p][c] == block_rank) { groups.push_back(2); bases.push_back(hd.b_g2_query); offs.push_back(1 + l); which.push_back(3); }
+      if (groups.empty()) continue;
+      std::vector<Point> r = driver.msm_public_points_multi_comp(groups, bases, offs, n_aux, aux, c);
+      for (size_t i = 0; i < which.size(); i++) {
+        PointShare& dst = which[i] == 0 ? m.l_acc : which[i] == 1 ? m.a_acc : which[i] == 2 ? m.b1_acc : m.b2_acc;
+        (c ? dst.b : dst.a) = r[i];
       }
     }
   }

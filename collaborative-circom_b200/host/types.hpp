@@ -73,31 +73,45 @@ struct Domain {
 struct BlockPlan {
   int world = 1;
   int wm[3] = {0, 0, 0};                 // rank of party p's witness map + h MSMs
-  int g1[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // rank of the {l, a, b_g1} bundle of (party, component)
+  int g1[3][2][3] = {};                  // rank of the l / a / b_g1 MSM (index 0 / 1 / 2) of (party, component)
   int g2[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // rank of the b_g2 MSM of (party, component)
+  // Costs in ms at 2^20 on a B200 (profiles/r02_launches_*): a witness map with its two h MSMs 9.7, a b_g2 MSM 8.3 with its digit
+  // sort, a G1 MSM 2.5 plus 0.4 for the digit sort of its (party, component) scalars when no other MSM of that vector runs on the
+  // rank.  Largest first onto the least-loaded rank; the G1 MSMs are placed ONE BY ONE (round 2 placed the {l, a, b_g1} bundles:
+  // 15 blocks on 2 / 4 / 8 ranks left the slowest rank 5 - 10 % above the mean).  A pure function of `world`: ranks agree without talking.
   static BlockPlan make(int world) {
     BlockPlan p;
     p.world = world;
     std::vector<double> load(world, 0.0);
-    auto place = [&](double cost) {
+    std::vector<char> sorted_here((size_t)world * 6, 0);  // [rank][party * 2 + component]: that scalar vector is sorted on the rank
+    auto least = [&](auto cost) {
       int best = 0;
       for (int r = 1; r < world; r++)
-        if (load[r] < load[best] - 1e-9) best = r;
-      load[best] += cost;
+        if (load[r] + cost(r) < load[best] + cost(best) - 1e-9) best = r;
+      load[best] += cost(best);
       return best;
     };
-    for (int q = 0; q < 3; q++) p.wm[q] = place(9.8);
+    for (int q = 0; q < 3; q++) p.wm[q] = least([](int) { return 9.7; });
     for (int q = 0; q < 3; q++)
-      for (int c = 0; c < 2; c++) p.g2[q][c] = place(8.8);
-    for (int q = 0; q < 3; q++)
-      for (int c = 0; c < 2; c++) p.g1[q][c] = place(9.1);
+      for (int c = 0; c < 2; c++) {
+        const int r = least([](int) { return 8.3; });
+        p.g2[q][c] = r;
+        sorted_here[(size_t)r * 6 + q * 2 + c] = 1;
+      }
+    for (int k = 0; k < 3; k++)
+      for (int q = 0; q < 3; q++)
+        for (int c = 0; c < 2; c++) {
+          const int r = least([&](int rr) { return sorted_here[(size_t)rr * 6 + q * 2 + c] ? 2.5 : 2.9; });
+          p.g1[q][c][k] = r;
+          sorted_here[(size_t)r * 6 + q * 2 + c] = 1;
+        }
     return p;
   }
   bool has_wm(int rank) const { return wm[0] == rank || wm[1] == rank || wm[2] == rank; }
-  bool has_g1(int rank) const {
+  bool has_g1(int rank, int k) const {  // k: 0 l_query, 1 a_query, 2 b_g1_query
     for (int q = 0; q < 3; q++)
       for (int c = 0; c < 2; c++)
-        if (g1[q][c] == rank) return true;
+        if (g1[q][c][k] == rank) return true;
     return false;
   }
   bool has_g2(int rank) const {
@@ -105,6 +119,10 @@ struct BlockPlan {
       for (int c = 0; c < 2; c++)
         if (g2[q][c] == rank) return true;
     return false;
+  }
+  // does `rank` read share component c of party q's witness?
+  bool reads_witness(int rank, int q, int c) const {
+    return wm[q] == rank || g2[q][c] == rank || g1[q][c][0] == rank || g1[q][c][1] == rank || g1[q][c][2] == rank;
   }
 };
 

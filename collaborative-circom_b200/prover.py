@@ -280,11 +280,13 @@ def plonk_zkey_header(path: str) -> dict:
 
 
 def block_plan(world: int) -> dict:
-    """The block-mode work distribution for `world` ranks: {"wm": [3 ranks], "g1": [[a, b] x 3], "g2": [[a, b] x 3]}."""
-    out = (ci * 15)()
+    """The block-mode work distribution for `world` ranks: {"wm": [rank x 3 parties], "g2": [[a, b] x 3],
+    "g1": [[[l, a, b_g1] x 2 components] x 3 parties]}."""
+    out = (ci * 27)()
     _ck(load_host().cohost_block_plan(world, out))
     v = [int(x) for x in out]
-    return {"wm": v[:3], "g1": [v[3 + 2 * q:5 + 2 * q] for q in range(3)], "g2": [v[9 + 2 * q:11 + 2 * q] for q in range(3)]}
+    return {"wm": v[:3], "g2": [v[3 + 2 * q:5 + 2 * q] for q in range(3)],
+            "g1": [[v[9 + 6 * q + 3 * c:12 + 6 * q + 3 * c] for c in range(2)] for q in range(3)]}
 
 
 def r1cs_info(path: str) -> dict:

@@ -101,7 +101,7 @@ typedef struct cohost_comm_op { int dir; int peer; void* dptr; size_t bytes; } c
 typedef int (*cohost_comm_cb)(void* user, const cohost_comm_op* ops, int nops);
 COHOST_API int cohost_rep3_session_create_blocks(cohost_zkey* z, const uint8_t* seeds, int rank, int world, cohost_comm_cb comm, void* user,
                                                  cohost_rep3_session** out);
-/* The block plan for `world` ranks (no GPU needed): out[15] = wm[3] | g1[3][2] | g2[3][2] ranks. */
+/* The block plan for `world` ranks (no GPU needed): out[27] = wm[3] | g2[3][2] | g1[3][2][3] ranks (party, share component, query l / a / b_g1). */
 COHOST_API int cohost_block_plan(int world, int* out);
 COHOST_API void cohost_rep3_session_destroy(cohost_rep3_session* s);
 /* One proof = begin [-> partials -> (caller all-gathers) -> combine] -> end.  wit_a[i] / wit_b[i]: party i's HOST share
