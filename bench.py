@@ -243,7 +243,10 @@ def run_own(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL's kernels on a high-priority stream: a send / receive of a mul_vec round must not queue behind the thousands of pending
+        # thread blocks of an MSM launch on the same GPU (the witness maps of three ranks advance in lock-step through these rounds)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     rng = np.random.default_rng(SEED)
     log_n = args.log_n
     n = 1 << log_n
@@ -318,6 +321,31 @@ def run_own(args):
     sess.profile(False)
     assert np.array_equal(proofs[0], proofs[1]) and np.array_equal(proofs[1], proofs[2]), "the three parties disagree on the proof"
     phases_value = sess.phase_times().max(axis=0) * 1e3  # last proof of the value leg, slowest party per phase
+    # N > 1 diagnostics (outside the timed region): per rank, the host wall time of each API call of one more value-leg proof and
+    # the parties' phase times -- shows which rank the all-gather waits for and what surrounds it
+    rank_diag = None
+    if world > 1:
+        api = np.zeros(5)
+        reps = 4
+        for _ in range(reps):
+            dist.barrier()
+            t0 = time.perf_counter()
+            sess.begin(pub, dev_a, dev_b, None, True)
+            t1 = time.perf_counter()
+            part = sess.partials()
+            t2 = time.perf_counter()
+            gathered = all_gather(part)
+            t3 = time.perf_counter()
+            sess.combine(gathered)
+            t4 = time.perf_counter()
+            sess.end()
+            t5 = time.perf_counter()
+            api += np.array([t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4]) * 1e3 / reps
+        mine = {"rank": rank, "api_ms": {k: round(float(v), 2) for k, v in zip(("begin", "partials_wait", "all_gather", "combine", "end"), api)},
+                "party_phase_ms": [[round(float(x) * 1e3, 2) for x in row] for row in sess.phase_times()]}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        rank_diag = everyone
     # The PRF seeds are fixed and every mask / blinder is addressed by a counter the parties advance in lock-step, so proof number
     # warmup + steps of this leg is the same byte string in every run and at every N (sharding only changes who adds which points).
     import hashlib
@@ -419,7 +447,7 @@ def run_own(args):
                                    "durations, each instantiation timed alone with CUDA events on its launching stream in this run",
                          "in_situ": in_situ, "peak_source": peak_src,
                          "note": "MSM is bound by 32-bit integer multiply-add issue, not HBM (DESIGN.md section 4): see `issue`"},
-            "replicas": replicas,
+            "replicas": replicas, "rank_diag": rank_diag,
             "kernels": kernels, "setup_s": round(setup_s, 2),
             "host_phases_ms": {"witness_map": round(float(phases[0]), 2), "msm": round(float(phases[1]), 2),
                                "all_gather_wait": round(float(phases[2]), 2), "assembly": round(float(phases[3]), 2),

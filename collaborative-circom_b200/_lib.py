@@ -18,7 +18,7 @@ EC_ADD, EC_MUL, EC_TO_AFFINE, EC_FROM_AFFINE, EC_NEG, EC_DBL = range(6)
 
 # every symbol include/cocg.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "cocg_create", "cocg_destroy", "cocg_last_error", "cocg_version", "cocg_set_stream", "cocg_sync",
+    "cocg_create", "cocg_destroy", "cocg_last_error", "cocg_version", "cocg_set_stream", "cocg_set_stream_priority", "cocg_sync",
     "cocg_launch_count", "cocg_malloc", "cocg_free", "cocg_h2d", "cocg_d2h", "cocg_memset0", "cocg_vec_op",
     "cocg_vec_scale_powers", "cocg_rep3_mul_local", "cocg_ntt", "cocg_bases_upload", "cocg_bases_free",
     "cocg_msm", "cocg_msm_host", "cocg_csr_upload", "cocg_csr_free", "cocg_spmv", "cocg_ec_op",
@@ -59,6 +59,7 @@ def load():
         "cocg_last_error": (ctypes.c_char_p, [vp]),
         "cocg_version": (ci, []),
         "cocg_set_stream": (ci, [vp, vp]),
+        "cocg_set_stream_priority": (ci, [vp, ci]),
         "cocg_sync": (ci, [vp]),
         "cocg_launch_count": (u64, [vp]),
         "cocg_malloc": (ci, [vp, sz, pvp]),

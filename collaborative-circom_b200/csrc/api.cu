@@ -73,6 +73,22 @@ extern "C" int cocg_set_stream(cocg_ctx* ctx, void* cuda_stream) {
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return 0;
 }
+// Re-creates the context's own stream with the device's highest (high != 0) or default priority.  Thread blocks of a high-priority
+// stream are scheduled ahead of the pending blocks of other streams' running kernels: a party whose short witness-map kernels share
+// the GPU with another party's MSM launches is no longer queued behind each of them (multi-GPU block mode).
+extern "C" int cocg_set_stream_priority(cocg_ctx* ctx, int high) {
+  if (!ctx) return 1;
+  COCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->stream != ctx->own_stream) return fail(ctx, "cocg_set_stream_priority: the context runs on a caller's stream");
+  COCG_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+  int lo = 0, hi = 0;
+  COCG_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // numerically lower = higher priority
+  cudaStream_t st;
+  COCG_CUDA(ctx, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, high ? hi : 0));
+  cudaStreamDestroy(ctx->own_stream);
+  ctx->own_stream = ctx->stream = st;
+  return 0;
+}
 extern "C" int cocg_sync(cocg_ctx* ctx) {
   if (!ctx) return 1;
   COCG_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -297,6 +297,10 @@ static int rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, i
         s->drv[i]->bridge = s->bridge.get();
         s->prover[i]->blocks = &z->zk.plan;
         s->prover[i]->block_rank = rank;
+        // the party whose witness map runs here has the longest dependent chain on this rank (witness map, lock-step with two other
+        // GPUs, then its h MSMs): its stream's thread blocks go ahead of the other parties' pending MSM blocks
+        const char* pr = getenv("COHOST_WM_PRIORITY");
+        if (z->zk.plan.wm[i] == rank && !(pr && std::string(pr) == "0")) check(s->drv[i]->ctx, cocg_set_stream_priority(s->drv[i]->ctx, 1), "cocg_set_stream_priority");
       }
       share_handles(s->drv[i]->ctx, z->zk, s->hd[i]);
     }

@@ -51,6 +51,9 @@ COCG_API const char* cocg_last_error(cocg_ctx* ctx); /* ctx may be NULL: error o
 COCG_API int cocg_version(void);
 /* Use an externally owned cudaStream_t (e.g. the torch current stream); NULL restores the context's own. */
 COCG_API int cocg_set_stream(cocg_ctx* ctx, void* cuda_stream);
+/* high != 0: the context's own stream gets the device's highest scheduling priority (its pending thread blocks go ahead of those of
+ * other streams' running kernels); 0: default priority.  Call while the context is idle. */
+COCG_API int cocg_set_stream_priority(cocg_ctx* ctx, int high);
 COCG_API int cocg_sync(cocg_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench.py's `gpu_launches`). */
 COCG_API uint64_t cocg_launch_count(cocg_ctx* ctx);
