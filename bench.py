@@ -286,6 +286,8 @@ def run_own(args):
             return sess.prove(pub, dev_a, dev_b, all_gather=all_gather, device_ptrs=True)
         return sess.prove(pub, host_a, host_b, all_gather=all_gather)
 
+    step_walls = {}
+
     def timed(device_resident, steps, sample_clocks=False):
         torch.cuda.synchronize()
         if world > 1:
@@ -295,8 +297,11 @@ def run_own(args):
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        walls = []
         for _ in range(steps):
+            tw = time.perf_counter()
             proofs = step(device_resident)
+            walls.append((time.perf_counter() - tw) * 1e3)
         e1.record()
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
@@ -304,6 +309,7 @@ def run_own(args):
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        step_walls[device_resident] = [round(float(np.min(walls)), 2), round(float(np.median(walls)), 2), round(float(np.max(walls)), 2), int(np.argmax(walls))]
         return float(ms.item()), clocks, proofs
 
     # `value` leg: everything resident in HBM -- witness shares AND the mul_vec payloads the three co-located parties exchange;
@@ -448,6 +454,7 @@ def run_own(args):
                          "in_situ": in_situ, "peak_source": peak_src,
                          "note": "MSM is bound by 32-bit integer multiply-add issue, not HBM (DESIGN.md section 4): see `issue`"},
             "replicas": replicas, "rank_diag": rank_diag,
+            "step_wall_ms_rank0": {"value_leg_min_median_max_argmax": step_walls.get(True), "e2e_leg_min_median_max_argmax": step_walls.get(False)},
             "kernels": kernels, "setup_s": round(setup_s, 2),
             "host_phases_ms": {"witness_map": round(float(phases[0]), 2), "msm": round(float(phases[1]), 2),
                                "all_gather_wait": round(float(phases[2]), 2), "assembly": round(float(phases[3]), 2),
