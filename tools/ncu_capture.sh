@@ -12,7 +12,7 @@ cap() {  # name, kernel regex, skip, count, target mode
 }
 cap r2_ncu_msm_accumulate_g1 msm_accumulate_kernel 1 1 msm_g1
 cap r2_ncu_msm_accumulate_g2 msm_accumulate_kernel 1 1 msm_g2
-cap r2_ncu_msm_marginals_g1 msm_marginals 1 1 msm_g1
+cap r2_ncu_msm_marginals_multi msm_marginals 2 2 msm_multi
 cap r2_ncu_ntt_pass ntt_pass 3 3 ntt
 cap r2_ncu_plonk_quotient_l1 plonk_quotient_l1 0 1 plonk
 cap r2_ncu_plonk_quotient_l2 plonk_quotient_l2 0 1 plonk
