@@ -6,6 +6,7 @@
 // the reference's; the bodies enqueue kernels on the driver's cocg context instead of looping on the CPU.  Share
 // vectors live in HBM between calls; only the MPC network rounds cross PCIe.
 #pragma once
+#include <future>
 #include <map>
 #include <memory>
 
@@ -456,15 +457,31 @@ class Rep3Protocol : public DeviceDriver {
     else if (id() == 1) a.b = ec_add(g, a.b, b);
   }
   void add_assign_points_public_affine(int g, PointShare& a, const Point& b_aff) { add_assign_points_public(g, a, from_affine(g, b_aff)); }
-  PointShare scalar_mul_public_point(int g, const Point& a, const FieldShare& b) { return PointShare{ec_mul(g, a, b.a), ec_mul(g, a, b.b)}; }
+  // The host scalar multiplications of the proof assembly (0.2 ms each) sit on the critical path after the last MSM: independent ones
+  // run on helper threads (cocg_ec_op is pure host arithmetic on its arguments).
+  PointShare scalar_mul_public_point(int g, const Point& a, const FieldShare& b) {
+    auto fb = std::async(std::launch::async, [&] { return ec_mul(g, a, b.b); });
+    Point pa = ec_mul(g, a, b.a);
+    return PointShare{pa, fb.get()};
+  }
   Point masking_ec_element(int g) {  // rngs.rs:48-57; a PRF scalar times the generator instead of C::rand
     if (injected && injected->i_ec < injected->ec_masks.size()) return injected->ec_masks[injected->i_ec++];
     FieldShare r = rand();
     return ec_mul(g, generator(g), fr.sub(r.a, r.b));
   }
   PointShare scalar_mul(int g, const PointShare& a, const FieldShare& b) {  // rep3.rs:835-847, pointshare.rs Mul
-    Point local_a = ec_add(g, ec_mul(g, a.a, fr.add(b.a, b.b)), ec_mul(g, a.b, b.a));
-    local_a = ec_add(g, local_a, masking_ec_element(g));
+    const Point mask_base = generator(g);
+    const bool mask_injected = injected && injected->i_ec < injected->ec_masks.size();
+    Fr mask_scalar = fr.zero();
+    if (!mask_injected) {  // masking_ec_element's PRF draw stays on this thread (the counter is not shared); only the multiplication moves
+      FieldShare rr = rand();
+      mask_scalar = fr.sub(rr.a, rr.b);
+    }
+    auto f1 = std::async(std::launch::async, [&] { return ec_mul(g, a.b, b.a); });
+    auto f2 = std::async(std::launch::async, [&] { return mask_injected ? Point{} : ec_mul(g, mask_base, mask_scalar); });
+    Point local_a = ec_add(g, ec_mul(g, a.a, fr.add(b.a, b.b)), f1.get());
+    const Point mask_computed = f2.get();
+    local_a = ec_add(g, local_a, mask_injected ? masking_ec_element(g) : mask_computed);
     size_t nb = 3 * g * lq * 8;
     net->send_next_bytes(local_a.l, nb);
     PointShare r;
