@@ -80,6 +80,10 @@ class Context:
     def set_stream(self, stream_ptr: int | None):
         self._ck(self.L.cocg_set_stream(self.h, stream_ptr))
 
+    def set_stream_priority(self, high: bool):
+        """Re-creates the context's own stream with the device's highest (or the default) scheduling priority; call while idle."""
+        self._ck(self.L.cocg_set_stream_priority(self.h, 1 if high else 0))
+
     def sync(self):
         self._ck(self.L.cocg_sync(self.h))
 

@@ -137,6 +137,33 @@ def test_ntt_matches_oracle(cocg, bn, bls, curve, logn):
     assert np.array_equal(dd.to_host(), cref.ntt(curve, pre, om) if n > 1 else pre)
 
 
+def test_ntt_many_vectors_on_a_priority_stream(cocg):
+    """The witness map sends a, b, c (two share components each: 6 vectors) through a transform as one launch sequence, and in the
+    multi-GPU block mode it does so on a stream re-created with the highest priority (cocg_set_stream_priority): 9 vectors (more than
+    one batch of 8) at 2^13 (two passes) and 2^9, forward, inverse with the fused coset scaling, against the C oracle."""
+    c = BN254
+    ctx = cocg.Context(cocg.BN254, 0)
+    ctx.set_stream_priority(True)
+    for logn in (13, 9):
+        n = 1 << logn
+        omega, g = ontt.groth16_roots(c, logn)
+        om, omi, gm, one = (cref.fr_to_mont(c, [v]) for v in (omega, pow(omega, -1, c.r), g, 1))
+        hosts = [rand_fr(n, 300 + i) for i in range(9)]
+        dev = [ctx.upload(h) for h in hosts]
+        ctx.ntt(dev, logn, om)
+        for h, d in zip(hosts, dev):
+            assert np.array_equal(d.to_host(), cref.ntt(c, h, om))
+        dev = [ctx.upload(h) for h in hosts]
+        ctx.ntt(dev, logn, om, inverse=True, coset_g=gm)
+        for h, d in zip(hosts, dev):
+            assert np.array_equal(d.to_host(), cref.distribute_powers(c, cref.ntt(c, h, omi, inverse=True), gm, one))
+    ctx.set_stream_priority(False)
+    d = ctx.upload(hosts[0])
+    ctx.ntt([d], 9, om)
+    assert np.array_equal(d.to_host(), cref.ntt(c, hosts[0], om))
+    ctx.close()
+
+
 def test_ntt_small_against_naive_dft(cocg, bn):
     c = BN254
     for logn in (1, 2, 4):
