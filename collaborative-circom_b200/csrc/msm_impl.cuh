@@ -196,22 +196,46 @@ static __global__ void __launch_bounds__(256) bucket_size_hist_kernel(const uint
   for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
-// hist[s] <- number of buckets larger than s (start of size class s in the descending order); one thread, 514 steps
-static __global__ void bucket_size_scan_kernel(uint32_t* hist) {
-  if (threadIdx.x || blockIdx.x) return;
-  uint32_t run = 0;
-  for (int s = kSizeBins - 1; s >= 0; s--) {
-    uint32_t v = hist[s];
-    hist[s] = run;
-    run += v;
+// hist[s] <- number of buckets larger than s (start of size class s in the descending order).  One block: the bins are staged in
+// shared memory and scanned by thread 0 there (a serial walk over global memory was 35 us of load latency per sort).
+static __global__ void __launch_bounds__(256) bucket_size_scan_kernel(uint32_t* hist) {
+  __shared__ uint32_t sh[kSizeBins];
+  for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x) sh[i] = hist[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int s = kSizeBins - 1; s >= 0; s--) {
+      uint32_t v = sh[s];
+      sh[s] = run;
+      run += v;
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x) hist[i] = sh[i];
 }
-static __global__ void __launch_bounds__(256) bucket_order_kernel(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ pos,
-                                                            uint32_t* __restrict__ order) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  uint32_t s = counts[b];
-  order[atomicAdd(&pos[s > (uint32_t)kHeavy ? kHeavy + 1 : s], 1u)] = b;
+// Bucket sizes concentrate on a few dozen values (mean n * nwin / nb), so one global atomic per bucket was ~2^19 atomics on ~40
+// addresses (100 us per sort).  A block counts its buckets per size class in shared memory, reserves one range per class with ONE
+// global atomic, and its threads take consecutive slots of that range.  The order inside a size class is irrelevant (it only decides
+// which thread accumulates which bucket).
+constexpr int kOrderThreads = 1024;
+static __global__ void __launch_bounds__(kOrderThreads) bucket_order_kernel(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ pos,
+                                                                     uint32_t* __restrict__ order) {
+  __shared__ uint32_t sh_cnt[kSizeBins];
+  __shared__ uint32_t sh_base[kSizeBins];
+  for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x) sh_cnt[i] = 0;
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cls = 0, mine = 0;
+  if (b < nb) {
+    const uint32_t s = counts[b];
+    cls = s > (uint32_t)kHeavy ? kHeavy + 1 : s;
+    mine = atomicAdd(&sh_cnt[cls], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSizeBins; i += blockDim.x)
+    if (sh_cnt[i]) sh_base[i] = atomicAdd(&pos[i], sh_cnt[i]);
+  __syncthreads();
+  if (b < nb) order[sh_base[cls] + mine] = b;
 }
 
 // ------------------------------------------------------------------ 3. scatter (counting sort by bucket)
@@ -710,9 +734,9 @@ int msm_sort_impl(cocg_ctx* ctx, const void* scalars, size_t n, int c, int mont,
   COCG_CUDA(ctx, cudaMemsetAsync(shist, 0, kSizeBins * 4, st));
   bucket_size_hist_kernel<<<grid_for(nb, 256, 2), 256, 0, st>>>(counts, nb, shist);
   COCG_LAUNCH_CHECK(ctx);
-  bucket_size_scan_kernel<<<1, 32, 0, st>>>(shist);
+  bucket_size_scan_kernel<<<1, 256, 0, st>>>(shist);
   COCG_LAUNCH_CHECK(ctx);
-  bucket_order_kernel<<<(nb + 255) / 256, 256, 0, st>>>(counts, nb, shist, S.order);
+  bucket_order_kernel<<<(nb + kOrderThreads - 1) / kOrderThreads, kOrderThreads, 0, st>>>(counts, nb, shist, S.order);
   COCG_LAUNCH_CHECK(ctx);
   msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dig, n, nwin, S.start, counts, S.sorted);  // drains counts[] to zero
   COCG_LAUNCH_CHECK(ctx);
