@@ -53,11 +53,12 @@ struct cohost_rep3_session {
   std::unique_ptr<Rep3Protocol> drv[3];
   std::unique_ptr<CoGroth16<Rep3Protocol>> prover[3];
   CoGroth16<Rep3Protocol>::Handles hd[3];
+  CoGroth16<Rep3Protocol>::Handles hd_aux[3];  // the same queries in the parties' aux contexts (single GPU: MSMs overlap the witness map)
   DevVec pub[3];
   std::unique_ptr<DeviceBridge> bridge;  // block mode: cross-GPU leg of the witness maps' mul_vec rounds
   // multi-GPU two-phase state
   int world = 1, rank = 0;
-  std::mutex mu;
+  std::mutex mu, upload_mu;
   std::condition_variable cv;
   int partials_ready = 0;
   bool combined_ready = false;
@@ -306,6 +307,14 @@ static int rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, i
         if (z->zk.plan.wm[i] == rank && want) check(s->drv[i]->ctx, cocg_set_stream_priority(s->drv[i]->ctx, 1), "cocg_set_stream_priority");
       }
       share_handles(s->drv[i]->ctx, z->zk, s->hd[i]);
+      // single GPU, whole queries resident: the four MSMs over the witness run on a second context per party, concurrently with
+      // that party's witness map (COHOST_AUX_MSM=0 keeps everything on one context)
+      const char* ax = getenv("COHOST_AUX_MSM");
+      if (world == 1 && z->zk.world == 1 && !z->zk.blocks && !(ax && std::string(ax) == "0")) {
+        s->drv[i]->enable_aux_ctx(z->device);
+        share_handles(s->drv[i]->aux_ctx, z->zk, s->hd_aux[i]);
+        s->prover[i]->aux_hd = &s->hd_aux[i];
+      }
     }
     cohost_rep3_session* sp = s.get();
     if (world > 1) {
@@ -418,6 +427,9 @@ static int rep3_prove_begin(cohost_rep3_session* s, const void* public_inputs, c
           wit.a = DevVec{const_cast<void*>(wit_a_i), zk.n_aux()};
           wit.b = DevVec{const_cast<void*>(wit_b_i), zk.n_aux()};
         } else {
+          // one party at a time: the three uploads share one PCIe link anyway, and the party that finishes first can start its
+          // witness MSMs (aux context) while the others are still uploading
+          std::lock_guard<std::mutex> up(s->upload_mu);
           if (need[0]) wit.a = d.upload(wit_a_i, zk.n_aux());
           if (need[1]) wit.b = d.upload(wit_b_i, zk.n_aux());
         }
@@ -511,13 +523,16 @@ extern "C" int cohost_rep3_prove_end(cohost_rep3_session* s, void* proofs_out, v
 extern "C" uint64_t cohost_rep3_launch_count(cohost_rep3_session* s) {
   uint64_t t = 0;
   if (s)
-    for (int i = 0; i < 3; i++) t += cocg_launch_count(s->drv[i]->ctx);
+    for (int i = 0; i < 3; i++) t += cocg_launch_count(s->drv[i]->ctx) + (s->drv[i]->aux_ctx ? cocg_launch_count(s->drv[i]->aux_ctx) : 0);
   return t;
 }
 
 extern "C" int cohost_rep3_profile_enable(cohost_rep3_session* s, int on) {
   if (!s) return fail("null session");
-  for (int i = 0; i < 3; i++) cocg_profile_enable(s->drv[i]->ctx, on);
+  for (int i = 0; i < 3; i++) {
+    cocg_profile_enable(s->drv[i]->ctx, on);
+    if (s->drv[i]->aux_ctx) cocg_profile_enable(s->drv[i]->aux_ctx, on);
+  }
   return 0;
 }
 extern "C" int cohost_rep3_profile_read(cohost_rep3_session* s, int cls, double* total_ms, uint64_t* scopes) {
@@ -530,6 +545,11 @@ extern "C" int cohost_rep3_profile_read(cohost_rep3_session* s, int cls, double*
     if (cocg_profile_read(s->drv[i]->ctx, cls, &ms, &k)) return fail(cocg_last_error(s->drv[i]->ctx));
     t += ms;
     n += k;
+    if (s->drv[i]->aux_ctx) {
+      if (cocg_profile_read(s->drv[i]->aux_ctx, cls, &ms, &k)) return fail(cocg_last_error(s->drv[i]->aux_ctx));
+      t += ms;
+      n += k;
+    }
   }
   if (total_ms) *total_ms = t;
   if (scopes) *scopes = n;
@@ -537,7 +557,10 @@ extern "C" int cohost_rep3_profile_read(cohost_rep3_session* s, int cls, double*
 }
 extern "C" int cohost_rep3_profile_reset(cohost_rep3_session* s) {
   if (!s) return fail("null session");
-  for (int i = 0; i < 3; i++) cocg_profile_reset(s->drv[i]->ctx);
+  for (int i = 0; i < 3; i++) {
+    cocg_profile_reset(s->drv[i]->ctx);
+    if (s->drv[i]->aux_ctx) cocg_profile_reset(s->drv[i]->aux_ctx);
+  }
   return 0;
 }
 

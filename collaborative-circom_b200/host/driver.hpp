@@ -56,7 +56,15 @@ class DeviceDriver {
     if (cocg_create(&ctx, device, curve)) throw Error(std::string("cocg_create: ") + cocg_last_error(nullptr));
     lq = curve == COCG_BN254 ? 4 : 6;
   }
+  // A second context on the same device (own stream, own scratch): single-GPU proving runs the four MSMs over the witness on it from
+  // a helper thread while this driver's context computes the witness map (CoGroth16::prove) -- the MSM kernels then fill the bubbles
+  // of the witness map's exchange rounds and, end to end, of its PCIe staging.
+  cocg_ctx* aux_ctx = nullptr;
+  void enable_aux_ctx(int device) {
+    if (!aux_ctx && cocg_create(&aux_ctx, device, fr.curve)) throw Error(std::string("cocg_create (aux): ") + cocg_last_error(nullptr));
+  }
   virtual ~DeviceDriver() {
+    if (aux_ctx) cocg_destroy(aux_ctx);
     if (ctx) {
       for (auto& kv : free_) for (void* p : kv.second) cocg_free(ctx, p);
       for (auto& kv : pinned_free_) for (void* p : kv.second) cocg_host_free(ctx, p);
@@ -221,13 +229,14 @@ class PlainDriver : public DeviceDriver {
   }
   // several queries times the same scalars: one digit sort shared (cocg_msm_multi)
   std::vector<PointShare> msm_public_points_multi(const std::vector<int>& groups, const std::vector<uint64_t>& bases, const std::vector<size_t>& offs,
-                                                  size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
+                                                  size_t n, const FieldShareVec& scalars, size_t scalar_off = 0, cocg_ctx* on = nullptr) {
+    cocg_ctx* c = on ? on : ctx;  // `on`: run on the aux context (the handles in `bases` must be that context's)
     const int nq = (int)bases.size();
     std::vector<PointShare> r(nq);
     std::vector<void*> outs(nq);
     for (int q = 0; q < nq; q++) outs[q] = r[q].a.l;
     const void* sc[1] = {scalars.a.at(scalar_off)};
-    check(ctx, cocg_msm_multi(ctx, bases.data(), offs.data(), nq, n, sc, 1, 1, outs.data()), "cocg_msm_multi");
+    check(c, cocg_msm_multi(c, bases.data(), offs.data(), nq, n, sc, 1, 1, outs.data()), "cocg_msm_multi");
     (void)groups;
     return r;
   }
@@ -419,7 +428,8 @@ class Rep3Protocol : public DeviceDriver {
     return PointShare{out[0], out[1]};
   }
   std::vector<PointShare> msm_public_points_multi(const std::vector<int>& groups, const std::vector<uint64_t>& bases, const std::vector<size_t>& offs,
-                                                  size_t n, const FieldShareVec& scalars, size_t scalar_off = 0) {
+                                                  size_t n, const FieldShareVec& scalars, size_t scalar_off = 0, cocg_ctx* on = nullptr) {
+    cocg_ctx* c = on ? on : ctx;
     const int nq = (int)bases.size();
     std::vector<PointShare> r(nq);
     std::vector<std::vector<uint64_t>> packed(nq);
@@ -429,7 +439,7 @@ class Rep3Protocol : public DeviceDriver {
       outs[q] = packed[q].data();
     }
     const void* sc[2] = {scalars.a.at(scalar_off), scalars.b.at(scalar_off)};
-    check(ctx, cocg_msm_multi(ctx, bases.data(), offs.data(), nq, n, sc, 2, 1, outs.data()), "cocg_msm_multi");
+    check(c, cocg_msm_multi(c, bases.data(), offs.data(), nq, n, sc, 2, 1, outs.data()), "cocg_msm_multi");
     for (int q = 0; q < nq; q++) {
       const size_t nl = 3 * groups[q] * lq;
       memcpy(r[q].a.l, packed[q].data(), nl * 8);

@@ -116,6 +116,10 @@ class CoGroth16 {
   struct Handles {
     uint64_t a_query, b_g1_query, b_g2_query, h_query, l_query, csr_a, csr_b;
   };
+  // Single GPU, whole queries resident: handles of the same queries in driver.aux_ctx.  When set, the four MSMs over the witness
+  // (they do not depend on h) start on the aux context as soon as the witness is resident and run WHILE the witness map is computed.
+  const Handles* aux_hd = nullptr;
+  using AuxMsms = std::future<std::vector<PointShare>>;
 
   // public_inputs: num_inputs = l + 1 elements (leading 1 included) in HBM; witness: n_aux share elements
   Groth16Proof prove(const ZKey& zkey, const Handles& hd, const DevVec& public_inputs, const std::vector<Fr>& public_inputs_host,
@@ -132,6 +136,14 @@ class CoGroth16 {
     last_s = s;
     FieldShare rs = driver.mul(r, s);
     std::future<Precomputed> pre = std::async(std::launch::async, [this, &zkey, r, s, rs, &public_inputs_host] { return precompute(zkey, r, s, rs, public_inputs_host); });
+    AuxMsms aux;
+    if (aux_hd && driver.aux_ctx && !blocks && shard.world == 1 && zkey.world == 1) {
+      const size_t l = zkey.n_public, n_aux = zkey.n_aux();
+      aux = std::async(std::launch::async, [this, l, n_aux, &private_witness] {
+        return driver.msm_public_points_multi({1, 1, 1, 2}, {aux_hd->l_query, aux_hd->a_query, aux_hd->b_g1_query, aux_hd->b_g2_query},
+                                              {0, 1 + l, 1 + l, 1 + l}, n_aux, private_witness, 0, driver.aux_ctx);
+      });
+    }
     FieldShareVec h;
     try {
       if (!blocks || blocks->wm[party_id()] == block_rank) h = witness_map_from_matrices(zkey, hd, public_inputs, private_witness);
@@ -139,10 +151,11 @@ class CoGroth16 {
       check(driver.ctx, cocg_sync(driver.ctx), "cocg_sync");
     } catch (...) {
       pre.wait();
+      if (aux.valid()) aux.wait();
       throw;
     }
     phase_s[0] = now() - t0;
-    Groth16Proof p = create_proof_with_assignment(zkey, hd, r, s, h, public_inputs_host, private_witness, &pre);
+    Groth16Proof p = create_proof_with_assignment(zkey, hd, r, s, h, public_inputs_host, private_witness, &pre, &aux);
     last_h = h;
     return p;
   }
@@ -215,7 +228,7 @@ class CoGroth16 {
 
   Groth16Proof create_proof_with_assignment(const ZKey& zkey, const Handles& hd, const FieldShare& r, const FieldShare& s, const FieldShareVec& h,
                                             const std::vector<Fr>& public_inputs_host, const FieldShareVec& aux_assignment,
-                                            std::future<Precomputed>* pre_async = nullptr) {
+                                            std::future<Precomputed>* pre_async = nullptr, AuxMsms* aux_async = nullptr) {
     const double t_start = now();
     const size_t l = zkey.n_public, n_aux = zkey.n_aux();
     // ---- all secret-scalar MSMs first (msm_public_points at groth16.rs:248, 251-255 and inside calculate_coeff :221-225)
@@ -223,6 +236,18 @@ class CoGroth16 {
     size_t off, len;
     if (blocks) {
       block_msms(zkey, hd, h, aux_assignment, m);
+    } else if (aux_async && aux_async->valid()) {  // the four witness MSMs have been running on the aux context since before the witness map
+      try {
+        m.h_acc = driver.msm_public_points(1, hd.h_query, 0, std::min(h.len(), zkey.domain_size()), h, 0);
+      } catch (...) {
+        aux_async->wait();
+        throw;
+      }
+      std::vector<PointShare> r4 = aux_async->get();
+      m.l_acc = r4[0];
+      m.a_acc = r4[1];
+      m.b1_acc = r4[2];
+      m.b2_acc = r4[3];
     } else {
     if (zkey.world != 1 && (zkey.world != shard.world || zkey.rank != shard.rank)) throw Error("the zkey holds another rank's shard of the queries");
     shard.range(std::min(h.len(), zkey.domain_size()), off, len);

@@ -360,13 +360,14 @@ class ShamirProtocol : public DeviceDriver {
     return r;
   }
   std::vector<PointShare> msm_public_points_multi(const std::vector<int>&, const std::vector<uint64_t>& bases, const std::vector<size_t>& offs, size_t n,
-                                                  const FieldShareVec& scalars, size_t scalar_off = 0) {
+                                                  const FieldShareVec& scalars, size_t scalar_off = 0, cocg_ctx* on = nullptr) {
+    cocg_ctx* c = on ? on : ctx;
     const int nq = (int)bases.size();
     std::vector<PointShare> r(nq);
     std::vector<void*> outs(nq);
     for (int q = 0; q < nq; q++) outs[q] = r[q].a.l;
     const void* sc[1] = {scalars.a.at(scalar_off)};
-    check(ctx, cocg_msm_multi(ctx, bases.data(), offs.data(), nq, n, sc, 1, 1, outs.data()), "cocg_msm_multi");
+    check(c, cocg_msm_multi(c, bases.data(), offs.data(), nq, n, sc, 1, 1, outs.data()), "cocg_msm_multi");
     return r;
   }
   // ---- EcMpcProtocol (:714-806): public points are added by every party
