@@ -286,7 +286,7 @@ def run_own(args):
             return sess.prove(pub, dev_a, dev_b, all_gather=all_gather, device_ptrs=True)
         return sess.prove(pub, host_a, host_b, all_gather=all_gather)
 
-    step_walls = {}
+    step_walls, outliers = {}, {}
 
     def timed(device_resident, steps, sample_clocks=False):
         torch.cuda.synchronize()
@@ -297,11 +297,13 @@ def run_own(args):
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        walls = []
+        walls, step_phases = [], []
         for _ in range(steps):
             tw = time.perf_counter()
             proofs = step(device_resident)
             walls.append((time.perf_counter() - tw) * 1e3)
+            if world > 1:
+                step_phases.append(sess.phase_times() * 1e3)
         e1.record()
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
@@ -310,6 +312,14 @@ def run_own(args):
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         step_walls[device_resident] = [round(float(np.min(walls)), 2), round(float(np.median(walls)), 2), round(float(np.max(walls)), 2), int(np.argmax(walls))]
+        if world > 1:  # a step far above the median: every rank's per-party phase times of THAT step (which rank, which phase stalled)
+            worst = torch.tensor([int(np.argmax(walls)) if np.max(walls) > 1.4 * np.median(walls) else -1], device="cuda")
+            dist.broadcast(worst, 0)
+            w = int(worst.item())
+            rows = [None] * world
+            dist.all_gather_object(rows, None if w < 0 else {"rank": rank, "wall_ms": round(walls[w], 2),
+                                                              "party_phase_ms": [[round(float(x), 2) for x in r] for r in step_phases[w]]})
+            outliers[device_resident] = None if w < 0 else {"step": w, "ranks": rows}
         return float(ms.item()), clocks, proofs
 
     # `value` leg: everything resident in HBM -- witness shares AND the mul_vec payloads the three co-located parties exchange;
@@ -454,7 +464,8 @@ def run_own(args):
                          "in_situ": in_situ, "peak_source": peak_src,
                          "note": "MSM is bound by 32-bit integer multiply-add issue, not HBM (DESIGN.md section 4): see `issue`"},
             "replicas": replicas, "rank_diag": rank_diag,
-            "step_wall_ms_rank0": {"value_leg_min_median_max_argmax": step_walls.get(True), "e2e_leg_min_median_max_argmax": step_walls.get(False)},
+            "step_wall_ms_rank0": {"value_leg_min_median_max_argmax": step_walls.get(True), "e2e_leg_min_median_max_argmax": step_walls.get(False),
+                                   "outlier_value_leg": outliers.get(True), "outlier_e2e_leg": outliers.get(False)},
             "kernels": kernels, "setup_s": round(setup_s, 2),
             "host_phases_ms": {"witness_map": round(float(phases[0]), 2), "msm": round(float(phases[1]), 2),
                                "all_gather_wait": round(float(phases[2]), 2), "assembly": round(float(phases[3]), 2),

@@ -300,8 +300,8 @@ static int rep3_session_create(cohost_zkey* z, const uint8_t* seeds, int rank, i
         s->prover[i]->block_rank = rank;
         // the party whose witness map runs here has the longest dependent chain on this rank (witness map, lock-step with two other
         // GPUs, then its h MSMs): its stream's thread blocks go ahead of the other parties' pending MSM blocks.  Only with three or
-        // more ranks, where a rank runs at most one witness map: with two of them on one GPU (world = 2) the steady state was faster
-        // as well (61 vs 65 ms) but one step in ~20 stalled for ~125 ms, in three runs out of three -- not understood, so not used.
+        // more ranks, where a rank runs at most one witness map.  (world = 2 shows occasional steps whose NCCL exchange round stalls
+        // behind the MSM launches, with or without this priority -- DESIGN.md section 6; the priority is kept off there.)
         const char* pr = getenv("COHOST_WM_PRIORITY");
         const bool want = pr ? std::string(pr) == "1" : world >= 3;
         if (z->zk.plan.wm[i] == rank && want) check(s->drv[i]->ctx, cocg_set_stream_priority(s->drv[i]->ctx, 1), "cocg_set_stream_priority");
